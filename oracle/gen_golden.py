@@ -196,7 +196,7 @@ def scenario_dense_reporting(vm):
     fit_kwargs = dict(K=2, seed=8, max_iter=15, R=R)
     model_kwargs = dict(mutuality=True, convergence_tol=0.0)
     rec = run_reference_trace(gt.X, fit_kwargs, model_kwargs)
-    save_fixture("dense_reporting", gt.X, R, 2, 30, 30, 2, model_kwargs, fit_kwargs, rec)
+    save_fixture("dense_reporting", gt.X, R, 2, 30, 8, 2, model_kwargs, fit_kwargs, rec)
 
 
 def scenario_custom_mask(vm):
@@ -213,7 +213,7 @@ def scenario_custom_mask(vm):
     fit_kwargs = dict(K=2, seed=12, max_iter=15, R=R)
     model_kwargs = dict(mutuality=True, convergence_tol=0.0)
     rec = run_reference_trace(gt.X, fit_kwargs, model_kwargs)
-    save_fixture("custom_mask", gt.X, R, 2, 40, 40, 2, model_kwargs, fit_kwargs, rec)
+    save_fixture("custom_mask", gt.X, R, 2, 40, 10, 2, model_kwargs, fit_kwargs, rec)
 
 
 def scenario_karnataka(vm):
