@@ -1,0 +1,207 @@
+/*
+ * vimure_b200 -- C ABI of the B200-native CAVI hot path of VIMuRe (`VimureModel.fit`).
+ *
+ * The reference (latentnetworks/vimure) is pure Python: it has no FFI/plugin seam, the drop-in
+ * boundary is the Python class `vimure.model.VimureModel` (reference `src/python/vimure/model.py:28-448`).
+ * This header is the LOWER face of that boundary: what the Python host (`vimure_b200/model.py`)
+ * binds with ctypes, and what any other host (R via .C/.Call, C++) would bind instead.
+ * Each entry point names the reference routine(s) it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive cudaError_t, or a negative VM_E* code;
+ *     nothing throws, nothing is allocated or kept by the library: the caller owns every buffer
+ *     (device pointers, normally PyTorch tensors) and passes them in `vm_ctx`;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no host sync;
+ *   - one host thread per GPU/rank; no global state;
+ *   - `vm_ctx` contains only 8-byte fields (int64_t / double / pointers) so that its layout is
+ *     padding-free and trivially mirrored from ctypes; `vm_ctx_size()` lets the host verify it.
+ *
+ * Tie indexing.  A rank owns the node rows [row0, row0+nloc) of every layer (row-block sharding,
+ * SURVEY.md section 8e).  Local row  lrow = l*nloc + (i-row0);  local tie = lrow*N + j;  the dense
+ * posterior slab `rho` is float32 [L][nloc][N][K] (same order as the reference's (L,N,N,K) array).
+ */
+#ifndef VIMURE_B200_H
+#define VIMURE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VM_ABI_VERSION 3
+
+/* reporter-mask structure (how R[l,i,j,m] is represented) */
+#define VM_R_EGO 0 /* reporter m == node m reports row m and column m (vimure synthetic.py:1184-1204, _io.py:229-242) */
+#define VM_R_ALL 1 /* every reporter reports every tie (R == 1, model.py:207-211) */
+#define VM_R_CSR 2 /* general mask: explicit per-tie CSR + per-reporter CSC */
+
+/* flags for vm_phase_rho / vm_phase_finish / vm_iteration */
+#define VM_F_ELBO 1      /* also produce the ELBO (model.py:948-1019) */
+#define VM_F_NO_STORE 2  /* do not write the dense rho slab this iteration (statistics only) */
+#define VM_F_INIT 4      /* vm_phase_finish only: consume the initial statistics, do not update nu */
+
+/* error codes (negative) */
+#define VM_EINVAL (-1)    /* bad argument / unsupported K */
+#define VM_ENOTSUP (-2)   /* combination not implemented */
+
+/* slots of the small fp64 vector `nu` */
+#define VM_NU_SHP 0
+#define VM_NU_RTE 1
+#define VM_NU_G 2       /* exp(psi(nu_shp)-log(nu_rte)) to be used by the NEXT iteration's cache */
+#define VM_NU_E 3       /* nu_shp/nu_rte */
+#define VM_NU_G_STALE 4 /* the G_exp_nu used during the last iteration (what the reference leaves in self.G_exp_nu, Q2) */
+#define VM_NU_LEN 8
+
+/* slots appended after A[L*M*K] in the `red3` statistics vector (the all-reduced payload) */
+#define VM_R3_NU 0   /* sum_I sum_k dz2*rho_new         (model.py:822-825) */
+#define VM_R3_CAT 1  /* categorical ELBO term           (model.py:1306-1313) */
+#define VM_R3_T2 2   /* sum_I x log(EPS + ...)          (model.py:967-995) */
+#define VM_R3_B 3    /* sum_J x^T_J sum_k rho_k         (model.py:1286-1290, the eta part) */
+#define VM_R3_EXTRA 4
+
+/* maximum K compiled in */
+#define VM_MAX_K 8
+
+typedef struct vm_ctx {
+  /* ---- dimensions ---- */
+  int64_t L, N, M, K;
+  int64_t row0, nloc;       /* this rank's node-row block */
+  int64_t r_mode;           /* VM_R_* */
+  int64_t ego_diag;         /* EGO: the mask contains the (m,m) tie of reporter m */
+  int64_t mutuality;        /* model.py:39-65 */
+  int64_t may_dead;         /* 1 = always check closed-form rows for complete underflow (else decided per layer on device) */
+  int64_t U;                /* special ties owned (union of X ties, all diagonal ties) */
+  int64_t I;                /* X entries whose tie is owned */
+  int64_t IT;               /* X entries whose TRANSPOSED tie is owned and reported (ELBO eta term) */
+  int64_t tile_w, tile_h;   /* dense tiling; tile_w must be 1024 */
+  int64_t nct, nrt;         /* ceil(N/tile_w), ceil(nloc/tile_h) */
+  int64_t n_gchunk;         /* reporter chunks (gamma pass) */
+  int64_t phi_chunk;        /* entries per block in the phi pass */
+  int64_t n_phichunk;       /* max over layers of ceil(entries_in_layer/phi_chunk) */
+  int64_t n_ublk;           /* blocks of the special-tie kernel = ceil(U/256) */
+  double eps;               /* EPS, model.py:215-218 */
+  double alpha_eta, beta_eta;
+
+  /* ---- special ties, sorted by (lrow, col) ---- */
+  const int32_t* u_lrow;    /* [U] */
+  const int32_t* u_col;     /* [U] */
+  const int64_t* u_ptr;     /* [U+1] range of entries of the tie */
+  const double* u_logpr;    /* [U*K] log(pr_rho+EPS) (model.py:559) */
+  const int32_t* utile_ptr; /* [L*nloc*nct+1] first special tie of each (lrow, column tile) */
+  const int64_t* ucol_ptr;  /* [L*N+1] EGO: special ties grouped by (l, col) */
+  const int32_t* ucol_perm; /* [U] */
+
+  /* ---- X entries, sorted by tie ---- */
+  const int32_t* e_u;       /* [I] special-tie index */
+  const int32_t* e_m;       /* [I] reporter */
+  const float* e_x;         /* [I] X[l,i,j,m] */
+  const float* e_xT;        /* [I] X[l,j,i,m], pre-paired (replaces data_T_vals, model.py:152-161) */
+  const uint8_t* e_flags;   /* [I] bit0: (l,i,j,m) is in R */
+  const int64_t* lay_eptr;  /* [L+1] entry range of each layer */
+  const int64_t* g_chunk_ptr; /* [n_gchunk+1] ranges in reporter-sorted order */
+  const int32_t* g_chunk_lm;  /* [n_gchunk] reporter id l*M+m */
+  const int32_t* g_perm;      /* [I] entry ids sorted by reporter */
+  const int64_t* g_lm_cptr;   /* [L*M+1] chunk range of each reporter */
+
+  /* ---- transposed-position list (ELBO eta term) ---- */
+  const int32_t* t_u;       /* [IT] special index of the transposed tie, or -1 */
+  const int32_t* t_lrow;    /* [IT] */
+  const int32_t* t_col;     /* [IT] */
+  const float* t_x;         /* [IT] x * multiplicity in R */
+
+  /* ---- reporter mask ---- */
+  const uint8_t* rep;       /* EGO: [L*M] reporter is active */
+  const int64_t* r_ptr;     /* CSR: [L*nloc*N+1] */
+  const int32_t* r_m;       /* CSR: reporter of each mask entry */
+  const float* r_val;       /* CSR: R.vals (used by the rho update only, Q4) */
+  const int64_t* c_ptr;     /* CSC: [L*M+1] */
+  const int64_t* c_tie;     /* CSC: local tie of each mask entry */
+
+  /* ---- priors (model.py:238-317), broadcast to full arrays ---- */
+  const double* alpha_theta; /* [L*M] */
+  const double* beta_theta;  /* [L*M] */
+  const double* alpha_lambda; /* [L*K] */
+  const double* beta_lambda;  /* [L*K] */
+
+  /* ---- variational state (fp64) ---- */
+  double* gamma_shp;        /* [L*M] */
+  double* gamma_rte;        /* [L*M] */
+  double* phi_shp;          /* [L*K] */
+  double* phi_rte;          /* [L*K] */
+  double* nu;               /* [VM_NU_LEN] */
+  double* G_theta;          /* [L*M] exp(psi(shp)-log(rte)) */
+  double* E_theta;          /* [L*M] shp/rte */
+  double* Elog_theta;       /* [L*M] psi(shp)-log(rte) */
+  double* G_lambda;         /* [L*K] */
+  double* E_lambda;         /* [L*K] */
+  double* Elog_lambda;      /* [L*K] */
+  double* A;                /* [L*M*K] sum of rho_k over the ties reported by (l,m) */
+  double* rho_u;            /* [U*K] posterior of the special ties, fp64 */
+  float* rho_u32;           /* [U*K] fp32 copy used to patch the dense slab */
+  double* delta_u;          /* [U*K] rho_u - formula value */
+  float* rho;               /* [L*nloc*N*K] dense posterior slab */
+
+  /* ---- workspaces ---- */
+  double* layer_consts;     /* [L*(2*K+4)] per layer: c_k, d_k (log2 domain), S_all, log-prior consts, dead flag */
+  float* tab_p;             /* [L*nloc*K] row part of the log2-odds */
+  float* tab_q;             /* [L*N*K] column part */
+  float* rowpart;           /* [L*nloc*nct*K] */
+  float* colpart;           /* [L*nrt*N*K] */
+  double* blkpart;          /* [max(n_ublk, nct*L*nrt, L*n_phichunk*K, n_gchunk, ...)*4] */
+  double* red1;             /* [L*M] gamma-shape sums (all-reduced by the host between phases when sharded) */
+  double* red2;             /* [L*K] phi-shape sums */
+  double* red3;             /* [L*M*K + VM_R3_EXTRA] */
+  double* elbo_out;         /* [8]: [0]=ELBO, [1..] its terms */
+} vm_ctx;
+
+/* sizeof(vm_ctx) and ABI version, for the host-side mirror to verify */
+int64_t vm_ctx_size(void);
+int64_t vm_abi_version(void);
+
+/* theta/lambda/nu caches (G_*, E_*, Elog_*) from the current shapes/rates: `_update_cache` (model.py:676-684) and the
+ * cache part of `_initialize_priors` (model.py:596-605). Call once after injecting the initial state. */
+int vm_refresh_cache(const vm_ctx* c, void* stream);
+
+/* Initial statistics from rho = pr_rho (model.py:602): fills delta_u from rho_u, and red3[A] with this
+ * rank's share of A. Follow with (all-reduce red3 and) vm_phase_finish(VM_F_INIT). */
+int vm_init_stats(const vm_ctx* c, void* stream);
+
+/* Phase 1 -- replaces `_update_cache` + `_sp_uttkrp_theta` (model.py:662-696, 832-859):
+ * red1[l,m] = sum over owned X entries of (l,m) of sum_k rho_k * dz1_k. */
+int vm_phase_gamma(const vm_ctx* c, void* stream);
+
+/* Phase 2 -- finishes `_update_gamma` (model.py:698-727) from red1 and A, refreshes the theta cache, then
+ * `_sp_uttkrp_lambda` (model.py:861-887): red2[l,k] = sum over owned X entries of rho_k * dz1_k. */
+int vm_phase_phi(const vm_ctx* c, void* stream);
+
+/* Phase 3 -- finishes `_update_phi` (model.py:729-761) from red2 and A, then `_update_rho` +
+ * `_sp_uttkrp_rho` (model.py:763-818, 889-923) for every owned tie: special ties in fp64, all ties by
+ * the per-tie dense kernel (writes the fp32 slab unless VM_F_NO_STORE), and this rank's share of the
+ * statistics of the NEW rho into red3: A, the nu sum (model.py:820-830) and, with VM_F_ELBO, the ELBO sums. */
+int vm_phase_rho(const vm_ctx* c, int flags, void* stream);
+
+/* Phase 4 -- consumes (all-reduced) red3: A <- red3, `_update_nu` (model.py:820-830), refreshes the nu cache,
+ * and with VM_F_ELBO assembles `__ELBO` (model.py:948-1019) into elbo_out[0]. */
+int vm_phase_finish(const vm_ctx* c, int flags, void* stream);
+
+/* One full `_update_CAVI` (model.py:623-660) on a single rank = the four phases back to back. */
+int vm_iteration(const vm_ctx* c, int flags, void* stream);
+
+/* n_iter iterations back to back; the LAST one runs with `last_flags` (the others with `flags`). */
+int vm_run(const vm_ctx* c, int n_iter, int flags, int last_flags, void* stream);
+
+/* Writes rho = pr_rho into the dense slab (one-hot + special ties), model.py:602. */
+int vm_materialize_prior(const vm_ctx* c, void* stream);
+
+/* Posterior consumers on the dense slab (model.py:1148-1166, utils.py:207-217):
+ * out[t] = argmax_k rho[t,k] (mode 0) or rho[t,1] >= threshold (mode 1), uint8, [L*nloc*N]. */
+int vm_infer(const vm_ctx* c, int mode, double threshold, uint8_t* out, void* stream);
+
+/* Special functions exposed for testing the device implementations against scipy. */
+int vm_test_special(const double* x, double* out_digamma, double* out_lgamma, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIMURE_B200_H */

@@ -1,0 +1,139 @@
+"""CPU-only checks: the C-ABI library loads and exports every declared symbol; packing logic; masks."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden_util import Golden
+
+
+def test_library_exports_every_declared_symbol():
+    from vimure_b200 import _capi, build
+
+    build.build()
+    lib = _capi.load()
+    names = _capi.header_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.vm_ctx_size() == ctypes.sizeof(_capi.ctx_class())
+    assert lib.vm_abi_version() == _capi.consts()["VM_ABI_VERSION"]
+
+
+def test_no_cpu_fallback():
+    import vimure_b200 as vm
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    g = Golden("sbm_k3")
+    X = vm.sptensor.sptensor(tuple(g.X_subs), g.X_vals, shape=(g.L, g.N, g.N, g.M))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        vm.VimureModel().fit(X, K=3, R=vm.masks.EgoMask(g.L, g.N, g.M))
+
+
+@pytest.mark.parametrize("name", ["f1_over", "karnataka_vil1", "custom_mask", "dense_reporting"])
+def test_mask_detection(name):
+    import vimure_b200 as vm
+
+    g = Golden(name)
+    spec = g.R_spec
+    if spec["kind"] == "all":
+        m = vm.masks.from_input(np.ones((g.L, g.N, g.N, g.M)), g.L, g.N, g.M)
+        assert m.kind == "all"
+        return
+    subs, vals = g.R_coo()
+    R = vm.sptensor.sptensor(tuple(subs), vals, shape=(g.L, g.N, g.N, g.M))
+    m = vm.masks.from_input(R, g.L, g.N, g.M)
+    assert m.kind == spec["kind"]
+    if m.kind == "ego":
+        assert m.diag == spec["diag"]
+        assert np.array_equal(m.rep, spec["rep"])
+        # round trip through the explicit form
+        R2 = m.to_sptensor()
+        k1 = np.sort(np.ravel_multi_index(tuple(subs), R.shape))
+        k2 = np.sort(np.ravel_multi_index(R2.subs, R.shape))
+        assert np.array_equal(k1, k2)
+    # membership queries agree with the explicit mask
+    rng = np.random.RandomState(0)
+    q = np.stack([rng.randint(0, g.L, 500), rng.randint(0, g.N, 500), rng.randint(0, g.N, 500), rng.randint(0, g.M, 500)])
+    q[:, :250] = subs[:, rng.randint(0, subs.shape[1], 250)]
+    dense = R.toarray()
+    mult = m.entry_multiplicity(*[torch.as_tensor(a) for a in q]).numpy()
+    assert np.array_equal(mult > 0, dense[tuple(q)] > 0)
+    rep_any = dense.sum(axis=-1) > 0
+    tr = m.tie_reported(*[torch.as_tensor(a) for a in q[:3]]).numpy()
+    assert np.array_equal(tr, rep_any[tuple(q[:3])])
+
+
+@pytest.mark.parametrize("name,world", [("f1_over", 1), ("karnataka_vil1", 1), ("gm_l2_k3", 3), ("custom_mask", 2)])
+def test_packing_invariants(name, world):
+    import vimure_b200 as vm
+    from vimure_b200 import _packing
+    from vimure_b200.model import shard_rows
+
+    g = Golden(name)
+    spec = g.R_spec
+    if spec["kind"] == "ego":
+        mask = vm.masks.EgoMask(g.L, g.N, g.M, rep=spec["rep"], diag=spec["diag"])
+    elif spec["kind"] == "all":
+        mask = vm.masks.AllMask(g.L, g.N, g.M)
+    else:
+        mask = vm.masks.CooMask(spec["subs"], spec["vals"], (g.L, g.N, g.N, g.M))
+    Xd = np.zeros((g.L, g.N, g.N, g.M))
+    Xd[tuple(g.X_subs)] = g.X_vals
+    tot_I, tot_IT = 0, 0
+    for r in range(world):
+        row0, nloc = shard_rows(g.N, world, r)
+        P = _packing.pack(g.X_subs, g.X_vals, g.L, g.N, g.M, g.K, mask, "cpu", row0=row0, nloc=nloc, tile_h=16)
+        t = {k: v.numpy() for k, v in P.t.items()}
+        tot_I += P.I
+        tot_IT += P.IT
+        # every entry: tie, reporter, value and reciprocal are right
+        eu = t["e_u"]
+        lrow, col = t["u_lrow"][eu], t["u_col"][eu]
+        l, i = lrow // nloc, lrow % nloc + row0
+        assert np.array_equal(Xd[l, i, col, t["e_m"]], t["e_x"])
+        assert np.array_equal(Xd[l, col, i, t["e_m"]], t["e_xT"])
+        # CSR by tie is consistent
+        assert t["u_ptr"][0] == 0 and t["u_ptr"][-1] == P.I
+        assert np.all(np.diff(t["u_ptr"]) >= 0)
+        assert np.array_equal(np.repeat(np.arange(P.U), np.diff(t["u_ptr"])), eu)
+        # special ties sorted, tile pointers monotone and complete
+        key = t["u_lrow"].astype(np.int64) * g.N + t["u_col"]
+        assert np.all(np.diff(key) > 0)
+        tp = t["utile_ptr"]
+        assert tp[0] == 0 and tp[-1] == P.U and np.all(np.diff(tp) >= 0)
+        # reporter chunks partition the entries by reporter
+        gp, cp, clm = t["g_perm"], t["g_chunk_ptr"], t["g_chunk_lm"]
+        assert sorted(gp.tolist()) == list(range(P.I))
+        lm_of_entry = l * g.M + t["e_m"]
+        for c in range(P.n_gchunk):
+            assert np.all(lm_of_entry[gp[cp[c]:cp[c + 1]]] == clm[c])
+            assert 0 < cp[c + 1] - cp[c] <= _packing.GAMMA_CHUNK
+        # column grouping
+        cperm, cptr = t["ucol_perm"], t["ucol_ptr"]
+        ck = (t["u_lrow"] // nloc).astype(np.int64) * g.N + t["u_col"]
+        assert np.all(np.diff(ck[cperm]) >= 0) and cptr[-1] == P.U
+    assert tot_I == len(g.X_vals)
+    if g.mutuality:
+        l, i, j, m = g.X_subs
+        mult = mask.entry_multiplicity(*[torch.as_tensor(a) for a in (l, j, i, m)]).numpy()
+        assert tot_IT == int((mult > 0).sum())
+
+
+def test_reference_prior_stream():
+    """`reference_prior_draws` reproduces `prng.rand(L,N,N,K)` (model.py:470) at the requested ties."""
+    from vimure_b200._packing import reference_prior_draws
+
+    L, N, K = 2, 37, 3
+    full = np.random.RandomState(5).rand(L, N, N, K).reshape(-1, K)
+    ties = np.sort(np.random.RandomState(1).choice(L * N * N, 200, replace=False))
+    prng = np.random.RandomState(5)
+    got = reference_prior_draws(prng, L, N, K, ties, chunk=1000)
+    assert np.array_equal(got, full[ties])
+    # the stream continues exactly where the reference's would
+    ref = np.random.RandomState(5)
+    ref.rand(L, N, N, K)
+    assert prng.random_sample() == ref.random_sample()

@@ -1,0 +1,117 @@
+"""ctypes binding of the C ABI declared in include/vimure_b200.h.
+
+There is NO CPU fallback: if the CUDA library is missing this module raises, loudly.
+The `vm_ctx` mirror is generated from the header itself (single source of truth) and its size is checked
+against `vm_ctx_size()` at load time.
+"""
+import ctypes
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(os.path.dirname(HERE), "include", "vimure_b200.h")
+LIB_PATH = os.path.join(HERE, "_lib", "libvimure_b200.so")
+
+_lib = None
+_ctx_cls = None
+_consts = None
+
+
+def _parse_header():
+    src = open(HEADER).read()
+    consts = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+(VM_\w+)\s+\(?(-?\d+)\)?\s", src)}
+    body = re.search(r"typedef struct vm_ctx \{(.*?)\}\s*vm_ctx;", src, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if not decl:
+            continue
+        m = re.match(r"(const\s+)?(\w+)\s*(.*)$", decl)
+        base, rest = m.group(2), m.group(3)
+        for name in rest.split(","):
+            name = name.strip()
+            ptr = name.startswith("*") or base.endswith("*")
+            name = name.lstrip("* ")
+            if ptr:
+                ctype = ctypes.c_void_p
+            elif base == "int64_t":
+                ctype = ctypes.c_int64
+            elif base == "double":
+                ctype = ctypes.c_double
+            else:
+                raise RuntimeError("vm_ctx may only hold int64_t/double/pointers, got %r" % decl)
+            fields.append((name, ctype))
+    return fields, consts
+
+
+def header_symbols():
+    """Names of every function the header declares."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(?:int|int64_t)\s+(vm_\w+)\s*\(", src)))
+
+
+def ctx_class():
+    global _ctx_cls, _consts
+    if _ctx_cls is None:
+        fields, _consts = _parse_header()
+
+        class VmCtx(ctypes.Structure):
+            _fields_ = fields
+
+        _ctx_cls = VmCtx
+    return _ctx_cls
+
+
+def consts():
+    ctx_class()
+    return _consts
+
+
+def load():
+    """Load the CUDA library (building is `__graft_entry__.build()` / `python -m vimure_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "vimure_b200: CUDA library %s is missing -- run `python -m vimure_b200.build` (needs nvcc). "
+            "There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    Ctx = ctx_class()
+    P = ctypes.POINTER(Ctx)
+    vp, i, i64, d = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+    protos = {
+        "vm_ctx_size": (i64, []),
+        "vm_abi_version": (i64, []),
+        "vm_refresh_cache": (i, [P, vp]),
+        "vm_init_stats": (i, [P, vp]),
+        "vm_phase_gamma": (i, [P, vp]),
+        "vm_phase_phi": (i, [P, vp]),
+        "vm_phase_rho": (i, [P, i, vp]),
+        "vm_phase_finish": (i, [P, i, vp]),
+        "vm_iteration": (i, [P, i, vp]),
+        "vm_run": (i, [P, i, i, i, vp]),
+        "vm_materialize_prior": (i, [P, vp]),
+        "vm_infer": (i, [P, i, d, vp, vp]),
+        "vm_test_special": (i, [vp, vp, vp, i64, vp]),
+    }
+    for name, (res, args) in protos.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.vm_ctx_size() != ctypes.sizeof(Ctx):
+        raise RuntimeError("vm_ctx layout mismatch: library %d bytes, python mirror %d bytes (stale build?)"
+                           % (lib.vm_ctx_size(), ctypes.sizeof(Ctx)))
+    if lib.vm_abi_version() != consts()["VM_ABI_VERSION"]:
+        raise RuntimeError("vimure_b200: ABI version mismatch between header and library (stale build?)")
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        if rc > 0:
+            raise RuntimeError("vimure_b200: %s failed with cudaError %d" % (what, rc))
+        raise RuntimeError("vimure_b200: %s failed with error code %d (see include/vimure_b200.h)" % (what, rc))

@@ -1,0 +1,215 @@
+"""Host-side driver of the CUDA CAVI kernels: owns the device buffers (PyTorch tensors = plumbing),
+fills the `vm_ctx` of include/vimure_b200.h and calls the extern "C" launchers.
+
+One engine = one rank's shard (node-row block) of one fit.  With `group` set, the three statistics vectors
+(red1: gamma-shape sums, red2: phi-shape sums, red3: A + nu + ELBO sums) are all-reduced with
+torch.distributed (NCCL over NVLink on the GPU box) between the phases -- the only exchange the path needs
+(SURVEY.md section 8e).  There is no CPU fallback: without CUDA the constructor raises.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi
+
+
+class CaviEngine:
+    def __init__(self, packed, priors, mutuality=True, eps=1e-12, group=None, may_dead=False):
+        P = self.P = packed
+        if not torch.cuda.is_available():
+            raise RuntimeError("vimure_b200 needs a CUDA device: the CAVI kernels have no CPU fallback")
+        self.lib = _capi.load()
+        self.C = _capi.consts()
+        self.group = group
+        L, N, M, K, nloc = P.L, P.N, P.M, P.K, P.nloc
+        if not (2 <= K <= self.C["VM_MAX_K"]):
+            raise ValueError("vimure_b200 supports 2 <= K <= %d (got K=%d)" % (self.C["VM_MAX_K"], K))
+        dev = self.dev = P.t["u_lrow"].device
+        if dev.type != "cuda":
+            raise RuntimeError("packed data must live on a CUDA device")
+        self.mutuality = bool(mutuality)
+        f64 = dict(dtype=torch.float64, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        def bcast(v, shape):
+            return torch.as_tensor(np.broadcast_to(np.asarray(v, dtype=np.float64), shape).copy(), **f64).contiguous()
+
+        self.alpha_theta = bcast(priors["alpha_theta"], (L, M))
+        self.beta_theta = bcast(priors["beta_theta"], (L, M))
+        self.alpha_lambda = bcast(priors["alpha_lambda"], (L, K))
+        self.beta_lambda = bcast(priors["beta_lambda"], (L, K))
+        self.alpha_eta, self.beta_eta = float(priors["alpha_eta"]), float(priors["beta_eta"])
+
+        z = lambda *s: torch.zeros(*s, **f64)  # noqa: E731
+        self.gamma_shp, self.gamma_rte = z(L, M), z(L, M)
+        self.phi_shp, self.phi_rte = z(L, K), z(L, K)
+        self.nu = z(self.C["VM_NU_LEN"])
+        self.G_theta, self.E_theta, self.Elog_theta = z(L, M), z(L, M), z(L, M)
+        self.G_lambda, self.E_lambda, self.Elog_lambda = z(L, K), z(L, K), z(L, K)
+        U = P.U
+        self.u_logpr = z(max(U, 1), K)
+        self.rho_u = z(max(U, 1), K)
+        self.rho_u32 = torch.zeros(max(U, 1), K, **f32)
+        self.delta_u = z(max(U, 1), K)
+        self.rho = torch.empty(L, nloc, N, K, **f32)
+        self.rho_valid = False
+        # workspaces
+        self.layer_consts = z(L * (2 * K + 4))
+        self.tab_p = torch.zeros(L * nloc * K, **f32)
+        self.tab_q = torch.zeros(L * N * K, **f32)
+        self.rowpart = torch.zeros(L * nloc * P.nct * K, **f32)
+        self.colpart = torch.zeros(L * P.nrt * N * K, **f32)
+        n_blk = max(P.n_gchunk, L * P.n_phichunk * K,
+                    L * P.n_ublk * (4 + self.C["VM_MAX_K"]) + P.nct * L * P.nrt + 128 + 2 * 64) + 64
+        self.blkpart = z(n_blk)
+        self.red1, self.red2 = z(L * M), z(L * K)
+        self.red3 = z(L * M * K + self.C["VM_R3_EXTRA"])
+        self.elbo_out = z(8)
+        self._dummy = torch.zeros(8, dtype=torch.int64, device=dev)
+
+        Ctx = _capi.ctx_class()
+        c = self.ctx = Ctx()
+        for name in ("L", "N", "M", "K", "row0", "nloc", "U", "I", "IT", "tile_w", "tile_h", "nct", "nrt", "n_gchunk",
+                     "phi_chunk", "n_phichunk", "n_ublk", "r_mode", "ego_diag"):
+            setattr(c, name, int(getattr(P, name)))
+        c.mutuality = int(self.mutuality)
+        c.may_dead = int(bool(may_dead))
+        c.eps = float(eps)
+        c.alpha_eta, c.beta_eta = self.alpha_eta, self.beta_eta
+        self._keep = []
+
+        def ptr(t):
+            self._keep.append(t)
+            return t.data_ptr() if t.numel() else self._dummy.data_ptr()
+
+        for name in ("u_lrow", "u_col", "u_ptr", "utile_ptr", "ucol_ptr", "ucol_perm", "e_u", "e_m", "e_x", "e_xT",
+                     "e_flags", "lay_eptr", "g_chunk_ptr", "g_chunk_lm", "g_perm", "g_lm_cptr", "t_u", "t_lrow",
+                     "t_col", "t_x", "rep", "r_ptr", "r_m", "r_val", "c_ptr", "c_tie"):
+            setattr(c, name, ptr(P.t[name]) if name in P.t else self._dummy.data_ptr())
+        for name in ("u_logpr", "alpha_theta", "beta_theta", "alpha_lambda", "beta_lambda", "gamma_shp", "gamma_rte",
+                     "phi_shp", "phi_rte", "nu", "G_theta", "E_theta", "Elog_theta", "G_lambda", "E_lambda",
+                     "Elog_lambda", "rho_u", "rho_u32", "delta_u", "rho", "layer_consts", "tab_p", "tab_q", "rowpart",
+                     "colpart", "blkpart", "red1", "red2", "red3", "elbo_out"):
+            setattr(c, name, ptr(getattr(self, name)))
+        c.A = self.red3.data_ptr()  # A aliases the (all-reduced) statistics vector
+        self._cref = ctypes.byref(c)
+        self.n_launch = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _allreduce(self, t):
+        if self.group is not None:
+            torch.distributed.all_reduce(t, group=self.group if self.group is not True else None)
+
+    def kernels_per_iteration(self, elbo=False):
+        """Number of kernels of this library launched by one iteration (for bench.py's gpu_launches)."""
+        n = 2 + 3 + 1 + (0 if self.P.r_mode == 2 else 1) + 3 + 1 + 1  # gamma(2) phi(3) rho: phi_finish,tables,special,dense,stats,sums ; finish
+        if elbo:
+            n += 1 + (1 if self.mutuality else 0)
+        return n
+
+    # ------------------------------------------------------------------ state
+    def set_state(self, gamma_shp, gamma_rte, phi_shp, phi_rte, nu_shp, nu_rte, pr_u, eps):
+        """Inject the initial variational state (what `_initialize_priors`, model.py:561-605, draws) and the prior of
+        the special ties; computes the caches and the initial statistics A from rho = pr_rho."""
+        P = self.P
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        self.gamma_shp.copy_(torch.as_tensor(np.asarray(gamma_shp, dtype=np.float64), **f64).reshape(P.L, P.M))
+        self.gamma_rte.copy_(torch.as_tensor(np.asarray(gamma_rte, dtype=np.float64), **f64).reshape(P.L, P.M))
+        self.phi_shp.copy_(torch.as_tensor(np.asarray(phi_shp, dtype=np.float64), **f64).reshape(P.L, P.K))
+        self.phi_rte.copy_(torch.as_tensor(np.asarray(phi_rte, dtype=np.float64), **f64).reshape(P.L, P.K))
+        nu = np.zeros(self.C["VM_NU_LEN"])
+        nu[self.C["VM_NU_SHP"]], nu[self.C["VM_NU_RTE"]] = float(nu_shp), float(nu_rte)
+        self.nu.copy_(torch.as_tensor(nu, **f64))
+        if P.U:
+            pr = torch.as_tensor(pr_u, **f64).reshape(P.U, P.K)
+            self.rho_u.copy_(pr)
+            self.u_logpr.copy_(torch.log(pr + float(eps)))
+        st = self._stream()
+        _capi.check(self.lib.vm_refresh_cache(self._cref, st), "vm_refresh_cache")
+        _capi.check(self.lib.vm_init_stats(self._cref, st), "vm_init_stats")
+        self._allreduce(self.red3)
+        _capi.check(self.lib.vm_phase_finish(self._cref, self.C["VM_F_INIT"], st), "vm_phase_finish")
+        self.rho_valid = False
+        self.rho_is_prior = True
+
+    # ------------------------------------------------------------------ iterations
+    def iterate(self, n=1, elbo_last=False, store=True, store_last=True):
+        """Run n CAVI iterations; the last one also evaluates the ELBO if `elbo_last`.
+        Returns nothing; read `elbo()` after an ELBO iteration (one D2H scalar)."""
+        if n <= 0:
+            return
+        F = self.C
+        base = 0 if store else F["VM_F_NO_STORE"]
+        last = (0 if (store or store_last) else F["VM_F_NO_STORE"]) | (F["VM_F_ELBO"] if elbo_last else 0)
+        st = self._stream()
+        if self.group is None:
+            _capi.check(self.lib.vm_run(self._cref, int(n), base, last, st), "vm_run")
+        else:
+            for it in range(n):
+                fl = last if it == n - 1 else base
+                _capi.check(self.lib.vm_phase_gamma(self._cref, st), "vm_phase_gamma")
+                self._allreduce(self.red1)
+                _capi.check(self.lib.vm_phase_phi(self._cref, st), "vm_phase_phi")
+                self._allreduce(self.red2)
+                _capi.check(self.lib.vm_phase_rho(self._cref, fl, st), "vm_phase_rho")
+                self._allreduce(self.red3)
+                _capi.check(self.lib.vm_phase_finish(self._cref, fl, st), "vm_phase_finish")
+        self.n_launch += (n - 1) * self.kernels_per_iteration(False) + self.kernels_per_iteration(elbo_last)
+        self.rho_valid = bool(store or store_last)
+        self.rho_is_prior = False
+
+    # single phases, for tests that emulate several ranks on one GPU
+    def phase(self, name, flags=0):
+        st = self._stream()
+        fn = getattr(self.lib, "vm_phase_" + name)
+        if name in ("rho", "finish"):
+            _capi.check(fn(self._cref, int(flags), st), "vm_phase_" + name)
+        else:
+            _capi.check(fn(self._cref, st), "vm_phase_" + name)
+        if name == "rho":
+            self.rho_valid = not (flags & self.C["VM_F_NO_STORE"])
+            self.rho_is_prior = False
+
+    def elbo(self):
+        return float(self.elbo_out[0].item())
+
+    def elbo_terms(self):
+        return self.elbo_out.cpu().numpy()
+
+    # ------------------------------------------------------------------ results
+    def params(self):
+        """Small posterior parameters as numpy (one D2H each; a few KB .. MB)."""
+        C = self.C
+        nu = self.nu.cpu().numpy()
+        return dict(
+            gamma_shp=self.gamma_shp.cpu().numpy().copy(), gamma_rte=self.gamma_rte.cpu().numpy().copy(),
+            phi_shp=self.phi_shp.cpu().numpy().copy(), phi_rte=self.phi_rte.cpu().numpy().copy(),
+            nu_shp=np.float64(nu[C["VM_NU_SHP"]]), nu_rte=np.float64(nu[C["VM_NU_RTE"]]),
+            G_exp_theta=self.G_theta.cpu().numpy().copy(), G_exp_lambda=self.G_lambda.cpu().numpy().copy(),
+            G_exp_nu=np.float64(nu[C["VM_NU_G_STALE"]]),
+        )
+
+    def rho_slab(self):
+        """The dense posterior slab of this rank, float32 (L, nloc, N, K), on the device."""
+        if not self.rho_valid:
+            if getattr(self, "rho_is_prior", False):
+                _capi.check(self.lib.vm_materialize_prior(self._cref, self._stream()), "vm_materialize_prior")
+                self.n_launch += 2
+                self.rho_valid = True
+            else:
+                raise RuntimeError("the dense rho slab was not stored in the last iteration (store=False)")
+        return self.rho
+
+    def infer(self, mode=0, threshold=0.5):
+        """argmax_k rho (mode 0) or rho[...,1] >= threshold (mode 1) on the device: uint8 (L, nloc, N)."""
+        self.rho_slab()
+        P = self.P
+        out = torch.empty(P.L, P.nloc, P.N, dtype=torch.uint8, device=self.dev)
+        _capi.check(self.lib.vm_infer(self._cref, int(mode), float(threshold), ctypes.c_void_p(out.data_ptr()),
+                                      self._stream()), "vm_infer")
+        self.n_launch += 1
+        return out

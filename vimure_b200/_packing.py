@@ -1,0 +1,215 @@
+"""Data packing: the sptensor X and the reporter mask R -> the tie-sorted device layout the kernels read.
+
+Replaces, for the hot path, the reference's `__check_fit_params` data preparation (`model.py:147-176`):
+`data_T` / `data_T_vals` (an O(nnz^2) python lookup, `utils.py:73-84`) become one sort + searchsorted that
+pre-pairs every report X[l,i,j,m] with its reciprocal X[l,j,i,m]; the union-of-ties DataFrame merges of
+`_set_rho_prior` (`model.py:509-556`) become a `unique` over the tie keys.
+
+Everything here is index plumbing done with torch ops on whatever device it is given (the GPU in
+production, the CPU in the `-m "not gpu"` tests); the arithmetic of the model lives in `csrc/`.
+
+Layout (see include/vimure_b200.h): this rank owns node rows [row0, row0+nloc) of every layer;
+`special ties` = owned ties that carry at least one X entry, plus (ego mask) every owned diagonal tie.
+"""
+import numpy as np
+import torch
+
+TILE_W = 1024
+GAMMA_CHUNK = 256
+PHI_CHUNK = 4096
+
+
+def _i32(t):
+    return t.to(torch.int32).contiguous()
+
+
+class Packed:
+    """Plain container of the packed tensors + dimensions."""
+
+    def __init__(self):
+        self.t = {}
+
+    def __getattr__(self, k):
+        t = self.__dict__.get("t", {})
+        if k in t:
+            return t[k]
+        raise AttributeError(k)
+
+
+def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64):
+    """Build the packed layout.
+
+    X_subs : (4, I) integer array-like (l, i, j, m);  X_vals : (I,) counts;  mask : masks.ReporterMask.
+    """
+    dev = torch.device(device)
+    nloc = N - row0 if nloc is None else int(nloc)
+    P = Packed()
+    P.L, P.N, P.M, P.K, P.row0, P.nloc = int(L), int(N), int(M), int(K), int(row0), nloc
+    P.tile_w, P.tile_h = TILE_W, int(tile_h)
+    P.nct = (N + TILE_W - 1) // TILE_W
+    P.nrt = (nloc + P.tile_h - 1) // P.tile_h
+    P.mask = mask
+
+    subs = torch.as_tensor(np.ascontiguousarray(np.asarray(X_subs)), device=dev).to(torch.int64)
+    xl, xi, xj, xm = subs[0], subs[1], subs[2], subs[3]
+    xv = torch.as_tensor(np.ascontiguousarray(np.asarray(X_vals)), device=dev).to(torch.float64)
+    I_all = xv.numel()
+    if I_all:
+        if int(xl.max()) >= L or int(max(xi.max(), xj.max())) >= N or int(xm.max()) >= M or int(subs.min()) < 0:
+            raise ValueError("X has subscripts outside its shape")
+
+    # ---- reciprocal pairing: xT[I] = X[l, j, i, m]   (model.py:152-161)
+    key = ((xl * N + xi) * N + xj) * M + xm
+    skey, order = torch.sort(key)
+    if I_all > 1 and bool((skey[1:] == skey[:-1]).any()):
+        raise ValueError("Duplicate entries without specified accumulation function")
+    keyT = ((xl * N + xj) * N + xi) * M + xm
+    if I_all:
+        pos = torch.searchsorted(skey, keyT).clamp(max=I_all - 1)
+        found = skey[pos] == keyT
+        xT = torch.where(found, xv[order][pos], torch.zeros_like(xv))
+    else:
+        xT = xv.clone()
+    P.sumX = float(xv.sum()) if I_all else 0.0
+
+    in_R = mask.entry_multiplicity(xl, xi, xj, xm) if I_all else xv.clone()
+    in_RT = mask.entry_multiplicity(xl, xj, xi, xm) if I_all else xv.clone()
+
+    # ---- ownership and tie-sorted order of the owned entries
+    own = (xi >= row0) & (xi < row0 + nloc)
+    sel = torch.nonzero(own).flatten()
+    tk = (xl[sel] * nloc + (xi[sel] - row0)) * N + xj[sel]  # local tie id
+    tk_sorted, o2 = torch.sort(tk, stable=True)
+    sel = sel[o2]
+    I = sel.numel()
+    P.I = int(I)
+    P.entry_src = sel  # position of each packed entry in the caller's COO order
+
+    # ---- special ties
+    ukeys = torch.unique_consecutive(tk_sorted)
+    if mask.kind == "ego":
+        ii = torch.arange(row0, row0 + nloc, device=dev, dtype=torch.int64)
+        ll = torch.arange(L, device=dev, dtype=torch.int64)
+        dk = ((ll[:, None] * nloc + (ii[None, :] - row0)) * N + ii[None, :]).flatten()
+        ukeys = torch.unique(torch.cat([ukeys, dk]))
+    U = ukeys.numel()
+    P.U = int(U)
+    if U >= 2**31 or I >= 2**31:
+        raise ValueError("too many special ties / entries for one rank (int32 indices)")
+    u_lrow = ukeys // N
+    u_col = ukeys - u_lrow * N
+    P.t["u_lrow"] = _i32(u_lrow)
+    P.t["u_col"] = _i32(u_col)
+    P.t["u_key"] = ukeys
+    e_u = torch.searchsorted(ukeys, tk_sorted)
+    P.t["e_u"] = _i32(e_u)
+    u_ptr = torch.searchsorted(tk_sorted, torch.cat([ukeys, ukeys.new_tensor([L * nloc * N])]))
+    P.t["u_ptr"] = u_ptr.to(torch.int64).contiguous()
+    P.t["e_m"] = _i32(xm[sel])
+    P.t["e_x"] = xv[sel].to(torch.float32).contiguous()
+    P.t["e_xT"] = xT[sel].to(torch.float32).contiguous()
+    P.t["e_flags"] = (in_R[sel] > 0).to(torch.uint8).contiguous()
+    # has this special tie any X entry / is it reported by anybody (model.py:536-556)
+    u_l = u_lrow // nloc
+    u_i = u_lrow - u_l * nloc + row0
+    P.t["u_has_x"] = (u_ptr[1:] > u_ptr[:-1])
+    P.t["u_reported"] = mask.tie_reported(u_l, u_i, u_col) if U else torch.zeros(0, dtype=torch.bool, device=dev)
+    P.t["u_gflat"] = (u_l * N + u_i) * N + u_col  # global flat tie id (l,i,j) -> position in the reference's arrays
+
+    # dense-tile pointers: first special tie of every (local row, column tile)
+    rows = torch.arange(L * nloc, device=dev, dtype=torch.int64)
+    bounds = (rows[:, None] * N + torch.arange(P.nct, device=dev, dtype=torch.int64)[None, :] * TILE_W).flatten()
+    bounds = torch.cat([bounds, bounds.new_tensor([L * nloc * N])])
+    P.t["utile_ptr"] = _i32(torch.searchsorted(ukeys, bounds))
+    # special ties grouped by (layer, column)   [ego statistics]
+    ck = u_l * N + u_col
+    ck_sorted, cperm = torch.sort(ck, stable=True)
+    P.t["ucol_perm"] = _i32(cperm)
+    P.t["ucol_ptr"] = torch.searchsorted(ck_sorted, torch.arange(L * N + 1, device=dev, dtype=torch.int64)).contiguous()
+    n_ul = (P.t["utile_ptr"][:: nloc * P.nct][1:] - P.t["utile_ptr"][:: nloc * P.nct][:-1]) if U else None
+    max_ul = int(n_ul.max()) if U else 0
+    P.n_ublk = max(1, (max_ul + 255) // 256)
+
+    # ---- layer ranges and reporter chunks of the entries
+    lay_eptr = torch.searchsorted(tk_sorted, torch.arange(L + 1, device=dev, dtype=torch.int64) * (nloc * N))
+    P.t["lay_eptr"] = lay_eptr.contiguous()
+    n_lay = lay_eptr[1:] - lay_eptr[:-1]
+    P.phi_chunk = PHI_CHUNK
+    P.n_phichunk = max(1, int((int(n_lay.max()) + PHI_CHUNK - 1) // PHI_CHUNK)) if L else 1
+    e_l = tk_sorted // (nloc * N)
+    lm = e_l * M + xm[sel]
+    lm_sorted, gperm = torch.sort(lm, stable=True)
+    P.t["g_perm"] = _i32(gperm)
+    cnt = torch.bincount(lm, minlength=L * M) if I else torch.zeros(L * M, dtype=torch.int64, device=dev)
+    nch = (cnt + GAMMA_CHUNK - 1) // GAMMA_CHUNK
+    cptr = torch.cat([nch.new_zeros(1), torch.cumsum(nch, 0)])
+    P.t["g_lm_cptr"] = cptr.contiguous()
+    n_gchunk = int(cptr[-1])
+    P.n_gchunk = n_gchunk
+    chunk_lm = torch.repeat_interleave(torch.arange(L * M, device=dev, dtype=torch.int64), nch)
+    estart = torch.cat([cnt.new_zeros(1), torch.cumsum(cnt, 0)])
+    within = torch.arange(n_gchunk, device=dev, dtype=torch.int64) - cptr[chunk_lm]
+    cstart = estart[chunk_lm] + within * GAMMA_CHUNK
+    P.t["g_chunk_lm"] = _i32(chunk_lm)
+    P.t["g_chunk_ptr"] = torch.cat([cstart, cstart.new_tensor([I])]).contiguous()
+
+    # ---- transposed-position list for the eta part of the ELBO (model.py:1269-1290): the X entry (l,i,j,m)
+    # is the "X_T" value of the mask entry (l,j,i,m); it belongs to the rank that owns row j
+    ownT = (xj >= row0) & (xj < row0 + nloc) & (in_RT > 0)
+    st = torch.nonzero(ownT).flatten()
+    t_lrow = xl[st] * nloc + (xj[st] - row0)
+    t_col = xi[st]
+    tkey = t_lrow * N + t_col
+    if U and st.numel():
+        pos = torch.searchsorted(ukeys, tkey).clamp(max=U - 1)
+        t_u = torch.where(ukeys[pos] == tkey, pos, torch.full_like(pos, -1))
+    else:
+        t_u = torch.full_like(tkey, -1)
+    P.IT = int(st.numel())
+    P.t["t_u"] = _i32(t_u)
+    P.t["t_lrow"] = _i32(t_lrow)
+    P.t["t_col"] = _i32(t_col)
+    P.t["t_x"] = (xv[st] * in_RT[st]).to(torch.float32).contiguous()
+
+    # ---- reporter mask
+    P.r_mode = {"ego": 0, "all": 1, "coo": 2}[mask.kind]
+    P.ego_diag = int(getattr(mask, "diag", False))
+    if mask.kind == "ego":
+        P.t["rep"] = torch.as_tensor(mask.rep, device=dev).to(torch.uint8).flatten().contiguous()
+    elif mask.kind == "coo":
+        rs = torch.as_tensor(mask.subs, device=dev)
+        rv = torch.as_tensor(mask.vals, device=dev)
+        rown = (rs[1] >= row0) & (rs[1] < row0 + nloc)
+        rsel = torch.nonzero(rown).flatten()
+        rtie = (rs[0][rsel] * nloc + (rs[1][rsel] - row0)) * N + rs[2][rsel]
+        rtie_s, ro = torch.sort(rtie, stable=True)
+        rsel = rsel[ro]
+        T = L * nloc * N
+        P.t["r_ptr"] = torch.searchsorted(rtie_s, torch.arange(T + 1, device=dev, dtype=torch.int64)).contiguous()
+        P.t["r_m"] = _i32(rs[3][rsel])
+        P.t["r_val"] = rv[rsel].to(torch.float32).contiguous()
+        rlm = rs[0][rsel] * M + rs[3][rsel]
+        rlm_s, co = torch.sort(rlm, stable=True)
+        P.t["c_ptr"] = torch.searchsorted(rlm_s, torch.arange(L * M + 1, device=dev, dtype=torch.int64)).contiguous()
+        P.t["c_tie"] = rtie_s[co].contiguous()
+    return P
+
+
+def reference_prior_draws(prng, L, N, K, flat_ties_sorted, chunk=1 << 22):
+    """The reference draws `prng.rand(L, N, N, K)` (model.py:470) and then keeps the result only on the ties
+    that carry an X and an R entry.  Reproduce the stream: consume L*N*N*K doubles in chunks, keeping the K
+    values of the requested ties (`flat_ties_sorted` = sorted flat (l,i,j) ids).  Returns (n, K) float64."""
+    flat = np.asarray(flat_ties_sorted, dtype=np.int64)
+    out = np.empty((flat.size, K), dtype=np.float64)
+    T = L * N * N
+    per = max(1, chunk // K)
+    t0 = 0
+    while t0 < T:
+        t1 = min(T, t0 + per)
+        block = prng.random_sample((t1 - t0) * K)
+        a, b = np.searchsorted(flat, t0), np.searchsorted(flat, t1)
+        if b > a:
+            idx = (flat[a:b] - t0)[:, None] * K + np.arange(K)[None, :]
+            out[a:b] = block[idx]
+        t0 = t1
+    return out

@@ -1,0 +1,1048 @@
+// vimure_b200 -- hand-written sm_100a kernels of the CAVI hot path + the extern "C" launcher layer.
+//
+// What runs where (one CAVI iteration = reference `_update_CAVI`, model.py:623-660):
+//   phase gamma : k_gamma_partial -> k_gamma_reduce                       (red1)
+//   phase phi   : k_gamma_finish -> k_phi_partial -> k_phi_reduce         (red2)
+//   phase rho   : k_phi_finish -> k_tables -> k_special<K> -> k_dense<K>  (the HBM-bound per-tie kernel)
+//                 -> k_stats_* -> k_sums_reduce                            (red3)
+//   phase finish: k_elbo_partial -> k_finish
+// All reductions are two-pass (block partials, then a fixed-order second pass): results are bit-reproducible
+// run to run. No atomics anywhere.
+#include <stdio.h>
+
+#include "vm_common.cuh"
+
+#define VM_CHECK_LAUNCH()                        \
+  do {                                           \
+    cudaError_t e__ = cudaGetLastError();        \
+    if (e__ != cudaSuccess) return (int)e__;     \
+  } while (0)
+
+#define UPART_STRIDE (4 + VM_MAX_K)  // per block of k_special: nu, cat, t2, spare, delta sums[K]
+
+// =====================================================================================================
+// phase gamma
+// =====================================================================================================
+// One warp per reporter chunk (<= 256 entries of one reporter (l,m)): sum_k rho_k * dz1_k per entry.
+// Replaces `_sp_uttkrp_theta` (model.py:851-859) whose python loop is 65% of the reference's CAVI time.
+template <int K>
+__global__ void __launch_bounds__(256) k_gamma_partial(const __grid_constant__ vm_ctx c, double* part) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t chunk = (int64_t)blockIdx.x * 8 + warp;
+  if (chunk >= c.n_gchunk) return;
+  const int lm = c.g_chunk_lm[chunk];
+  const int l = lm / (int)c.M;
+  const bool mut = c.mutuality != 0;
+  const double Gth = c.G_theta[lm];
+  const double Gnu = c.nu[VM_NU_G];
+  double Gl[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) Gl[k] = c.G_lambda[l * K + k];
+  double acc = 0.0;
+  const int64_t p1 = c.g_chunk_ptr[chunk + 1];
+  for (int64_t p = c.g_chunk_ptr[chunk] + lane; p < p1; p += 32) {
+    const int e = c.g_perm[p];
+    const int64_t u = c.e_u[e];
+    double dz1[K], dz2[K];
+    vm_alloc<K>(mut, (double)c.e_x[e], (double)c.e_xT[e], Gth, Gl, Gnu, dz1, dz2);
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc += c.rho_u[u * K + k] * dz1[k];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) part[chunk] = acc;
+}
+
+__global__ void k_gamma_reduce(const __grid_constant__ vm_ctx c, const double* part) {
+  const int64_t lm = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lm >= c.L * c.M) return;
+  double s = 0.0;
+  for (int64_t q = c.g_lm_cptr[lm]; q < c.g_lm_cptr[lm + 1]; ++q) s += part[q];
+  c.red1[lm] = s;
+}
+
+// =====================================================================================================
+// phase phi
+// =====================================================================================================
+// `_update_gamma` (model.py:698-718) from the (all-reduced) shape sums and A, then the theta part of
+// `_update_cache` (model.py:676).  gamma_rte[l,m] = beta + sum_k A[l,m,k] E[lambda_lk].
+template <int K>
+__global__ void k_gamma_finish(const __grid_constant__ vm_ctx c) {
+  const int64_t lm = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lm >= c.L * c.M) return;
+  const int l = (int)(lm / c.M);
+  const double shp = c.alpha_theta[lm] + c.red1[lm];
+  double r = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) r += c.A[lm * K + k] * c.E_lambda[l * K + k];
+  const double rte = c.beta_theta[lm] + r;
+  c.gamma_shp[lm] = shp;
+  c.gamma_rte[lm] = rte;
+  const double el = vm_digamma(shp) - log(rte);
+  c.Elog_theta[lm] = el;
+  c.G_theta[lm] = exp(el);
+  c.E_theta[lm] = shp / rte;
+}
+
+// `_sp_uttkrp_lambda` (model.py:880-887): per-layer sums of rho_k*dz1_k over the X entries (new theta cache).
+template <int K>
+__global__ void __launch_bounds__(256) k_phi_partial(const __grid_constant__ vm_ctx c, double* part) {
+  __shared__ double sm[8];
+  const int l = blockIdx.y;
+  const int64_t s0 = c.lay_eptr[l] + (int64_t)blockIdx.x * c.phi_chunk;
+  const int64_t s1 = min(s0 + c.phi_chunk, c.lay_eptr[l + 1]);
+  const bool mut = c.mutuality != 0;
+  const double Gnu = c.nu[VM_NU_G];
+  double Gl[K], acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    Gl[k] = c.G_lambda[l * K + k];
+    acc[k] = 0.0;
+  }
+  for (int64_t e = s0 + threadIdx.x; e < s1; e += 256) {
+    const int64_t u = c.e_u[e];
+    const double Gth = c.G_theta[(int64_t)l * c.M + c.e_m[e]];
+    double dz1[K], dz2[K];
+    vm_alloc<K>(mut, (double)c.e_x[e], (double)c.e_xT[e], Gth, Gl, Gnu, dz1, dz2);
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] += c.rho_u[u * K + k] * dz1[k];
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double v = block_sum<256>(acc[k], sm);
+    if (threadIdx.x == 0) part[((int64_t)l * c.n_phichunk + blockIdx.x) * K + k] = v;
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) k_phi_reduce(const __grid_constant__ vm_ctx c, const double* part) {
+  __shared__ double sm[8];
+  const int l = blockIdx.x;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double v = 0.0;
+    for (int64_t q = threadIdx.x; q < c.n_phichunk; q += 256) v += part[((int64_t)l * c.n_phichunk + q) * K + k];
+    v = block_sum<256>(v, sm);
+    if (threadIdx.x == 0) c.red2[l * K + k] = v;
+  }
+}
+
+// =====================================================================================================
+// phase rho
+// =====================================================================================================
+// `_update_phi` (model.py:729-749): phi_rte[l,k] = beta + sum_m E[theta_lm](new) A[l,m,k]; lambda part of the cache;
+// then the per-layer constants of the closed-form tie posterior.
+template <int K>
+__global__ void __launch_bounds__(256) k_phi_finish(const __grid_constant__ vm_ctx c) {
+  __shared__ double sm[8];
+  __shared__ double rte_s[K + 1];
+  const int l = blockIdx.x;
+  const int64_t M = c.M;
+  double acc[K + 1];
+  double emax = 0.0;
+#pragma unroll
+  for (int k = 0; k <= K; ++k) acc[k] = 0.0;
+  for (int64_t m = threadIdx.x; m < M; m += 256) {
+    const double et = c.E_theta[l * M + m];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] += et * c.A[(l * M + m) * K + k];
+    acc[K] += et;
+    emax = fmax(emax, et);
+  }
+#pragma unroll
+  for (int k = 0; k <= K; ++k) {
+    const double v = block_sum<256>(acc[k], sm);
+    if (threadIdx.x == 0) rte_s[k] = v;
+  }
+  emax = block_max<256>(emax, sm);
+  if (threadIdx.x == 0) {
+    double El[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double shp = c.alpha_lambda[l * K + k] + c.red2[l * K + k];
+      const double rte = c.beta_lambda[l * K + k] + rte_s[k];
+      c.phi_shp[l * K + k] = shp;
+      c.phi_rte[l * K + k] = rte;
+      const double el = vm_digamma(shp) - log(rte);
+      c.Elog_lambda[l * K + k] = el;
+      c.G_lambda[l * K + k] = exp(el);
+      El[k] = shp / rte;
+      c.E_lambda[l * K + k] = El[k];
+    }
+    double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
+    const double lp0 = log1p(c.eps), lpk = log(c.eps);
+    lc[VM_LC_C(0)] = lp0 * VM_LOG2E;
+    lc[VM_LC_D(K, 0)] = El[0] * VM_LOG2E;
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+      lc[VM_LC_C(k)] = (lpk - lp0) * VM_LOG2E;
+      lc[VM_LC_D(K, k)] = (El[k] - El[0]) * VM_LOG2E;
+    }
+    lc[VM_LC_SALL(K)] = rte_s[K];
+    lc[VM_LC_LP0(K)] = lp0;
+    lc[VM_LC_LPK(K)] = lpk;
+    // no closed-form row can underflow completely if even the largest possible S keeps k=0 alive
+    const double s_max = (c.r_mode == VM_R_EGO) ? 2.0 * emax : rte_s[K];
+    lc[VM_LC_DEAD(K)] = (c.r_mode == VM_R_CSR || lp0 - s_max * El[0] < VM_DEAD_LN + 8.0) ? 1.0 : 0.0;
+  }
+}
+
+// theta/lambda/nu caches from the current shapes and rates (`_update_cache`, model.py:676-684); used once after the
+// initial state has been injected.
+__global__ void k_refresh_cache(const __grid_constant__ vm_ctx c) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < c.L * c.M) {
+    const double el = vm_digamma(c.gamma_shp[t]) - log(c.gamma_rte[t]);
+    c.Elog_theta[t] = el;
+    c.G_theta[t] = exp(el);
+    c.E_theta[t] = c.gamma_shp[t] / c.gamma_rte[t];
+  }
+  if (t < c.L * c.K) {
+    const double el = vm_digamma(c.phi_shp[t]) - log(c.phi_rte[t]);
+    c.Elog_lambda[t] = el;
+    c.G_lambda[t] = exp(el);
+    c.E_lambda[t] = c.phi_shp[t] / c.phi_rte[t];
+  }
+  if (t == 0) {
+    double* nu = c.nu;
+    nu[VM_NU_E] = nu[VM_NU_SHP] / nu[VM_NU_RTE];
+    nu[VM_NU_G] = c.mutuality ? exp(vm_digamma(nu[VM_NU_SHP]) - log(nu[VM_NU_RTE])) : 0.0;
+    nu[VM_NU_G_STALE] = nu[VM_NU_G];
+  }
+}
+
+__device__ __forceinline__ double vm_Er(const vm_ctx& c, int l, int n) {
+  // E[theta] of node n acting as reporter in layer l (0 when it is not an active reporter)
+  return (n < (int)c.M && c.rep[(int64_t)l * c.M + n]) ? c.E_theta[(int64_t)l * c.M + n] : 0.0;
+}
+
+// Row/column tables of the separable log2-odds: a_k(l,i,j) = tab_p[lrow,k] + tab_q[l,j,k] since for the ego mask
+// S = E[theta_i]+E[theta_j], and for the all-reporter mask S is a per-layer constant.
+template <int K>
+__global__ void k_tables(const __grid_constant__ vm_ctx c) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nq = c.L * c.N, np = c.L * c.nloc;
+  if (t < nq) {
+    const int l = (int)(t / c.N), n = (int)(t - (int64_t)l * c.N);
+    const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
+    const double er = (c.r_mode == VM_R_EGO) ? vm_Er(c, l, n) : 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) c.tab_q[t * K + k] = (float)(-er * lc[VM_LC_D(K, k)]);
+  }
+  if (t < np) {
+    const int l = (int)(t / c.nloc), i = (int)(t - (int64_t)l * c.nloc) + (int)c.row0;
+    const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
+    const double s = (c.r_mode == VM_R_EGO) ? vm_Er(c, l, i) : lc[VM_LC_SALL(K)];
+#pragma unroll
+    for (int k = 0; k < K; ++k) c.tab_p[t * K + k] = (float)(lc[VM_LC_C(k)] - s * lc[VM_LC_D(K, k)]);
+  }
+}
+
+template <int K>
+__device__ __forceinline__ bool vm_may_dead(const vm_ctx& c, int l) {
+  return c.may_dead != 0 || c.layer_consts[(int64_t)l * VM_LC_STRIDE(K) + VM_LC_DEAD(K)] != 0.0;
+}
+
+// fp32 S of a tie under the general (CSR) mask, in CSR order -- shared by k_dense<CSR> and k_special.
+__device__ __forceinline__ float vm_csr_S32(const vm_ctx& c, int l, int64_t tie) {
+  float s = 0.f;
+  for (int64_t e = c.r_ptr[tie]; e < c.r_ptr[tie + 1]; ++e)
+    s = __fmaf_rn((float)c.E_theta[(int64_t)l * c.M + c.r_m[e]], c.r_val[e], s);
+  return s;
+}
+
+template <int K>
+__device__ __forceinline__ void vm_tie_logodds(const vm_ctx& c, int l, int64_t lrow, int j, float* a) {
+  if (c.r_mode == VM_R_CSR) {
+    const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
+    const float s = vm_csr_S32(c, l, lrow * c.N + j);
+#pragma unroll
+    for (int k = 0; k < K; ++k) a[k] = __fmaf_rn(-s, (float)lc[VM_LC_D(K, k)], (float)lc[VM_LC_C(k)]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      a[k] = __fadd_rn(c.tab_p[lrow * K + k], c.tab_q[((int64_t)l * c.N + j) * K + k]);
+  }
+}
+
+// ---- special ties (ties that carry X entries, and the diagonal): the full `_update_rho` in fp64 -------------
+// log rho_k = log(pr_k+EPS) + sum_{entries} dz1_k (E[log theta_m] + E[log lambda_k]) - S E[lambda_k]   (model.py:800-804,
+// 911-921), softmax over k (model.py:807-811), nu statistic (model.py:822-825), ELBO pieces (model.py:967-995, 1306-1313).
+template <int K>
+__global__ void __launch_bounds__(256) k_special(const __grid_constant__ vm_ctx c, int flags, double* part) {
+  __shared__ double sm[8];
+  const int l = blockIdx.y;
+  const int nloc = (int)c.nloc, nct = (int)c.nct;
+  const int64_t u0 = c.utile_ptr[(int64_t)l * nloc * nct], u1 = c.utile_ptr[(int64_t)(l + 1) * nloc * nct];
+  const int64_t u = u0 + (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const bool active = u < u1;
+  const bool elbo = flags & VM_F_ELBO;
+  const bool mut = c.mutuality != 0;
+  double nu_acc = 0.0, cat_acc = 0.0, t2_acc = 0.0;
+  double dlt[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) dlt[k] = 0.0;
+  if (active) {
+    const int64_t lrow = c.u_lrow[u];
+    const int i = (int)(lrow - (int64_t)l * nloc) + (int)c.row0, j = c.u_col[u];
+    // S = sum over the tie's reporters of E[theta] * R.vals (model.py:766-792)
+    double S;
+    if (c.r_mode == VM_R_EGO) {
+      const double ti = vm_Er(c, l, i);
+      S = (i == j) ? (c.ego_diag ? ti : 0.0) : ti + vm_Er(c, l, j);
+    } else if (c.r_mode == VM_R_ALL) {
+      S = c.layer_consts[(int64_t)l * VM_LC_STRIDE(K) + VM_LC_SALL(K)];
+    } else {
+      S = 0.0;
+      const int64_t tie = lrow * c.N + j;
+      for (int64_t e = c.r_ptr[tie]; e < c.r_ptr[tie + 1]; ++e)
+        S += c.E_theta[(int64_t)l * c.M + c.r_m[e]] * (double)c.r_val[e];
+    }
+    double Gl[K], Ell[K], lw[K], logpr[K];
+    const double Gnu = c.nu[VM_NU_G];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      Gl[k] = c.G_lambda[l * K + k];
+      Ell[k] = c.Elog_lambda[l * K + k];
+      logpr[k] = c.u_logpr[u * K + k];
+      lw[k] = logpr[k] - S * c.E_lambda[l * K + k];
+    }
+    const int64_t e0 = c.u_ptr[u], e1 = c.u_ptr[u + 1];
+    for (int64_t e = e0; e < e1; ++e) {
+      const int64_t lm = (int64_t)l * c.M + c.e_m[e];
+      double dz1[K], dz2[K];
+      vm_alloc<K>(mut, (double)c.e_x[e], (double)c.e_xT[e], c.G_theta[lm], Gl, Gnu, dz1, dz2);
+      const double et = c.Elog_theta[lm];
+#pragma unroll
+      for (int k = 0; k < K; ++k) lw[k] += dz1[k] * (et + Ell[k]);
+    }
+    double mx = lw[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) mx = fmax(mx, lw[k]);
+    double rho[K];
+    if (mx < VM_DEAD_LN) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) rho[k] = 0.0;
+    } else {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        rho[k] = exp(lw[k] - mx);
+        s += rho[k];
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) rho[k] /= s;
+    }
+    // second sweep over the entries: nu statistic and the log-Poisson-mean ELBO term (uses exp(rho), Q1)
+    if (mut || elbo) {
+      double erho[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) erho[k] = exp(rho[k]);
+      for (int64_t e = e0; e < e1; ++e) {
+        const int64_t lm = (int64_t)l * c.M + c.e_m[e];
+        const double x = (double)c.e_x[e], xT = (double)c.e_xT[e], Gth = c.G_theta[lm];
+        double dz1[K], dz2[K];
+        vm_alloc<K>(mut, x, xT, Gth, Gl, Gnu, dz1, dz2);
+#pragma unroll
+        for (int k = 0; k < K; ++k) nu_acc += dz2[k] * rho[k];
+        if (elbo) {
+          double val = 0.0;
+          if (c.e_flags[e] & 1) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) val += erho[k] * (Gth * Gl[k] + Gnu * xT);
+          }
+          t2_acc += x * log(val + c.eps);
+        }
+      }
+    }
+    // closed-form value the dense kernel uses for this tie: subtract it again from the statistics
+    float a[K], f[K], epsr;
+    bool dead;
+    vm_tie_logodds<K>(c, l, lrow, j, a);
+    vm_formula_rho<K>(a, vm_may_dead<K>(c, l), f, epsr, dead);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      c.rho_u[u * K + k] = rho[k];
+      c.rho_u32[u * K + k] = (float)rho[k];
+      dlt[k] = rho[k] - (double)f[k];
+      c.delta_u[u * K + k] = dlt[k];
+    }
+    if (elbo) {
+      const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
+#pragma unroll
+      for (int k = 0; k < K; ++k) cat_acc += rho[k] * (logpr[k] - log(rho[k] + c.eps));
+      cat_acc -= (double)vm_formula_cat<K>(f, epsr, dead, (float)lc[VM_LC_LP0(K)], (float)lc[VM_LC_LPK(K)],
+                                            (float)c.eps);
+    }
+  }
+  double* out = part + ((int64_t)l * c.n_ublk + blockIdx.x) * UPART_STRIDE;
+  double v;
+  v = block_sum<256>(nu_acc, sm);
+  if (threadIdx.x == 0) out[0] = v;
+  v = block_sum<256>(cat_acc, sm);
+  if (threadIdx.x == 0) out[1] = v;
+  v = block_sum<256>(t2_acc, sm);
+  if (threadIdx.x == 0) out[2] = v;
+  if (c.r_mode == VM_R_ALL) {  // the all-reporter statistics only need per-layer totals of delta
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      v = block_sum<256>(dlt[k], sm);
+      if (threadIdx.x == 0) out[4 + k] = v;
+    }
+  }
+}
+
+// ---- the per-tie dense kernel: every owned tie, closed form, fp32 slab write + statistics partials -------------
+// HBM-bound: writes 4*K bytes per tie, reads only the (L2-resident) tables.  256 threads x 4 consecutive ties
+// = one 1024-tie row segment per step, tile_h rows per CTA.  Per row it (1) evaluates the closed form,
+// (2) stores it with 128-bit stores, (3) patches the special ties of the segment with their fp64-computed values
+// (same CTA, after a barrier: the sectors are still dirty in L2, so no extra DRAM traffic), (4) emits the row
+// partial; column partials are kept in registers across the rows and written once per CTA.
+template <int K, bool ELBO, bool STORE, bool CSR>
+__global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constant__ vm_ctx c, double* catpart) {
+  const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
+  const int ct = blockIdx.x;
+  const int l = blockIdx.y / nrt, rt = blockIdx.y - l * nrt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j0 = ct * VM_TILE_W + tid * 4;
+  const int i_lo = rt * (int)c.tile_h, i_hi = min(i_lo + (int)c.tile_h, nloc);
+  const bool may_dead = vm_may_dead<K>(c, l);
+  const bool vec_ok = ((((int64_t)N * K) & 3) == 0) && (j0 + 3 < N);
+  __shared__ float sm_row[2][VM_DENSE_THREADS / 32][K];
+  __shared__ double sm_red[8];
+
+  const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
+  const float lp0 = (float)lc[VM_LC_LP0(K)], lpk = (float)lc[VM_LC_LPK(K)], epsf = (float)c.eps;
+  float q[K][4], cc[K], dd[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    cc[k] = (float)lc[VM_LC_C(k)];
+    dd[k] = (float)lc[VM_LC_D(K, k)];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      q[k][t] = (!CSR && j0 + t < N) ? __ldg(&c.tab_q[((int64_t)l * N + j0 + t) * K + k]) : -INFINITY;
+  }
+  float colacc[K][4];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) colacc[k][t] = 0.f;
+  double cat = 0.0;
+
+  for (int i = i_lo; i < i_hi; ++i) {
+    const int64_t lrow = (int64_t)l * nloc + i;
+    float p[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) p[k] = CSR ? 0.f : __ldg(&c.tab_p[lrow * K + k]);
+    float o[4 * K], rowacc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) rowacc[k] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const bool valid = j0 + t < N;
+      float a[K];
+      if (CSR) {
+        const float s = valid ? vm_csr_S32(c, l, lrow * N + j0 + t) : 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) a[k] = valid ? __fmaf_rn(-s, dd[k], cc[k]) : -INFINITY;
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) a[k] = __fadd_rn(p[k], q[k][t]);
+      }
+      float epsr;
+      bool dead;
+      vm_formula_rho<K>(a, may_dead, &o[t * K], epsr, dead);
+      if (!CSR) {
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+          colacc[k][t] += o[t * K + k];
+          rowacc[k] += o[t * K + k];
+        }
+        if (may_dead && dead && valid) {
+          colacc[0][t] += 1.f;
+          rowacc[0] += 1.f;
+        }
+      }
+      if (ELBO && valid) cat += (double)vm_formula_cat<K>(&o[t * K], epsr, dead, lp0, lpk, epsf);
+    }
+    if (STORE) {
+      float* dst = c.rho + (lrow * N + j0) * K;
+      if (vec_ok) {
+#pragma unroll
+        for (int v = 0; v < K; ++v)
+          reinterpret_cast<float4*>(dst)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (j0 + t < N) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) dst[t * K + k] = o[t * K + k];
+          }
+      }
+    }
+    if (!CSR) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float v = warp_sum(rowacc[k]);
+        if (lane == 0) sm_row[i & 1][warp][k] = v;
+      }
+    }
+    __syncthreads();
+    if (STORE) {
+      const int ua = c.utile_ptr[lrow * nct + ct], ub = c.utile_ptr[lrow * nct + ct + 1];
+      for (int u = ua + tid; u < ub; u += VM_DENSE_THREADS) {
+        float* dst = c.rho + (lrow * N + c.u_col[u]) * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) dst[k] = c.rho_u32[(int64_t)u * K + k];
+      }
+    }
+    if (!CSR && tid < K) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < VM_DENSE_THREADS / 32; ++w) v += sm_row[i & 1][w][tid];
+      c.rowpart[(lrow * nct + ct) * K + tid] = v;
+    }
+  }
+  if (!CSR) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (j0 + t < N) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) c.colpart[(((int64_t)l * nrt + rt) * N + j0 + t) * K + k] = colacc[k][t];
+      }
+  }
+  if (ELBO) {
+    const double v = block_sum<VM_DENSE_THREADS>(cat, sm_red);
+    if (tid == 0) catpart[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
+  }
+}
+
+// ---- statistics of the new rho: A[l,m,k] = sum of rho_k over the ties reported by (l,m) ------------------------
+// ego mask: row sums + column sums of the closed form (dense partials) + the special-tie corrections.
+// One warp per reporter; fixed summation order.
+template <int K>
+__global__ void __launch_bounds__(256) k_stats_ego(const __grid_constant__ vm_ctx c, int init) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t lm = (int64_t)blockIdx.x * 8 + warp;
+  if (lm >= c.L * c.M) return;
+  double* out = c.red3 + lm * K;
+  if (!c.rep[lm]) {
+    if (lane < K) out[lane] = 0.0;
+    return;
+  }
+  const int l = (int)(lm / c.M), m = (int)(lm - (int64_t)l * c.M);
+  const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
+  const bool local = m >= c.row0 && m < c.row0 + nloc;
+  const int64_t lrow = (int64_t)l * nloc + (m - c.row0);
+  double f[K], d[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) f[k] = d[k] = 0.0;
+  if (!init) {
+    if (local)
+      for (int t = lane; t < nct; t += 32) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) f[k] += (double)c.rowpart[(lrow * nct + t) * K + k];
+      }
+    for (int t = lane; t < nrt; t += 32) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) f[k] += (double)c.colpart[(((int64_t)l * nrt + t) * N + m) * K + k];
+    }
+    if (local && lane == 0) {  // the (m,m) tie is in the row AND the column sums
+      float a[K], g[K], epsr;
+      bool dead;
+      vm_tie_logodds<K>(c, l, lrow, m, a);
+      vm_formula_rho<K>(a, vm_may_dead<K>(c, l), g, epsr, dead);
+      const double w = c.ego_diag ? 1.0 : 2.0;
+#pragma unroll
+      for (int k = 1; k < K; ++k) f[k] -= w * (double)g[k];
+      if (dead) f[0] -= w;
+    }
+  }
+  if (local) {
+    const int ua = c.utile_ptr[lrow * nct], ub = c.utile_ptr[(lrow + 1) * nct];
+    for (int u = ua + lane; u < ub; u += 32) {
+      if (!c.ego_diag && c.u_col[u] == m) continue;
+#pragma unroll
+      for (int k = 0; k < K; ++k) d[k] += c.delta_u[(int64_t)u * K + k];
+    }
+  }
+  for (int64_t p = c.ucol_ptr[(int64_t)l * N + m] + lane; p < c.ucol_ptr[(int64_t)l * N + m + 1]; p += 32) {
+    const int u = c.ucol_perm[p];
+    if (local && c.u_lrow[u] == lrow) continue;  // the diagonal tie: counted (at most) once, above
+#pragma unroll
+    for (int k = 0; k < K; ++k) d[k] += c.delta_u[(int64_t)u * K + k];
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    f[k] = warp_sum(f[k]);
+    d[k] = warp_sum(d[k]);
+  }
+  if (lane == 0) {
+    const double nties = (local ? (double)N : 0.0) + (double)nloc - (local ? (c.ego_diag ? 1.0 : 2.0) : 0.0);
+    double f0 = nties - (init ? 0.0 : f[0]);
+#pragma unroll
+    for (int k = 1; k < K; ++k) f0 -= f[k];
+    out[0] = f0 + d[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) out[k] = f[k] + d[k];
+  }
+}
+
+// all-reporter mask: A[l,m,:] is the same for every m = per-layer totals.
+template <int K>
+__global__ void __launch_bounds__(256) k_stats_all(const __grid_constant__ vm_ctx c, int init, const double* upart) {
+  __shared__ double sm[8];
+  __shared__ double tot[K];
+  const int l = blockIdx.x;
+  const int64_t nrow = c.nloc * c.nct;
+  double f[K], d[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) f[k] = d[k] = 0.0;
+  if (!init)
+    for (int64_t t = threadIdx.x; t < nrow; t += 256) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) f[k] += (double)c.rowpart[((int64_t)l * nrow + t) * K + k];
+    }
+  for (int64_t b = threadIdx.x; b < c.n_ublk; b += 256) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) d[k] += upart[((int64_t)l * c.n_ublk + b) * UPART_STRIDE + 4 + k];
+  }
+  double fs[K], ds[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    fs[k] = block_sum<256>(f[k], sm);
+    ds[k] = block_sum<256>(d[k], sm);
+  }
+  if (threadIdx.x == 0) {
+    double f0 = (double)c.nloc * (double)c.N - (init ? 0.0 : fs[0]);
+#pragma unroll
+    for (int k = 1; k < K; ++k) f0 -= fs[k];
+    tot[0] = f0 + ds[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) tot[k] = fs[k] + ds[k];
+  }
+  __syncthreads();
+  for (int64_t t = threadIdx.x; t < c.M * K; t += 256) c.red3[(int64_t)l * c.M * K + t] = tot[t % K];
+}
+
+// general mask: gather the (patched) dense slab through the per-reporter CSC.
+template <int K>
+__global__ void __launch_bounds__(256) k_stats_csc(const __grid_constant__ vm_ctx c, int init) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t lm = (int64_t)blockIdx.x * 8 + warp;
+  if (lm >= c.L * c.M) return;
+  double f[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) f[k] = 0.0;
+  for (int64_t p = c.c_ptr[lm] + lane; p < c.c_ptr[lm + 1]; p += 32) {
+    const int64_t tie = c.c_tie[p];
+#pragma unroll
+    for (int k = 0; k < K; ++k) f[k] += (double)c.rho[tie * K + k];
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) f[k] = warp_sum(f[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) c.red3[lm * K + k] = f[k];
+  }
+}
+
+// delta_u = rho_u - onehot for the initial statistics (rho = pr_rho, model.py:602)
+__global__ void k_init_delta(const __grid_constant__ vm_ctx c) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= c.U * c.K) return;
+  const int k = (int)(t % c.K);
+  const double r = c.rho_u[t];
+  c.delta_u[t] = r - (k == 0 ? 1.0 : 0.0);
+  c.rho_u32[t] = (float)r;
+}
+// per-layer totals of delta_u, for the all-reporter initial statistics
+__global__ void __launch_bounds__(256) k_init_delta_all(const __grid_constant__ vm_ctx c, double* upart) {
+  __shared__ double sm[8];
+  const int l = blockIdx.y;
+  const int64_t u0 = c.utile_ptr[(int64_t)l * c.nloc * c.nct], u1 = c.utile_ptr[(int64_t)(l + 1) * c.nloc * c.nct];
+  const int64_t u = u0 + (int64_t)blockIdx.x * 256 + threadIdx.x;
+  for (int k = 0; k < (int)c.K; ++k) {
+    const double v = block_sum<256>(u < u1 ? c.delta_u[u * c.K + k] : 0.0, sm);
+    if (threadIdx.x == 0) upart[((int64_t)l * c.n_ublk + blockIdx.x) * UPART_STRIDE + 4 + k] = v;
+  }
+}
+
+// ELBO eta part: B = sum over X entries whose transposed position is reported of x * sum_k rho_k[transposed tie]
+// (model.py:1269-1290); sum_k rho_k is 1 for a live tie and 0 for a fully-underflowed one (Q3).
+template <int K>
+__global__ void __launch_bounds__(256) k_elbo_b(const __grid_constant__ vm_ctx c, double* part) {
+  __shared__ double sm[8];
+  double acc = 0.0;
+  for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < c.IT; t += (int64_t)gridDim.x * 256) {
+    const int u = c.t_u[t];
+    bool alive = true;
+    if (u >= 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) s += c.rho_u[(int64_t)u * K + k];
+      alive = s > 0.0;
+    } else {
+      const int64_t lrow = c.t_lrow[t];
+      const int l = (int)(lrow / c.nloc);
+      if (vm_may_dead<K>(c, l)) {
+        float a[K], g[K], epsr;
+        bool dead;
+        vm_tie_logodds<K>(c, l, lrow, c.t_col[t], a);
+        vm_formula_rho<K>(a, true, g, epsr, dead);
+        alive = !dead;
+      }
+    }
+    if (alive) acc += (double)c.t_x[t];
+  }
+  const double v = block_sum<256>(acc, sm);
+  if (threadIdx.x == 0) part[blockIdx.x] = v;
+}
+
+// second pass over the scalar partials: nu, cat, t2 (special-tie blocks), cat (dense blocks), B
+__global__ void __launch_bounds__(256) k_sums_reduce(const __grid_constant__ vm_ctx c, int flags, const double* upart,
+                                                     int64_t n_upart, const double* catpart, int64_t n_cat,
+                                                     const double* bpart, int64_t n_b) {
+  __shared__ double sm[8];
+  double nu = 0.0, cat = 0.0, t2 = 0.0, b = 0.0;
+  for (int64_t q = threadIdx.x; q < n_upart; q += 256) {
+    nu += upart[q * UPART_STRIDE + 0];
+    cat += upart[q * UPART_STRIDE + 1];
+    t2 += upart[q * UPART_STRIDE + 2];
+  }
+  if (flags & VM_F_ELBO) {
+    for (int64_t q = threadIdx.x; q < n_cat; q += 256) cat += catpart[q];
+    for (int64_t q = threadIdx.x; q < n_b; q += 256) b += bpart[q];
+  }
+  nu = block_sum<256>(nu, sm);
+  cat = block_sum<256>(cat, sm);
+  t2 = block_sum<256>(t2, sm);
+  b = block_sum<256>(b, sm);
+  if (threadIdx.x == 0) {
+    double* ex = c.red3 + c.L * c.M * c.K;
+    ex[VM_R3_NU] = nu;
+    ex[VM_R3_CAT] = cat;
+    ex[VM_R3_T2] = t2;
+    ex[VM_R3_B] = b;
+  }
+}
+
+// =====================================================================================================
+// phase finish
+// =====================================================================================================
+#define VM_EP_BLOCKS 64
+// partial sums of the A-weighted Poisson-mean term and of the gamma ELBO terms of theta (model.py:957-965, 997-1002)
+template <int K>
+__global__ void __launch_bounds__(256) k_elbo_partial(const __grid_constant__ vm_ctx c, double* part) {
+  __shared__ double sm[8];
+  double t1 = 0.0, g = 0.0;
+  const int64_t LM = c.L * c.M;
+  for (int64_t lm = (int64_t)blockIdx.x * 256 + threadIdx.x; lm < LM; lm += (int64_t)gridDim.x * 256) {
+    const int l = (int)(lm / c.M);
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) s += c.E_lambda[l * K + k] * c.red3[lm * K + k];
+    t1 += c.E_theta[lm] * s;
+    g += vm_gamma_elbo_term(c.alpha_theta[lm], c.beta_theta[lm], c.gamma_shp[lm], c.gamma_rte[lm]);
+  }
+  t1 = block_sum<256>(t1, sm);
+  g = block_sum<256>(g, sm);
+  if (threadIdx.x == 0) {
+    part[2 * blockIdx.x] = t1;
+    part[2 * blockIdx.x + 1] = g;
+  }
+}
+
+// `_update_nu` (model.py:820-830), nu part of the cache (model.py:684), and `__ELBO` assembly (model.py:948-1019).
+__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ vm_ctx c, int flags, const double* part,
+                                                int n_part) {
+  __shared__ double sm[8];
+  const int64_t LMK = c.L * c.M * c.K;
+  const double* ex = c.red3 + LMK;
+  double t1 = 0.0, g = 0.0;
+  if (flags & VM_F_ELBO)
+    for (int q = threadIdx.x; q < n_part; q += 256) {
+      t1 += part[2 * q];
+      g += part[2 * q + 1];
+    }
+  t1 = block_sum<256>(t1, sm);
+  g = block_sum<256>(g, sm);
+  if (threadIdx.x != 0) return;
+  double* nu = c.nu;
+  if (c.mutuality && !(flags & VM_F_INIT)) nu[VM_NU_SHP] = c.alpha_eta + ex[VM_R3_NU];
+  nu[VM_NU_G_STALE] = nu[VM_NU_G];
+  nu[VM_NU_E] = nu[VM_NU_SHP] / nu[VM_NU_RTE];
+  if (c.mutuality) nu[VM_NU_G] = exp(vm_digamma(nu[VM_NU_SHP]) - log(nu[VM_NU_RTE]));
+  if (flags & VM_F_ELBO) {
+    double gl = 0.0;
+    for (int64_t t = 0; t < c.L * c.K; ++t)
+      gl += vm_gamma_elbo_term(c.alpha_lambda[t], c.beta_lambda[t], c.phi_shp[t], c.phi_rte[t]);
+    const double ge = vm_gamma_elbo_term(c.alpha_eta, c.beta_eta, nu[VM_NU_SHP], nu[VM_NU_RTE]);
+    const double tb = c.mutuality ? nu[VM_NU_E] * ex[VM_R3_B] : 0.0;
+    double* o = c.elbo_out;
+    o[1] = -t1;
+    o[2] = -tb;
+    o[3] = ex[VM_R3_T2];
+    o[4] = g;
+    o[5] = gl;
+    o[6] = ge;
+    o[7] = ex[VM_R3_CAT];
+    o[0] = -t1 - tb + ex[VM_R3_T2] + g + gl + ge + ex[VM_R3_CAT];
+  }
+}
+
+// =====================================================================================================
+// posterior consumers / utilities
+// =====================================================================================================
+__global__ void k_fill_onehot(float* rho, int64_t T, int K) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T * K; t += (int64_t)gridDim.x * blockDim.x)
+    rho[t] = (t % K == 0) ? 1.f : 0.f;
+}
+__global__ void k_patch_special(const __grid_constant__ vm_ctx c) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= c.U) return;
+  float* dst = c.rho + ((int64_t)c.u_lrow[u] * c.N + c.u_col[u]) * c.K;
+  for (int k = 0; k < (int)c.K; ++k) dst[k] = (float)c.rho_u[u * c.K + k];
+}
+// rho_max (model.py:1148-1149) / fixed threshold on rho[...,1] (model.py:1155-1166, utils.py:207-217)
+__global__ void k_infer(const float* rho, int64_t T, int K, int mode, float thr, uint8_t* out) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
+    const float* r = rho + t * K;
+    if (mode == 0) {
+      int best = 0;
+      float bv = r[0];
+      for (int k = 1; k < K; ++k)
+        if (r[k] > bv) {
+          bv = r[k];
+          best = k;
+        }
+      out[t] = (uint8_t)best;
+    } else {
+      out[t] = r[1] >= thr ? 1 : 0;
+    }
+  }
+}
+__global__ void k_test_special(const double* x, double* dg, double* lg, int64_t n) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  dg[t] = vm_digamma(x[t]);
+  lg[t] = lgamma(x[t]);
+}
+
+// =====================================================================================================
+// host-side launchers
+// =====================================================================================================
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
+
+// blkpart regions (doubles)
+static inline double* region_u(const vm_ctx* c) { return c->blkpart; }  // special-tie block partials
+static inline int64_t n_upart(const vm_ctx* c) { return c->L * c->n_ublk; }
+static inline double* region_cat(const vm_ctx* c) { return c->blkpart + n_upart(c) * UPART_STRIDE; }
+static inline int64_t n_catpart(const vm_ctx* c) { return c->nct * c->L * c->nrt; }
+static inline double* region_b(const vm_ctx* c) { return region_cat(c) + n_catpart(c); }
+#define VM_B_BLOCKS 128
+static inline double* region_ep(const vm_ctx* c) { return region_b(c) + VM_B_BLOCKS; }
+
+static int check_ctx(const vm_ctx* c) {
+  if (!c) return VM_EINVAL;
+  if (c->K < 2 || c->K > VM_MAX_K) return VM_EINVAL;
+  if (c->tile_w != VM_TILE_W || c->tile_h < 1) return VM_EINVAL;
+  if (c->nct != cdiv(c->N, VM_TILE_W) || c->nrt != cdiv(c->nloc, c->tile_h)) return VM_EINVAL;
+  if (c->r_mode < 0 || c->r_mode > 2) return VM_EINVAL;
+  if (c->L * c->nrt > 65535 || c->L > 65535) return VM_EINVAL;
+  return 0;
+}
+
+#define DISPATCH_K(KV, ...)     \
+  switch (KV) {                 \
+    case 2: { constexpr int K = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int K = 3; __VA_ARGS__; } break; \
+    case 4: { constexpr int K = 4; __VA_ARGS__; } break; \
+    case 5: { constexpr int K = 5; __VA_ARGS__; } break; \
+    case 6: { constexpr int K = 6; __VA_ARGS__; } break; \
+    case 7: { constexpr int K = 7; __VA_ARGS__; } break; \
+    case 8: { constexpr int K = 8; __VA_ARGS__; } break; \
+    default: return VM_EINVAL;  \
+  }
+
+template <int K>
+static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st) {
+  const dim3 grid((unsigned)c->nct, (unsigned)(c->L * c->nrt));
+  const bool elbo = flags & VM_F_ELBO, store = !(flags & VM_F_NO_STORE), csr = c->r_mode == VM_R_CSR;
+  double* cp = region_cat(c);
+#define LD(E, S, C) k_dense<K, E, S, C><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp)
+  if (csr) {
+    if (!store) return VM_ENOTSUP;  // the general-mask statistics gather the slab
+    if (elbo) LD(true, true, true); else LD(false, true, true);
+  } else if (elbo) {
+    if (store) LD(true, true, false); else LD(true, false, false);
+  } else {
+    if (store) LD(false, true, false); else LD(false, false, false);
+  }
+#undef LD
+  return 0;
+}
+
+template <int K>
+static int launch_stats(const vm_ctx* c, int init, cudaStream_t st) {
+  const int64_t LM = c->L * c->M;
+  if (c->r_mode == VM_R_EGO) {
+    k_stats_ego<K><<<(unsigned)cdiv(LM, 8), 256, 0, st>>>(*c, init);
+  } else if (c->r_mode == VM_R_ALL) {
+    k_stats_all<K><<<(unsigned)c->L, 256, 0, st>>>(*c, init, region_u(c));
+  } else {
+    k_stats_csc<K><<<(unsigned)cdiv(LM, 8), 256, 0, st>>>(*c, init);
+  }
+  return 0;
+}
+
+extern "C" int64_t vm_ctx_size(void) { return (int64_t)sizeof(vm_ctx); }
+extern "C" int64_t vm_abi_version(void) { return VM_ABI_VERSION; }
+
+extern "C" int vm_materialize_prior(const vm_ctx* c, void* stream) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t T = c->L * c->nloc * c->N;
+  k_fill_onehot<<<(unsigned)imin64(cdiv(T * c->K, 256), 148 * 16), 256, 0, st>>>(c->rho, T, (int)c->K);
+  VM_CHECK_LAUNCH();
+  if (c->U > 0) k_patch_special<<<(unsigned)cdiv(c->U, 256), 256, 0, st>>>(*c);
+  VM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vm_refresh_cache(const vm_ctx* c, void* stream) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  const int64_t n = c->L * (c->M > c->K ? c->M : c->K);
+  k_refresh_cache<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(*c);
+  VM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vm_init_stats(const vm_ctx* c, void* stream) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->U > 0) k_init_delta<<<(unsigned)cdiv(c->U * c->K, 256), 256, 0, st>>>(*c);
+  VM_CHECK_LAUNCH();
+  if (c->r_mode == VM_R_ALL) {
+    k_init_delta_all<<<dim3((unsigned)c->n_ublk, (unsigned)c->L), 256, 0, st>>>(*c, region_u(c));
+    VM_CHECK_LAUNCH();
+  }
+  if (c->r_mode == VM_R_CSR) {  // gather needs the slab
+    rc = vm_materialize_prior(c, stream);
+    if (rc) return rc;
+  }
+  DISPATCH_K(c->K, launch_stats<K>(c, 1, st));
+  VM_CHECK_LAUNCH();
+  // zero the scalar sums
+  cudaMemsetAsync(c->red3 + c->L * c->M * c->K, 0, VM_R3_EXTRA * sizeof(double), st);
+  VM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vm_phase_gamma(const vm_ctx* c, void* stream) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->n_gchunk > 0) {
+    DISPATCH_K(c->K, (k_gamma_partial<K><<<(unsigned)cdiv(c->n_gchunk, 8), 256, 0, st>>>(*c, c->blkpart)));
+    VM_CHECK_LAUNCH();
+  }
+  k_gamma_reduce<<<(unsigned)cdiv(c->L * c->M, 256), 256, 0, st>>>(*c, c->blkpart);
+  VM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vm_phase_phi(const vm_ctx* c, void* stream) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_K(c->K, (k_gamma_finish<K><<<(unsigned)cdiv(c->L * c->M, 256), 256, 0, st>>>(*c)));
+  VM_CHECK_LAUNCH();
+  DISPATCH_K(c->K, (k_phi_partial<K><<<dim3((unsigned)c->n_phichunk, (unsigned)c->L), 256, 0, st>>>(*c, c->blkpart)));
+  VM_CHECK_LAUNCH();
+  DISPATCH_K(c->K, (k_phi_reduce<K><<<(unsigned)c->L, 256, 0, st>>>(*c, c->blkpart)));
+  VM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vm_phase_rho(const vm_ctx* c, int flags, void* stream) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_K(c->K, (k_phi_finish<K><<<(unsigned)c->L, 256, 0, st>>>(*c)));
+  VM_CHECK_LAUNCH();
+  if (c->r_mode != VM_R_CSR) {
+    DISPATCH_K(c->K, (k_tables<K><<<(unsigned)cdiv(c->L * c->N, 256), 256, 0, st>>>(*c)));
+    VM_CHECK_LAUNCH();
+  }
+  DISPATCH_K(c->K, (k_special<K><<<dim3((unsigned)c->n_ublk, (unsigned)c->L), 256, 0, st>>>(*c, flags, region_u(c))));
+  VM_CHECK_LAUNCH();
+  DISPATCH_K(c->K, rc = launch_dense<K>(c, flags, st));
+  if (rc) return rc;
+  VM_CHECK_LAUNCH();
+  DISPATCH_K(c->K, launch_stats<K>(c, 0, st));
+  VM_CHECK_LAUNCH();
+  if ((flags & VM_F_ELBO) && c->mutuality) {
+    DISPATCH_K(c->K, (k_elbo_b<K><<<VM_B_BLOCKS, 256, 0, st>>>(*c, region_b(c))));
+    VM_CHECK_LAUNCH();
+  }
+  k_sums_reduce<<<1, 256, 0, st>>>(*c, flags, region_u(c), n_upart(c), region_cat(c), n_catpart(c), region_b(c),
+                                   c->mutuality ? VM_B_BLOCKS : 0);
+  VM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vm_phase_finish(const vm_ctx* c, int flags, void* stream) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->A != c->red3) {
+    cudaMemcpyAsync(c->A, c->red3, (size_t)(c->L * c->M * c->K) * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    VM_CHECK_LAUNCH();
+  }
+  const int nb = (int)imin64(VM_EP_BLOCKS, cdiv(c->L * c->M, 256));
+  if (flags & VM_F_ELBO) {
+    DISPATCH_K(c->K, (k_elbo_partial<K><<<nb, 256, 0, st>>>(*c, region_ep(c))));
+    VM_CHECK_LAUNCH();
+  }
+  k_finish<<<1, 256, 0, st>>>(*c, flags, region_ep(c), nb);
+  VM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vm_iteration(const vm_ctx* c, int flags, void* stream) {
+  int rc;
+  if ((rc = vm_phase_gamma(c, stream))) return rc;
+  if ((rc = vm_phase_phi(c, stream))) return rc;
+  if ((rc = vm_phase_rho(c, flags, stream))) return rc;
+  return vm_phase_finish(c, flags, stream);
+}
+
+extern "C" int vm_run(const vm_ctx* c, int n_iter, int flags, int last_flags, void* stream) {
+  for (int it = 0; it < n_iter; ++it) {
+    int rc = vm_iteration(c, it == n_iter - 1 ? last_flags : flags, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int vm_infer(const vm_ctx* c, int mode, double threshold, uint8_t* out, void* stream) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (mode == 1 && c->K < 2) return VM_EINVAL;
+  const int64_t T = c->L * c->nloc * c->N;
+  k_infer<<<(unsigned)imin64(cdiv(T, 256), 148 * 16), 256, 0, (cudaStream_t)stream>>>(c->rho, T, (int)c->K, mode,
+                                                                                          (float)threshold, out);
+  VM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int vm_test_special(const double* x, double* dg, double* lg, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  k_test_special<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dg, lg, n);
+  VM_CHECK_LAUNCH();
+  return 0;
+}
