@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the CAVI hot path (BASELINE.json metric: CAVI iter/s and ties/s at N=20k, % of HBM roofline).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (numpy oracle port)
+
+A "step" is ONE CAVI iteration (reference `_update_CAVI`, model.py:623-660) over the whole synthetic network, with
+the ELBO evaluated on the reference's cadence (iteration 1, every 10th, the last; model.py:1036) inside the timed
+region.  Workload (config 3 of BASELINE.json): StandardSBM law, N=20 000 nodes, M=N ego-only reporters, L=1, K=2,
+mutuality=True, generated sparsely (vimure_b200/synthetic.py).  With N>1 GPUs the ties are sharded by node-row
+blocks and the network is grown so that every GPU keeps 4e8 ties ("weak" scaling): N_nodes = 20 000*sqrt(N).
+`value` = ties processed per second by the whole job = steps * L * N_nodes^2 / time (max over ranks, CUDA events).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BASE_N = 20000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nodes", type=int, default=0, help="override the number of nodes per GPU-count rule")
+    ap.add_argument("--L", type=int, default=1)
+    ap.add_argument("--K", type=int, default=2)
+    ap.add_argument("--cpu-nodes", type=int, default=1500, help="nodes of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tile-h", type=int, default=64)
+    return ap.parse_args()
+
+
+def n_nodes_for(gpus, override):
+    if override:
+        return override
+    n = int(round(BASE_N * math.sqrt(gpus)))
+    return (n + 3) // 4 * 4
+
+
+def make_network(N, L, K, seed_y=10, seed_x=20):
+    from vimure_b200 import synthetic as syn
+
+    net = syn.StandardSBM(N=N, L=L, K=K, C=2, avg_degree=10, seed=seed_y)
+    net.build_X(mutuality=0.5, seed=seed_x)
+    return net
+
+
+def draw_state(net, K, seed=1):
+    """Initial variational state as `_initialize_priors` draws it (model.py:570-595), default priors."""
+    prng = np.random.RandomState(seed)
+    L, M = net.L, net.M
+    rs = prng.random_sample
+    st = dict(gamma_shp=0.1 * rs((L, M)) + 0.1, phi_shp=10.0 * rs((L, K)) + 10.0,
+              gamma_rte=0.1 * rs((L, M)) + 0.1, phi_rte=10.0 * rs((L, K)) + 10.0,
+              nu_shp=0.5 * rs(1)[0] + 0.5)
+    return st, prng
+
+
+PRIORS = dict(alpha_theta=0.1, beta_theta=0.1, alpha_lambda=10.0, beta_lambda=10.0, alpha_eta=0.5, beta_eta=1.0)
+
+
+# ----------------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_throughput(n_nodes, L, K, iters=3):
+    """ties/s of the numpy oracle port of the reference algorithm on a bounded sample of the same law."""
+    from oracle.cavi_numpy import OracleCAVI
+
+    net = make_network(n_nodes, L, K)
+    spec = {"kind": "ego", "rep": np.ones((L, net.M), dtype=np.uint8), "diag": True}
+    o = OracleCAVI(L, n_nodes, net.M, K, np.stack(net.X.subs), net.X.vals, spec, mutuality=True, **PRIORS)
+    st, prng = draw_state(net, K)
+    # random prior on the ties that carry a report (model.py:470-482, 536-556)
+    s = np.stack(net.X.subs[:3])
+    ties = np.unique(s, axis=1).T
+    pr = 1 + 0.01 * prng.random_sample((len(ties), K))
+    pr /= pr.sum(axis=1)[:, None]
+    o.set_state(st["gamma_shp"], st["gamma_rte"], st["phi_shp"], st["phi_rte"], st["nu_shp"],
+                o.default_pr_rho(ties, pr))
+    o.iterate()  # warm-up
+    t0 = time.time()
+    for it in range(iters):
+        o.iterate()
+        if it == 0 or it == iters - 1:
+            o.elbo()
+    dt = time.time() - t0
+    ties = float(L) * n_nodes * n_nodes
+    return iters * ties / dt, dt / iters, len(net.X.vals)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    try:
+        import torch
+
+        torch.set_num_threads(os.cpu_count() or 1)
+    except Exception:
+        pass
+    n = args.cpu_nodes
+    N_full = n_nodes_for(args.gpus, args.nodes)
+    # each step = one CAVI iteration on the bounded sample
+    from oracle.cavi_numpy import OracleCAVI  # noqa: F401
+
+    t_all = time.time()
+    val, s_per_it, nnz = cpu_oracle_throughput(n, args.L, args.K, iters=max(1, min(args.steps, 5)))
+    line = {
+        "impl": "reference", "metric": "cavi_ties_per_s", "value": val, "unit": "ties/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_it * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "StandardSBM ego-only N=%d M=N L=%d K=%d mutuality (config 3 of BASELINE.json)"
+                               % (N_full, args.L, args.K)},
+        "cpu_baseline": {"value": val, "unit": "ties/s", "cores": 1, "kind": "port",
+                         "sample": "numpy oracle port of model.py:623-1019, same law at N=%d (nnz(X)=%d), %d iterations"
+                                   % (n, nnz, max(1, min(args.steps, 5)))},
+        "e2e": {"value": val, "unit": "ties/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "iter_per_s_on_sample": 1.0 / s_per_it, "wall_s": time.time() - t_all,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop = index, [], False
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+                for nm, v in zip(names, s[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+
+    from vimure_b200 import _packing
+    from vimure_b200._engine import CaviEngine
+    from vimure_b200.model import VimureModel, shard_rows
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    L, K = args.L, args.K
+    N = n_nodes_for(world, args.nodes)
+    net = make_network(N, L, K)
+    T = float(L) * N * N
+    nnzX = len(net.X.vals)
+
+    row0, nloc = shard_rows(N, world, rank)
+    P = _packing.pack(net.X.subs, net.X.vals, L, N, net.M, K, net.R, dev, row0=row0, nloc=nloc, tile_h=args.tile_h)
+    eng = CaviEngine(P, PRIORS, mutuality=True, eps=1e-12, group=True if world > 1 else None)
+    st, prng = draw_state(net, K)
+    keep = (P.t["u_has_x"] & P.t["u_reported"]).cpu().numpy()
+    pr_u = np.zeros((P.U, K))
+    pr_u[:, 0] = 1.0
+    pr = 1 + 0.01 * prng.random_sample((int(keep.sum()), K))
+    pr_u[keep] = pr / pr.sum(axis=1)[:, None]
+    nu_rte = PRIORS["beta_eta"] + float(net.X.vals.sum())
+    eng.set_state(st["gamma_shp"], st["gamma_rte"], st["phi_shp"], st["phi_rte"], st["nu_shp"], nu_rte, pr_u, 1e-12)
+
+    def run_iters(first, count, total):
+        """iterations first..first+count-1 of a `total`-iteration fit, ELBO on the reference cadence"""
+        it = first
+        end = first + count - 1
+        while it <= end:
+            nxt = it
+            while not (nxt == 1 or nxt % 10 == 0 or nxt == total) and nxt < end:
+                nxt += 1
+            is_elbo = (nxt == 1 or nxt % 10 == 0 or nxt == total)
+            eng.iterate(nxt - it + 1, elbo_last=is_elbo)
+            if is_elbo:
+                e = eng.elbo()  # the one D2H scalar of `_check_for_convergence`
+                if not np.isfinite(e):
+                    raise RuntimeError("ELBO is not finite")
+            it = nxt + 1
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    total = args.warmup + args.steps
+    run_iters(1, args.warmup, total)
+    barrier()
+    n0 = eng.n_launch
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record()
+        run_iters(args.warmup + 1, args.steps, total)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.n_launch - n0
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = args.steps * T / (ms * 1e-3)
+    elbo_final = eng.elbo()
+
+    # ---- dominant kernel in isolation: the per-tie dense kernel (writes 4*K bytes per owned tie)
+    reps = 20
+    eng.dense_only(0)
+    torch.cuda.synchronize(dev)
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for _ in range(reps):
+        eng.dense_only(0)
+    d1.record()
+    torch.cuda.synchronize(dev)
+    dense_ms = d0.elapsed_time(d1) / reps
+    ties_local = float(L) * nloc * N
+    alg_bytes = 4.0 * K * ties_local
+    achieved = alg_bytes / (dense_ms * 1e-3) / 1e9
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "dense_traffic.json")))
+        if tr.get("N") == N and tr.get("K") == K and tr.get("nloc") == nloc:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_dense", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dense_ms,
+                "share_of_step": dense_ms / (ms / args.steps)}
+
+    # ---- end to end through the public API, host buffers in, posterior parameters + ELBO out
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        subs_host = [np.ascontiguousarray(s) for s in net.X.subs]
+        vals_host = np.ascontiguousarray(net.X.vals)
+        h2d = sum(s.nbytes for s in subs_host) + vals_host.nbytes
+        from vimure_b200.sptensor import sptensor
+
+        Xh = sptensor(tuple(subs_host), vals_host, shape=net.X.shape)
+        model = VimureModel(mutuality=True, convergence_tol=0.0)  # tol 0: never stops early -> exactly `steps` iterations
+        t0 = time.time()
+        model.fit(Xh, R=net.R, K=K, seed=1, max_iter=args.steps, init="fast")
+        post = model.get_posterior_estimates
+        d2h = model.gamma_shp.nbytes * 4 + model.phi_shp.nbytes * 4 + 8 * (2 + len(model.trace))
+        torch.cuda.synchronize(dev)
+        wall = time.time() - t0
+        if dist is not None:
+            t = torch.tensor([wall], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall = float(t.item())
+        e2e = {"value": args.steps * T / wall, "unit": "ties/s", "h2d_bytes_per_step": h2d / args.steps,
+               "d2h_bytes_per_step": d2h / args.steps, "wall_s": wall, "pack_s": model.pack_time,
+               "what": "VimureModel.fit(X host COO, R=EgoMask, max_iter=steps): pack + H2D + CAVI + ELBO + D2H of "
+                       "gamma/phi/nu posteriors; rho stays on the device"}
+        del model
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, s_it, nnz_s = cpu_oracle_throughput(args.cpu_nodes, L, K, iters=3)
+        cpu = {"value": v, "unit": "ties/s", "cores": 1, "kind": "port",
+               "sample": "numpy oracle port, same law at N=%d (nnz(X)=%d), 3 iterations, %.2f s/iter"
+                         % (args.cpu_nodes, nnz_s, s_it)}
+
+    if rank == 0:
+        line = {
+            "metric": "cavi_ties_per_s", "value": value, "unit": "ties/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 storage / f64 accumulate", "data": "synthetic",
+            "config": {"workload": "StandardSBM ego-only N=%d M=N L=%d K=%d mutuality (config 3 of BASELINE.json%s)"
+                                   % (N, L, K, "" if world == 1 else ", grown to keep 4e8 ties per GPU"),
+                       "nnz_X": nnzX, "special_ties_rank0": P.U, "ties": T, "row_block_sharding": world,
+                       "l2": "per-iteration output (%.1f GB slab) exceeds L2" % (alg_bytes / 1e9),
+                       "elbo_cadence": "iter 1, every 10th, last (inside the timed region)"},
+            "iter_per_s": args.steps / (ms * 1e-3), "reports_per_s": args.steps * (2.0 * N - 1) * net.M * L / (ms * 1e-3),
+            "elbo_final": elbo_final, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clk.summary(),
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

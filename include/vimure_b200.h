@@ -181,6 +181,10 @@ int vm_phase_phi(const vm_ctx* c, void* stream);
  * statistics of the NEW rho into red3: A, the nu sum (model.py:820-830) and, with VM_F_ELBO, the ELBO sums. */
 int vm_phase_rho(const vm_ctx* c, int flags, void* stream);
 
+/* Measurement hook: launches ONLY the per-tie dense kernel of phase 3 (tables and special ties as left by the last
+ * vm_phase_rho), so that its duration can be timed in isolation for the roofline figure. Results are unchanged. */
+int vm_dense_only(const vm_ctx* c, int flags, void* stream);
+
 /* Phase 4 -- consumes (all-reduced) red3: A <- red3, `_update_nu` (model.py:820-830), refreshes the nu cache,
  * and with VM_F_ELBO assembles `__ELBO` (model.py:948-1019) into elbo_out[0]. */
 int vm_phase_finish(const vm_ctx* c, int flags, void* stream);

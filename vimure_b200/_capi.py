@@ -91,6 +91,7 @@ def load():
         "vm_phase_phi": (i, [P, vp]),
         "vm_phase_rho": (i, [P, i, vp]),
         "vm_phase_finish": (i, [P, i, vp]),
+        "vm_dense_only": (i, [P, i, vp]),
         "vm_iteration": (i, [P, i, vp]),
         "vm_run": (i, [P, i, i, i, vp]),
         "vm_materialize_prior": (i, [P, vp]),

@@ -174,6 +174,11 @@ class CaviEngine:
             self.rho_valid = not (flags & self.C["VM_F_NO_STORE"])
             self.rho_is_prior = False
 
+    def dense_only(self, flags=0):
+        """Launch only the per-tie dense kernel (measurement hook, see vm_dense_only)."""
+        _capi.check(self.lib.vm_dense_only(self._cref, int(flags), self._stream()), "vm_dense_only")
+        self.n_launch += 1
+
     def elbo(self):
         return float(self.elbo_out[0].item())
 

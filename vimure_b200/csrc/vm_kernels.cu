@@ -995,6 +995,15 @@ extern "C" int vm_phase_rho(const vm_ctx* c, int flags, void* stream) {
   return 0;
 }
 
+extern "C" int vm_dense_only(const vm_ctx* c, int flags, void* stream) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  DISPATCH_K(c->K, rc = launch_dense<K>(c, flags, (cudaStream_t)stream));
+  if (rc) return rc;
+  VM_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int vm_phase_finish(const vm_ctx* c, int flags, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
