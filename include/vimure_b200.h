@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VM_ABI_VERSION 3
+#define VM_ABI_VERSION 4
 
 /* reporter-mask structure (how R[l,i,j,m] is represented) */
 #define VM_R_EGO 0 /* reporter m == node m reports row m and column m (vimure synthetic.py:1184-1204, _io.py:229-242) */
@@ -62,6 +62,8 @@ extern "C" {
 
 /* maximum K compiled in */
 #define VM_MAX_K 8
+/* special ties handled by one block of the special-tie kernel (n_ublk = ceil(max per layer / this)) */
+#define VM_SPECIAL_TIES_PER_BLOCK 1024
 
 typedef struct vm_ctx {
   /* ---- dimensions ---- */
@@ -79,9 +81,10 @@ typedef struct vm_ctx {
   int64_t n_gchunk;         /* reporter chunks (gamma pass) */
   int64_t phi_chunk;        /* entries per block in the phi pass */
   int64_t n_phichunk;       /* max over layers of ceil(entries_in_layer/phi_chunk) */
-  int64_t n_ublk;           /* blocks of the special-tie kernel = ceil(U/256) */
+  int64_t n_ublk;           /* blocks per layer of the special-tie kernel */
   double eps;               /* EPS, model.py:215-218 */
   double alpha_eta, beta_eta;
+  double b_all;             /* sum of t_x: the eta part of the ELBO when no tie has underflowed completely */
 
   /* ---- special ties, sorted by (lrow, col) ---- */
   const int32_t* u_lrow;    /* [U] */
@@ -101,7 +104,9 @@ typedef struct vm_ctx {
   const int64_t* lay_eptr;  /* [L+1] entry range of each layer */
   const int64_t* g_chunk_ptr; /* [n_gchunk+1] ranges in reporter-sorted order */
   const int32_t* g_chunk_lm;  /* [n_gchunk] reporter id l*M+m */
-  const int32_t* g_perm;      /* [I] entry ids sorted by reporter */
+  const int32_t* g_u;         /* [I] reporter-sorted copies of e_u / e_x / e_xT (coalesced gamma pass) */
+  const float* g_x;           /* [I] */
+  const float* g_xT;          /* [I] */
   const int64_t* g_lm_cptr;   /* [L*M+1] chunk range of each reporter */
 
   /* ---- transposed-position list (ELBO eta term) ---- */
@@ -136,6 +141,7 @@ typedef struct vm_ctx {
   double* G_lambda;         /* [L*K] */
   double* E_lambda;         /* [L*K] */
   double* Elog_lambda;      /* [L*K] */
+  double* GE_theta;         /* [L*M*2] (G_theta, Elog_theta) interleaved: one 16-byte gather per X entry */
   double* A;                /* [L*M*K] sum of rho_k over the ties reported by (l,m) */
   double* rho_u;            /* [U*K] posterior of the special ties, fp64 */
   float* rho_u32;           /* [U*K] fp32 copy used to patch the dense slab */
@@ -148,6 +154,9 @@ typedef struct vm_ctx {
   float* tab_q;             /* [L*N*K] column part */
   float* rowpart;           /* [L*nloc*nct*K] */
   float* colpart;           /* [L*nrt*N*K] */
+  double* er_node;          /* [L*N] EGO: E[theta] of node n acting as reporter (0 if not an active reporter) */
+  double* colsum;           /* [L*M*K] column partials reduced over the row tiles */
+  int64_t* dev_flags;       /* [8] [0]: a special tie underflowed completely in the last rho update */
   double* blkpart;          /* [max(n_ublk, nct*L*nrt, L*n_phichunk*K, n_gchunk, ...)*4] */
   double* red1;             /* [L*M] gamma-shape sums (all-reduced by the host between phases when sharded) */
   double* red2;             /* [L*K] phi-shape sums */

@@ -14,6 +14,12 @@ import torch
 from . import _capi
 
 
+def _packing_const():
+    from ._packing import SPECIAL_TIES_PER_BLOCK
+
+    return SPECIAL_TIES_PER_BLOCK
+
+
 class CaviEngine:
     def __init__(self, packed, priors, mutuality=True, eps=1e-12, group=None, may_dead=False):
         P = self.P = packed
@@ -47,6 +53,7 @@ class CaviEngine:
         self.nu = z(self.C["VM_NU_LEN"])
         self.G_theta, self.E_theta, self.Elog_theta = z(L, M), z(L, M), z(L, M)
         self.G_lambda, self.E_lambda, self.Elog_lambda = z(L, K), z(L, K), z(L, K)
+        self.GE_theta = z(L, M, 2)
         U = P.U
         self.u_logpr = z(max(U, 1), K)
         self.rho_u = z(max(U, 1), K)
@@ -60,8 +67,12 @@ class CaviEngine:
         self.tab_q = torch.zeros(L * N * K, **f32)
         self.rowpart = torch.zeros(L * nloc * P.nct * K, **f32)
         self.colpart = torch.zeros(L * P.nrt * N * K, **f32)
+        self.er_node = z(L * N)
+        self.colsum = z(L * M * K)
+        self.dev_flags = torch.zeros(8, dtype=torch.int64, device=dev)
+        assert _packing_const() == self.C["VM_SPECIAL_TIES_PER_BLOCK"]
         n_blk = max(P.n_gchunk, L * P.n_phichunk * K,
-                    L * P.n_ublk * (4 + self.C["VM_MAX_K"]) + P.nct * L * P.nrt + 128 + 2 * 64) + 64
+                    L * P.n_ublk * (3 + self.C["VM_MAX_K"]) + P.nct * L * P.nrt + 128 + 2 * 64) + 64
         self.blkpart = z(n_blk)
         self.red1, self.red2 = z(L * M), z(L * K)
         self.red3 = z(L * M * K + self.C["VM_R3_EXTRA"])
@@ -77,6 +88,7 @@ class CaviEngine:
         c.may_dead = int(bool(may_dead))
         c.eps = float(eps)
         c.alpha_eta, c.beta_eta = self.alpha_eta, self.beta_eta
+        c.b_all = float(P.b_all)
         self._keep = []
 
         def ptr(t):
@@ -84,13 +96,14 @@ class CaviEngine:
             return t.data_ptr() if t.numel() else self._dummy.data_ptr()
 
         for name in ("u_lrow", "u_col", "u_ptr", "utile_ptr", "ucol_ptr", "ucol_perm", "e_u", "e_m", "e_x", "e_xT",
-                     "e_flags", "lay_eptr", "g_chunk_ptr", "g_chunk_lm", "g_perm", "g_lm_cptr", "t_u", "t_lrow",
+                     "e_flags", "lay_eptr", "g_chunk_ptr", "g_chunk_lm", "g_u", "g_x", "g_xT", "g_lm_cptr", "t_u", "t_lrow",
                      "t_col", "t_x", "rep", "r_ptr", "r_m", "r_val", "c_ptr", "c_tie"):
             setattr(c, name, ptr(P.t[name]) if name in P.t else self._dummy.data_ptr())
         for name in ("u_logpr", "alpha_theta", "beta_theta", "alpha_lambda", "beta_lambda", "gamma_shp", "gamma_rte",
                      "phi_shp", "phi_rte", "nu", "G_theta", "E_theta", "Elog_theta", "G_lambda", "E_lambda",
-                     "Elog_lambda", "rho_u", "rho_u32", "delta_u", "rho", "layer_consts", "tab_p", "tab_q", "rowpart",
-                     "colpart", "blkpart", "red1", "red2", "red3", "elbo_out"):
+                     "Elog_lambda", "GE_theta", "rho_u", "rho_u32", "delta_u", "rho", "layer_consts", "tab_p", "tab_q",
+                     "rowpart", "colpart", "er_node", "colsum", "dev_flags", "blkpart", "red1", "red2", "red3",
+                     "elbo_out"):
             setattr(c, name, ptr(getattr(self, name)))
         c.A = self.red3.data_ptr()  # A aliases the (all-reduced) statistics vector
         self._cref = ctypes.byref(c)
@@ -106,7 +119,8 @@ class CaviEngine:
 
     def kernels_per_iteration(self, elbo=False):
         """Number of kernels of this library launched by one iteration (for bench.py's gpu_launches)."""
-        n = 2 + 3 + 1 + (0 if self.P.r_mode == 2 else 1) + 3 + 1 + 1  # gamma(2) phi(3) rho: phi_finish,tables,special,dense,stats,sums ; finish
+        # gamma(2) phi(3) rho: phi_finish, [tables], special, dense, [col_reduce], stats, sums; finish(1)
+        n = 2 + 3 + 1 + (0 if self.P.r_mode == 2 else 1) + 2 + (1 if self.P.r_mode == 0 else 0) + 2 + 1
         if elbo:
             n += 1 + (1 if self.mutuality else 0)
         return n

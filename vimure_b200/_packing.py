@@ -17,6 +17,7 @@ import torch
 TILE_W = 1024
 GAMMA_CHUNK = 256
 PHI_CHUNK = 4096
+SPECIAL_TIES_PER_BLOCK = 1024  # == VM_SPECIAL_TIES_PER_BLOCK of include/vimure_b200.h
 
 
 def _i32(t):
@@ -128,7 +129,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64)
     P.t["ucol_ptr"] = torch.searchsorted(ck_sorted, torch.arange(L * N + 1, device=dev, dtype=torch.int64)).contiguous()
     n_ul = (P.t["utile_ptr"][:: nloc * P.nct][1:] - P.t["utile_ptr"][:: nloc * P.nct][:-1]) if U else None
     max_ul = int(n_ul.max()) if U else 0
-    P.n_ublk = max(1, (max_ul + 255) // 256)
+    P.n_ublk = max(1, (max_ul + SPECIAL_TIES_PER_BLOCK - 1) // SPECIAL_TIES_PER_BLOCK)
 
     # ---- layer ranges and reporter chunks of the entries
     lay_eptr = torch.searchsorted(tk_sorted, torch.arange(L + 1, device=dev, dtype=torch.int64) * (nloc * N))
@@ -140,6 +141,9 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64)
     lm = e_l * M + xm[sel]
     lm_sorted, gperm = torch.sort(lm, stable=True)
     P.t["g_perm"] = _i32(gperm)
+    P.t["g_u"] = P.t["e_u"][gperm].contiguous()
+    P.t["g_x"] = P.t["e_x"][gperm].contiguous()
+    P.t["g_xT"] = P.t["e_xT"][gperm].contiguous()
     cnt = torch.bincount(lm, minlength=L * M) if I else torch.zeros(L * M, dtype=torch.int64, device=dev)
     nch = (cnt + GAMMA_CHUNK - 1) // GAMMA_CHUNK
     cptr = torch.cat([nch.new_zeros(1), torch.cumsum(nch, 0)])
@@ -170,6 +174,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64)
     P.t["t_lrow"] = _i32(t_lrow)
     P.t["t_col"] = _i32(t_col)
     P.t["t_x"] = (xv[st] * in_RT[st]).to(torch.float32).contiguous()
+    P.b_all = float(P.t["t_x"].to(torch.float64).sum()) if P.IT else 0.0
 
     # ---- reporter mask
     P.r_mode = {"ego": 0, "all": 1, "coo": 2}[mask.kind]

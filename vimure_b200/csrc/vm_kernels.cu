@@ -4,10 +4,10 @@
 //   phase gamma : k_gamma_partial -> k_gamma_reduce                       (red1)
 //   phase phi   : k_gamma_finish -> k_phi_partial -> k_phi_reduce         (red2)
 //   phase rho   : k_phi_finish -> k_tables -> k_special<K> -> k_dense<K>  (the HBM-bound per-tie kernel)
-//                 -> k_stats_* -> k_sums_reduce                            (red3)
-//   phase finish: k_elbo_partial -> k_finish
+//                 -> k_col_reduce -> k_stats_* -> [k_elbo_b] -> k_sums_reduce   (red3)
+//   phase finish: [k_elbo_partial] -> k_finish
 // All reductions are two-pass (block partials, then a fixed-order second pass): results are bit-reproducible
-// run to run. No atomics anywhere.
+// run to run. No floating-point atomics anywhere.
 #include <stdio.h>
 
 #include "vm_common.cuh"
@@ -18,13 +18,19 @@
     if (e__ != cudaSuccess) return (int)e__;     \
   } while (0)
 
-#define UPART_STRIDE (4 + VM_MAX_K)  // per block of k_special: nu, cat, t2, spare, delta sums[K]
+// slots of the special-tie block partials, stored slot-major: part[slot * n_upart + block]
+#define UP_NU 0
+#define UP_CAT 1
+#define UP_T2 2
+#define UP_DELTA 3  // + k
+#define UP_SLOTS (3 + VM_MAX_K)
 
 // =====================================================================================================
 // phase gamma
 // =====================================================================================================
-// One warp per reporter chunk (<= 256 entries of one reporter (l,m)): sum_k rho_k * dz1_k per entry.
-// Replaces `_sp_uttkrp_theta` (model.py:851-859) whose python loop is 65% of the reference's CAVI time.
+// One warp per reporter chunk (<= 256 entries of one reporter (l,m), reporter-sorted copies => coalesced):
+// sum_k rho_k * dz1_k per entry.  Replaces `_sp_uttkrp_theta` (model.py:851-859), whose python loop is 65% of the
+// reference's CAVI time.
 template <int K>
 __global__ void __launch_bounds__(256) k_gamma_partial(const __grid_constant__ vm_ctx c, double* part) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -41,10 +47,9 @@ __global__ void __launch_bounds__(256) k_gamma_partial(const __grid_constant__ v
   double acc = 0.0;
   const int64_t p1 = c.g_chunk_ptr[chunk + 1];
   for (int64_t p = c.g_chunk_ptr[chunk] + lane; p < p1; p += 32) {
-    const int e = c.g_perm[p];
-    const int64_t u = c.e_u[e];
+    const int64_t u = c.g_u[p];
     double dz1[K], dz2[K];
-    vm_alloc<K>(mut, (double)c.e_x[e], (double)c.e_xT[e], Gth, Gl, Gnu, dz1, dz2);
+    vm_alloc<K>(mut, (double)c.g_x[p], (double)c.g_xT[p], Gth, Gl, Gnu, dz1, dz2);
 #pragma unroll
     for (int k = 0; k < K; ++k) acc += c.rho_u[u * K + k] * dz1[k];
   }
@@ -63,6 +68,16 @@ __global__ void k_gamma_reduce(const __grid_constant__ vm_ctx c, const double* p
 // =====================================================================================================
 // phase phi
 // =====================================================================================================
+__device__ __forceinline__ void vm_store_theta_cache(const vm_ctx& c, int64_t lm, double shp, double rte) {
+  const double el = vm_digamma(shp) - log(rte);
+  const double g = exp(el);
+  c.Elog_theta[lm] = el;
+  c.G_theta[lm] = g;
+  c.E_theta[lm] = shp / rte;
+  c.GE_theta[2 * lm] = g;
+  c.GE_theta[2 * lm + 1] = el;
+}
+
 // `_update_gamma` (model.py:698-718) from the (all-reduced) shape sums and A, then the theta part of
 // `_update_cache` (model.py:676).  gamma_rte[l,m] = beta + sum_k A[l,m,k] E[lambda_lk].
 template <int K>
@@ -77,10 +92,7 @@ __global__ void k_gamma_finish(const __grid_constant__ vm_ctx c) {
   const double rte = c.beta_theta[lm] + r;
   c.gamma_shp[lm] = shp;
   c.gamma_rte[lm] = rte;
-  const double el = vm_digamma(shp) - log(rte);
-  c.Elog_theta[lm] = el;
-  c.G_theta[lm] = exp(el);
-  c.E_theta[lm] = shp / rte;
+  vm_store_theta_cache(c, lm, shp, rte);
 }
 
 // `_sp_uttkrp_lambda` (model.py:880-887): per-layer sums of rho_k*dz1_k over the X entries (new theta cache).
@@ -155,6 +167,7 @@ __global__ void __launch_bounds__(256) k_phi_finish(const __grid_constant__ vm_c
   }
   emax = block_max<256>(emax, sm);
   if (threadIdx.x == 0) {
+    if (l == 0) c.dev_flags[0] = 0;
     double El[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -190,12 +203,7 @@ __global__ void __launch_bounds__(256) k_phi_finish(const __grid_constant__ vm_c
 // initial state has been injected.
 __global__ void k_refresh_cache(const __grid_constant__ vm_ctx c) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < c.L * c.M) {
-    const double el = vm_digamma(c.gamma_shp[t]) - log(c.gamma_rte[t]);
-    c.Elog_theta[t] = el;
-    c.G_theta[t] = exp(el);
-    c.E_theta[t] = c.gamma_shp[t] / c.gamma_rte[t];
-  }
+  if (t < c.L * c.M) vm_store_theta_cache(c, t, c.gamma_shp[t], c.gamma_rte[t]);
   if (t < c.L * c.K) {
     const double el = vm_digamma(c.phi_shp[t]) - log(c.phi_rte[t]);
     c.Elog_lambda[t] = el;
@@ -225,6 +233,7 @@ __global__ void k_tables(const __grid_constant__ vm_ctx c) {
     const int l = (int)(t / c.N), n = (int)(t - (int64_t)l * c.N);
     const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
     const double er = (c.r_mode == VM_R_EGO) ? vm_Er(c, l, n) : 0.0;
+    c.er_node[t] = er;
 #pragma unroll
     for (int k = 0; k < K; ++k) c.tab_q[t * K + k] = (float)(-er * lc[VM_LC_D(K, k)]);
   }
@@ -267,53 +276,74 @@ __device__ __forceinline__ void vm_tie_logodds(const vm_ctx& c, int l, int64_t l
 // ---- special ties (ties that carry X entries, and the diagonal): the full `_update_rho` in fp64 -------------
 // log rho_k = log(pr_k+EPS) + sum_{entries} dz1_k (E[log theta_m] + E[log lambda_k]) - S E[lambda_k]   (model.py:800-804,
 // 911-921), softmax over k (model.py:807-811), nu statistic (model.py:822-825), ELBO pieces (model.py:967-995, 1306-1313).
+// One thread per tie, VM_SPECIAL_TIES_PER_BLOCK ties per block (4 per thread, strided for coalescing).
 template <int K>
 __global__ void __launch_bounds__(256) k_special(const __grid_constant__ vm_ctx c, int flags, double* part) {
   __shared__ double sm[8];
   const int l = blockIdx.y;
   const int nloc = (int)c.nloc, nct = (int)c.nct;
   const int64_t u0 = c.utile_ptr[(int64_t)l * nloc * nct], u1 = c.utile_ptr[(int64_t)(l + 1) * nloc * nct];
-  const int64_t u = u0 + (int64_t)blockIdx.x * 256 + threadIdx.x;
-  const bool active = u < u1;
   const bool elbo = flags & VM_F_ELBO;
   const bool mut = c.mutuality != 0;
-  double nu_acc = 0.0, cat_acc = 0.0, t2_acc = 0.0;
-  double dlt[K];
+  const bool may_dead = vm_may_dead<K>(c, l);
+  const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
+  const double Gnu = c.nu[VM_NU_G];
+  double Gl[K], Ell[K], El[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) dlt[k] = 0.0;
-  if (active) {
+  for (int k = 0; k < K; ++k) {
+    Gl[k] = c.G_lambda[l * K + k];
+    Ell[k] = c.Elog_lambda[l * K + k];
+    El[k] = c.E_lambda[l * K + k];
+  }
+  double nu_acc = 0.0, cat_acc = 0.0, t2_acc = 0.0;
+  double dsum[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) dsum[k] = 0.0;
+
+  for (int rep_i = 0; rep_i < VM_SPECIAL_TIES_PER_BLOCK / 256; ++rep_i) {
+    const int64_t u = u0 + (int64_t)blockIdx.x * VM_SPECIAL_TIES_PER_BLOCK + rep_i * 256 + threadIdx.x;
+    if (u >= u1) continue;
     const int64_t lrow = c.u_lrow[u];
     const int i = (int)(lrow - (int64_t)l * nloc) + (int)c.row0, j = c.u_col[u];
     // S = sum over the tie's reporters of E[theta] * R.vals (model.py:766-792)
     double S;
     if (c.r_mode == VM_R_EGO) {
-      const double ti = vm_Er(c, l, i);
-      S = (i == j) ? (c.ego_diag ? ti : 0.0) : ti + vm_Er(c, l, j);
+      const double ti = c.er_node[(int64_t)l * c.N + i];
+      S = (i == j) ? (c.ego_diag ? ti : 0.0) : ti + c.er_node[(int64_t)l * c.N + j];
     } else if (c.r_mode == VM_R_ALL) {
-      S = c.layer_consts[(int64_t)l * VM_LC_STRIDE(K) + VM_LC_SALL(K)];
+      S = lc[VM_LC_SALL(K)];
     } else {
       S = 0.0;
       const int64_t tie = lrow * c.N + j;
       for (int64_t e = c.r_ptr[tie]; e < c.r_ptr[tie + 1]; ++e)
         S += c.E_theta[(int64_t)l * c.M + c.r_m[e]] * (double)c.r_val[e];
     }
-    double Gl[K], Ell[K], lw[K], logpr[K];
-    const double Gnu = c.nu[VM_NU_G];
+    double lw[K], logpr[K], Dz[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      Gl[k] = c.G_lambda[l * K + k];
-      Ell[k] = c.Elog_lambda[l * K + k];
       logpr[k] = c.u_logpr[u * K + k];
-      lw[k] = logpr[k] - S * c.E_lambda[l * K + k];
+      lw[k] = logpr[k] - S * El[k];
+      Dz[k] = 0.0;
     }
     const int64_t e0 = c.u_ptr[u], e1 = c.u_ptr[u + 1];
     for (int64_t e = e0; e < e1; ++e) {
       const int64_t lm = (int64_t)l * c.M + c.e_m[e];
-      double dz1[K], dz2[K];
-      vm_alloc<K>(mut, (double)c.e_x[e], (double)c.e_xT[e], c.G_theta[lm], Gl, Gnu, dz1, dz2);
-      const double et = c.Elog_theta[lm];
+      const double2 ge = *reinterpret_cast<const double2*>(c.GE_theta + 2 * lm);  // (G_theta, Elog_theta)
+      const double x = (double)c.e_x[e];
+      if (mut) {
+        const double z2 = Gnu * (double)c.e_xT[e];
 #pragma unroll
-      for (int k = 0; k < K; ++k) lw[k] += dz1[k] * (et + Ell[k]);
+        for (int k = 0; k < K; ++k) {
+          const double z1 = ge.x * Gl[k];
+          const double den = z1 + z2;
+          const double xi = (den == 0.0) ? 0.0 : x / den;  // model.py:692 (Q5)
+          lw[k] += (xi * z1) * (ge.y + Ell[k]);
+          Dz[k] += xi * z2;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) lw[k] += x * (ge.y + Ell[k]);
+      }
     }
     double mx = lw[0];
 #pragma unroll
@@ -322,6 +352,7 @@ __global__ void __launch_bounds__(256) k_special(const __grid_constant__ vm_ctx 
     if (mx < VM_DEAD_LN) {
 #pragma unroll
       for (int k = 0; k < K; ++k) rho[k] = 0.0;
+      c.dev_flags[0] = 1;  // benign race: every writer stores the same value
     } else {
       double s = 0.0;
 #pragma unroll
@@ -329,76 +360,82 @@ __global__ void __launch_bounds__(256) k_special(const __grid_constant__ vm_ctx 
         rho[k] = exp(lw[k] - mx);
         s += rho[k];
       }
+      const double inv = 1.0 / s;
 #pragma unroll
-      for (int k = 0; k < K; ++k) rho[k] /= s;
+      for (int k = 0; k < K; ++k) rho[k] *= inv;
     }
-    // second sweep over the entries: nu statistic and the log-Poisson-mean ELBO term (uses exp(rho), Q1)
-    if (mut || elbo) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) nu_acc += Dz[k] * rho[k];  // sum_e sum_k dz2_k rho_k (model.py:822-825)
+    // closed-form value the dense kernel uses for this tie: subtract it again from the statistics
+    float a[K], f[K], epsr;
+    bool dead;
+    vm_tie_logodds<K>(c, l, lrow, j, a);
+    vm_formula_rho<K>(a, may_dead, f, epsr, dead);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double d = rho[k] - (double)f[k];
+      c.rho_u[u * K + k] = rho[k];
+      c.rho_u32[u * K + k] = (float)rho[k];
+      c.delta_u[u * K + k] = d;
+      dsum[k] += d;
+    }
+    if (elbo) {
+      // log-Poisson-mean term: uses exp(rho) (Q1) and only the entries that are also in R (model.py:967-995)
       double erho[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) erho[k] = exp(rho[k]);
       for (int64_t e = e0; e < e1; ++e) {
         const int64_t lm = (int64_t)l * c.M + c.e_m[e];
-        const double x = (double)c.e_x[e], xT = (double)c.e_xT[e], Gth = c.G_theta[lm];
-        double dz1[K], dz2[K];
-        vm_alloc<K>(mut, x, xT, Gth, Gl, Gnu, dz1, dz2);
+        const double Gth = c.GE_theta[2 * lm], x = (double)c.e_x[e], z2 = Gnu * (double)c.e_xT[e];
+        double val = 0.0;
+        if (c.e_flags[e] & 1) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) nu_acc += dz2[k] * rho[k];
-        if (elbo) {
-          double val = 0.0;
-          if (c.e_flags[e] & 1) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) val += erho[k] * (Gth * Gl[k] + Gnu * xT);
-          }
-          t2_acc += x * log(val + c.eps);
+          for (int k = 0; k < K; ++k) val += erho[k] * (Gth * Gl[k] + z2);
         }
+        t2_acc += x * log(val + c.eps);
       }
-    }
-    // closed-form value the dense kernel uses for this tie: subtract it again from the statistics
-    float a[K], f[K], epsr;
-    bool dead;
-    vm_tie_logodds<K>(c, l, lrow, j, a);
-    vm_formula_rho<K>(a, vm_may_dead<K>(c, l), f, epsr, dead);
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      c.rho_u[u * K + k] = rho[k];
-      c.rho_u32[u * K + k] = (float)rho[k];
-      dlt[k] = rho[k] - (double)f[k];
-      c.delta_u[u * K + k] = dlt[k];
-    }
-    if (elbo) {
-      const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
 #pragma unroll
       for (int k = 0; k < K; ++k) cat_acc += rho[k] * (logpr[k] - log(rho[k] + c.eps));
       cat_acc -= (double)vm_formula_cat<K>(f, epsr, dead, (float)lc[VM_LC_LP0(K)], (float)lc[VM_LC_LPK(K)],
                                             (float)c.eps);
     }
   }
-  double* out = part + ((int64_t)l * c.n_ublk + blockIdx.x) * UPART_STRIDE;
+  const int64_t nup = c.L * c.n_ublk, b = (int64_t)l * c.n_ublk + blockIdx.x;
   double v;
   v = block_sum<256>(nu_acc, sm);
-  if (threadIdx.x == 0) out[0] = v;
-  v = block_sum<256>(cat_acc, sm);
-  if (threadIdx.x == 0) out[1] = v;
-  v = block_sum<256>(t2_acc, sm);
-  if (threadIdx.x == 0) out[2] = v;
+  if (threadIdx.x == 0) part[UP_NU * nup + b] = v;
+  if (elbo) {
+    v = block_sum<256>(cat_acc, sm);
+    if (threadIdx.x == 0) part[UP_CAT * nup + b] = v;
+    v = block_sum<256>(t2_acc, sm);
+    if (threadIdx.x == 0) part[UP_T2 * nup + b] = v;
+  }
   if (c.r_mode == VM_R_ALL) {  // the all-reporter statistics only need per-layer totals of delta
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      v = block_sum<256>(dlt[k], sm);
-      if (threadIdx.x == 0) out[4 + k] = v;
+      v = block_sum<256>(dsum[k], sm);
+      if (threadIdx.x == 0) part[(UP_DELTA + k) * nup + b] = v;
     }
   }
 }
 
 // ---- the per-tie dense kernel: every owned tie, closed form, fp32 slab write + statistics partials -------------
 // HBM-bound: writes 4*K bytes per tie, reads only the (L2-resident) tables.  256 threads x 4 consecutive ties
-// = one 1024-tie row segment per step, tile_h rows per CTA.  Per row it (1) evaluates the closed form,
-// (2) stores it with 128-bit stores, (3) patches the special ties of the segment with their fp64-computed values
-// (same CTA, after a barrier: the sectors are still dirty in L2, so no extra DRAM traffic), (4) emits the row
-// partial; column partials are kept in registers across the rows and written once per CTA.
+// = one 1024-tie row segment per step, tile_h rows per CTA, processed in batches of RB rows.  Per batch:
+// (1) every thread evaluates the closed form for its 4 ties of each row, stores them with 128-bit stores, keeps the
+// column sums in registers and drops its per-row partial into shared memory; (2) after ONE barrier, warp w
+// patches the special ties of row w with their fp64-computed values (same CTA, after the barrier: the sectors are
+// still dirty in L2, so no extra DRAM traffic) and reduces row w's partials.  Column partials are written once
+// per CTA.  The tile pointers of the batch are prefetched before the arithmetic.
+template <int K>
+struct DenseCfg {
+  static constexpr int RB = (K <= 4) ? 8 : 4;  // rows per batch ((K-1)*RB KB of shared memory)
+};
+
 template <int K, bool ELBO, bool STORE, bool CSR>
 __global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constant__ vm_ctx c, double* catpart) {
+  constexpr int RB = DenseCfg<K>::RB;
+  constexpr int NW = VM_DENSE_THREADS / 32;
   const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
   const int ct = blockIdx.x;
   const int l = blockIdx.y / nrt, rt = blockIdx.y - l * nrt;
@@ -407,7 +444,8 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constan
   const int i_lo = rt * (int)c.tile_h, i_hi = min(i_lo + (int)c.tile_h, nloc);
   const bool may_dead = vm_may_dead<K>(c, l);
   const bool vec_ok = ((((int64_t)N * K) & 3) == 0) && (j0 + 3 < N);
-  __shared__ float sm_row[2][VM_DENSE_THREADS / 32][K];
+  __shared__ float rowbuf[K - 1][RB][VM_DENSE_THREADS];
+  __shared__ int rowdead[RB];
   __shared__ double sm_red[8];
 
   const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
@@ -428,79 +466,100 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constan
     for (int t = 0; t < 4; ++t) colacc[k][t] = 0.f;
   double cat = 0.0;
 
-  for (int i = i_lo; i < i_hi; ++i) {
-    const int64_t lrow = (int64_t)l * nloc + i;
-    float p[K];
+  for (int ib = i_lo; ib < i_hi; ib += RB) {
+    // tile pointers of the row this warp will patch
+    int ua = 0, ub = 0;
+    const bool my_row = warp < RB && ib + warp < i_hi;
+    const int64_t lrow_w = (int64_t)l * nloc + ib + warp;
+    if (STORE && my_row) {
+      ua = __ldg(&c.utile_ptr[lrow_w * nct + ct]);
+      ub = __ldg(&c.utile_ptr[lrow_w * nct + ct + 1]);
+    }
+    if (may_dead && tid < RB) rowdead[tid] = 0;
+    if (may_dead) __syncthreads();
 #pragma unroll
-    for (int k = 0; k < K; ++k) p[k] = CSR ? 0.f : __ldg(&c.tab_p[lrow * K + k]);
-    float o[4 * K], rowacc[K];
+    for (int r = 0; r < RB; ++r) {
+      const int i = ib + r;
+      float rowacc[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) rowacc[k] = 0.f;
+      for (int k = 0; k < K; ++k) rowacc[k] = 0.f;
+      if (i < i_hi) {
+        const int64_t lrow = (int64_t)l * nloc + i;
+        float p[K];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const bool valid = j0 + t < N;
-      float a[K];
-      if (CSR) {
-        const float s = valid ? vm_csr_S32(c, l, lrow * N + j0 + t) : 0.f;
+        for (int k = 0; k < K; ++k) p[k] = CSR ? 0.f : __ldg(&c.tab_p[lrow * K + k]);
+        float o[4 * K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) a[k] = valid ? __fmaf_rn(-s, dd[k], cc[k]) : -INFINITY;
-      } else {
+        for (int t = 0; t < 4; ++t) {
+          const bool valid = j0 + t < N;
+          float a[K];
+          if (CSR) {
+            const float s = valid ? vm_csr_S32(c, l, lrow * N + j0 + t) : 0.f;
 #pragma unroll
-        for (int k = 0; k < K; ++k) a[k] = __fadd_rn(p[k], q[k][t]);
+            for (int k = 0; k < K; ++k) a[k] = valid ? __fmaf_rn(-s, dd[k], cc[k]) : -INFINITY;
+          } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) a[k] = __fadd_rn(p[k], q[k][t]);
+          }
+          float epsr;
+          bool dead;
+          vm_formula_rho<K>(a, may_dead, &o[t * K], epsr, dead);
+          if (!CSR) {
+#pragma unroll
+            for (int k = 1; k < K; ++k) {
+              colacc[k][t] += o[t * K + k];
+              rowacc[k] += o[t * K + k];
+            }
+            if (may_dead && dead && valid) {
+              colacc[0][t] += 1.f;
+              atomicAdd(&rowdead[r], 1);
+            }
+          }
+          if (ELBO && valid) cat += (double)vm_formula_cat<K>(&o[t * K], epsr, dead, lp0, lpk, epsf);
+        }
+        if (STORE) {
+          float* dst = c.rho + (lrow * N + j0) * K;
+          if (vec_ok) {
+#pragma unroll
+            for (int v = 0; v < K; ++v)
+              reinterpret_cast<float4*>(dst)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (j0 + t < N) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) dst[t * K + k] = o[t * K + k];
+              }
+          }
+        }
       }
-      float epsr;
-      bool dead;
-      vm_formula_rho<K>(a, may_dead, &o[t * K], epsr, dead);
       if (!CSR) {
 #pragma unroll
-        for (int k = 1; k < K; ++k) {
-          colacc[k][t] += o[t * K + k];
-          rowacc[k] += o[t * K + k];
-        }
-        if (may_dead && dead && valid) {
-          colacc[0][t] += 1.f;
-          rowacc[0] += 1.f;
-        }
-      }
-      if (ELBO && valid) cat += (double)vm_formula_cat<K>(&o[t * K], epsr, dead, lp0, lpk, epsf);
-    }
-    if (STORE) {
-      float* dst = c.rho + (lrow * N + j0) * K;
-      if (vec_ok) {
-#pragma unroll
-        for (int v = 0; v < K; ++v)
-          reinterpret_cast<float4*>(dst)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
-      } else {
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-          if (j0 + t < N) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) dst[t * K + k] = o[t * K + k];
-          }
-      }
-    }
-    if (!CSR) {
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const float v = warp_sum(rowacc[k]);
-        if (lane == 0) sm_row[i & 1][warp][k] = v;
+        for (int k = 1; k < K; ++k) rowbuf[k - 1][r][tid] = rowacc[k];
       }
     }
     __syncthreads();
-    if (STORE) {
-      const int ua = c.utile_ptr[lrow * nct + ct], ub = c.utile_ptr[lrow * nct + ct + 1];
-      for (int u = ua + tid; u < ub; u += VM_DENSE_THREADS) {
-        float* dst = c.rho + (lrow * N + c.u_col[u]) * K;
+    if (my_row) {
+      if (STORE) {
+        for (int u = ua + lane; u < ub; u += 32) {
+          float* dst = c.rho + (lrow_w * N + c.u_col[u]) * K;
 #pragma unroll
-        for (int k = 0; k < K; ++k) dst[k] = c.rho_u32[(int64_t)u * K + k];
+          for (int k = 0; k < K; ++k) dst[k] = c.rho_u32[(int64_t)u * K + k];
+        }
+      }
+      if (!CSR) {
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+          float v = 0.f;
+#pragma unroll
+          for (int s = 0; s < NW; ++s) v += rowbuf[k - 1][warp][lane + 32 * s];
+          v = warp_sum(v);
+          if (lane == 0) c.rowpart[(lrow_w * nct + ct) * K + k] = v;
+        }
+        if (lane == 0) c.rowpart[(lrow_w * nct + ct) * K] = may_dead ? (float)rowdead[warp] : 0.f;
       }
     }
-    if (!CSR && tid < K) {
-      float v = 0.f;
-#pragma unroll
-      for (int w = 0; w < VM_DENSE_THREADS / 32; ++w) v += sm_row[i & 1][w][tid];
-      c.rowpart[(lrow * nct + ct) * K + tid] = v;
-    }
+    __syncthreads();
   }
   if (!CSR) {
 #pragma unroll
@@ -516,7 +575,21 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constan
   }
 }
 
+
 // ---- statistics of the new rho: A[l,m,k] = sum of rho_k over the ties reported by (l,m) ------------------------
+// column partials of the dense kernel summed over the row tiles (coalesced: consecutive threads = consecutive (m,k))
+template <int K>
+__global__ void k_col_reduce(const __grid_constant__ vm_ctx c) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= c.L * c.M * K) return;
+  const int64_t lm = t / K;
+  const int k = (int)(t - lm * K);
+  const int l = (int)(lm / c.M), m = (int)(lm - (int64_t)l * c.M);
+  double s = 0.0;
+  for (int64_t rt = 0; rt < c.nrt; ++rt) s += (double)c.colpart[((l * c.nrt + rt) * c.N + m) * K + k];
+  c.colsum[t] = s;
+}
+
 // ego mask: row sums + column sums of the closed form (dense partials) + the special-tie corrections.
 // One warp per reporter; fixed summation order.
 template <int K>
@@ -530,7 +603,7 @@ __global__ void __launch_bounds__(256) k_stats_ego(const __grid_constant__ vm_ct
     return;
   }
   const int l = (int)(lm / c.M), m = (int)(lm - (int64_t)l * c.M);
-  const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
+  const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct;
   const bool local = m >= c.row0 && m < c.row0 + nloc;
   const int64_t lrow = (int64_t)l * nloc + (m - c.row0);
   double f[K], d[K];
@@ -542,19 +615,19 @@ __global__ void __launch_bounds__(256) k_stats_ego(const __grid_constant__ vm_ct
 #pragma unroll
         for (int k = 0; k < K; ++k) f[k] += (double)c.rowpart[(lrow * nct + t) * K + k];
       }
-    for (int t = lane; t < nrt; t += 32) {
+    if (lane == 0) {
 #pragma unroll
-      for (int k = 0; k < K; ++k) f[k] += (double)c.colpart[(((int64_t)l * nrt + t) * N + m) * K + k];
-    }
-    if (local && lane == 0) {  // the (m,m) tie is in the row AND the column sums
-      float a[K], g[K], epsr;
-      bool dead;
-      vm_tie_logodds<K>(c, l, lrow, m, a);
-      vm_formula_rho<K>(a, vm_may_dead<K>(c, l), g, epsr, dead);
-      const double w = c.ego_diag ? 1.0 : 2.0;
+      for (int k = 0; k < K; ++k) f[k] += c.colsum[lm * K + k];
+      if (local) {  // the (m,m) tie is in the row AND the column sums
+        float a[K], g[K], epsr;
+        bool dead;
+        vm_tie_logodds<K>(c, l, lrow, m, a);
+        vm_formula_rho<K>(a, vm_may_dead<K>(c, l), g, epsr, dead);
+        const double w = c.ego_diag ? 1.0 : 2.0;
 #pragma unroll
-      for (int k = 1; k < K; ++k) f[k] -= w * (double)g[k];
-      if (dead) f[0] -= w;
+        for (int k = 1; k < K; ++k) f[k] -= w * (double)g[k];
+        if (dead) f[0] -= w;
+      }
     }
   }
   if (local) {
@@ -593,7 +666,7 @@ __global__ void __launch_bounds__(256) k_stats_all(const __grid_constant__ vm_ct
   __shared__ double sm[8];
   __shared__ double tot[K];
   const int l = blockIdx.x;
-  const int64_t nrow = c.nloc * c.nct;
+  const int64_t nrow = c.nloc * c.nct, nup = c.L * c.n_ublk;
   double f[K], d[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) f[k] = d[k] = 0.0;
@@ -604,7 +677,7 @@ __global__ void __launch_bounds__(256) k_stats_all(const __grid_constant__ vm_ct
     }
   for (int64_t b = threadIdx.x; b < c.n_ublk; b += 256) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) d[k] += upart[((int64_t)l * c.n_ublk + b) * UPART_STRIDE + 4 + k];
+    for (int k = 0; k < K; ++k) d[k] += upart[(UP_DELTA + k) * nup + (int64_t)l * c.n_ublk + b];
   }
   double fs[K], ds[K];
 #pragma unroll
@@ -660,27 +733,39 @@ __global__ void __launch_bounds__(256) k_init_delta_all(const __grid_constant__ 
   __shared__ double sm[8];
   const int l = blockIdx.y;
   const int64_t u0 = c.utile_ptr[(int64_t)l * c.nloc * c.nct], u1 = c.utile_ptr[(int64_t)(l + 1) * c.nloc * c.nct];
-  const int64_t u = u0 + (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t nup = c.L * c.n_ublk;
   for (int k = 0; k < (int)c.K; ++k) {
-    const double v = block_sum<256>(u < u1 ? c.delta_u[u * c.K + k] : 0.0, sm);
-    if (threadIdx.x == 0) upart[((int64_t)l * c.n_ublk + blockIdx.x) * UPART_STRIDE + 4 + k] = v;
+    double acc = 0.0;
+    for (int r = 0; r < VM_SPECIAL_TIES_PER_BLOCK / 256; ++r) {
+      const int64_t u = u0 + (int64_t)blockIdx.x * VM_SPECIAL_TIES_PER_BLOCK + r * 256 + threadIdx.x;
+      if (u < u1) acc += c.delta_u[u * c.K + k];
+    }
+    const double v = block_sum<256>(acc, sm);
+    if (threadIdx.x == 0) upart[(UP_DELTA + k) * nup + (int64_t)l * c.n_ublk + blockIdx.x] = v;
   }
 }
 
 // ELBO eta part: B = sum over X entries whose transposed position is reported of x * sum_k rho_k[transposed tie]
-// (model.py:1269-1290); sum_k rho_k is 1 for a live tie and 0 for a fully-underflowed one (Q3).
+// (model.py:1269-1290); sum_k rho_k is 1 for a live tie and 0 for a fully-underflowed one (Q3).  The kernel sums
+// the x of the DEAD positions (B = b_all - that); it exits at once when no tie can have underflowed.
 template <int K>
 __global__ void __launch_bounds__(256) k_elbo_b(const __grid_constant__ vm_ctx c, double* part) {
   __shared__ double sm[8];
+  bool any = c.dev_flags[0] != 0 || c.may_dead != 0;
+  for (int l = 0; l < (int)c.L && !any; ++l) any = c.layer_consts[(int64_t)l * VM_LC_STRIDE(K) + VM_LC_DEAD(K)] != 0.0;
+  if (!any) {
+    if (threadIdx.x == 0) part[blockIdx.x] = 0.0;
+    return;
+  }
   double acc = 0.0;
   for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < c.IT; t += (int64_t)gridDim.x * 256) {
     const int u = c.t_u[t];
     bool alive = true;
     if (u >= 0) {
-      double s = 0.0;
+      float s = 0.f;
 #pragma unroll
-      for (int k = 0; k < K; ++k) s += c.rho_u[(int64_t)u * K + k];
-      alive = s > 0.0;
+      for (int k = 0; k < K; ++k) s += c.rho_u32[(int64_t)u * K + k];
+      alive = s > 0.f;
     } else {
       const int64_t lrow = c.t_lrow[t];
       const int l = (int)(lrow / c.nloc);
@@ -692,37 +777,40 @@ __global__ void __launch_bounds__(256) k_elbo_b(const __grid_constant__ vm_ctx c
         alive = !dead;
       }
     }
-    if (alive) acc += (double)c.t_x[t];
+    if (!alive) acc += (double)c.t_x[t];
   }
   const double v = block_sum<256>(acc, sm);
   if (threadIdx.x == 0) part[blockIdx.x] = v;
 }
 
 // second pass over the scalar partials: nu, cat, t2 (special-tie blocks), cat (dense blocks), B
-__global__ void __launch_bounds__(256) k_sums_reduce(const __grid_constant__ vm_ctx c, int flags, const double* upart,
-                                                     int64_t n_upart, const double* catpart, int64_t n_cat,
-                                                     const double* bpart, int64_t n_b) {
-  __shared__ double sm[8];
+__global__ void __launch_bounds__(1024) k_sums_reduce(const __grid_constant__ vm_ctx c, int flags, const double* upart,
+                                                      int64_t n_upart, const double* catpart, int64_t n_cat,
+                                                      const double* bpart, int64_t n_b) {
+  __shared__ double sm[32];
   double nu = 0.0, cat = 0.0, t2 = 0.0, b = 0.0;
-  for (int64_t q = threadIdx.x; q < n_upart; q += 256) {
-    nu += upart[q * UPART_STRIDE + 0];
-    cat += upart[q * UPART_STRIDE + 1];
-    t2 += upart[q * UPART_STRIDE + 2];
+  const bool elbo = flags & VM_F_ELBO;
+  for (int64_t q = threadIdx.x; q < n_upart; q += 1024) {
+    nu += upart[UP_NU * n_upart + q];
+    if (elbo) {
+      cat += upart[UP_CAT * n_upart + q];
+      t2 += upart[UP_T2 * n_upart + q];
+    }
   }
-  if (flags & VM_F_ELBO) {
-    for (int64_t q = threadIdx.x; q < n_cat; q += 256) cat += catpart[q];
-    for (int64_t q = threadIdx.x; q < n_b; q += 256) b += bpart[q];
+  if (elbo) {
+    for (int64_t q = threadIdx.x; q < n_cat; q += 1024) cat += catpart[q];
+    for (int64_t q = threadIdx.x; q < n_b; q += 1024) b += bpart[q];
   }
-  nu = block_sum<256>(nu, sm);
-  cat = block_sum<256>(cat, sm);
-  t2 = block_sum<256>(t2, sm);
-  b = block_sum<256>(b, sm);
+  nu = block_sum<1024>(nu, sm);
+  cat = block_sum<1024>(cat, sm);
+  t2 = block_sum<1024>(t2, sm);
+  b = block_sum<1024>(b, sm);
   if (threadIdx.x == 0) {
     double* ex = c.red3 + c.L * c.M * c.K;
     ex[VM_R3_NU] = nu;
     ex[VM_R3_CAT] = cat;
     ex[VM_R3_T2] = t2;
-    ex[VM_R3_B] = b;
+    ex[VM_R3_B] = elbo ? c.b_all - b : 0.0;
   }
 }
 
@@ -837,7 +925,7 @@ static inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 // blkpart regions (doubles)
 static inline double* region_u(const vm_ctx* c) { return c->blkpart; }  // special-tie block partials
 static inline int64_t n_upart(const vm_ctx* c) { return c->L * c->n_ublk; }
-static inline double* region_cat(const vm_ctx* c) { return c->blkpart + n_upart(c) * UPART_STRIDE; }
+static inline double* region_cat(const vm_ctx* c) { return c->blkpart + n_upart(c) * UP_SLOTS; }
 static inline int64_t n_catpart(const vm_ctx* c) { return c->nct * c->L * c->nrt; }
 static inline double* region_b(const vm_ctx* c) { return region_cat(c) + n_catpart(c); }
 #define VM_B_BLOCKS 128
@@ -887,6 +975,7 @@ template <int K>
 static int launch_stats(const vm_ctx* c, int init, cudaStream_t st) {
   const int64_t LM = c->L * c->M;
   if (c->r_mode == VM_R_EGO) {
+    if (!init) k_col_reduce<K><<<(unsigned)cdiv(LM * K, 256), 256, 0, st>>>(*c);
     k_stats_ego<K><<<(unsigned)cdiv(LM, 8), 256, 0, st>>>(*c, init);
   } else if (c->r_mode == VM_R_ALL) {
     k_stats_all<K><<<(unsigned)c->L, 256, 0, st>>>(*c, init, region_u(c));
@@ -989,7 +1078,7 @@ extern "C" int vm_phase_rho(const vm_ctx* c, int flags, void* stream) {
     DISPATCH_K(c->K, (k_elbo_b<K><<<VM_B_BLOCKS, 256, 0, st>>>(*c, region_b(c))));
     VM_CHECK_LAUNCH();
   }
-  k_sums_reduce<<<1, 256, 0, st>>>(*c, flags, region_u(c), n_upart(c), region_cat(c), n_catpart(c), region_b(c),
+  k_sums_reduce<<<1, 1024, 0, st>>>(*c, flags, region_u(c), n_upart(c), region_cat(c), n_catpart(c), region_b(c),
                                    c->mutuality ? VM_B_BLOCKS : 0);
   VM_CHECK_LAUNCH();
   return 0;
