@@ -278,8 +278,9 @@ __device__ __forceinline__ void vm_tie_logodds(const vm_ctx& c, int l, int64_t l
 // 911-921), softmax over k (model.py:807-811), nu statistic (model.py:822-825), ELBO pieces (model.py:967-995, 1306-1313).
 // One thread per tie, VM_SPECIAL_TIES_PER_BLOCK ties per block (4 per thread, strided for coalescing).
 template <int K>
-__global__ void __launch_bounds__(256) k_special(const __grid_constant__ vm_ctx c, int flags, double* part) {
+__global__ void __launch_bounds__(256, (K <= 2 ? 3 : 2)) k_special(const __grid_constant__ vm_ctx c, int flags, double* part) {
   __shared__ double sm[8];
+  __shared__ double s_Gl[K], s_Ell[K], s_El[K];
   const int l = blockIdx.y;
   const int nloc = (int)c.nloc, nct = (int)c.nct;
   const int64_t u0 = c.utile_ptr[(int64_t)l * nloc * nct], u1 = c.utile_ptr[(int64_t)(l + 1) * nloc * nct];
@@ -288,28 +289,55 @@ __global__ void __launch_bounds__(256) k_special(const __grid_constant__ vm_ctx 
   const bool may_dead = vm_may_dead<K>(c, l);
   const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
   const double Gnu = c.nu[VM_NU_G];
-  double Gl[K], Ell[K], El[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    Gl[k] = c.G_lambda[l * K + k];
-    Ell[k] = c.Elog_lambda[l * K + k];
-    El[k] = c.E_lambda[l * K + k];
+  if (threadIdx.x < K) {
+    s_Gl[threadIdx.x] = c.G_lambda[l * K + threadIdx.x];
+    s_Ell[threadIdx.x] = c.Elog_lambda[l * K + threadIdx.x];
+    s_El[threadIdx.x] = c.E_lambda[l * K + threadIdx.x];
   }
+  __syncthreads();
   double nu_acc = 0.0, cat_acc = 0.0, t2_acc = 0.0;
   double dsum[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) dsum[k] = 0.0;
 
-  for (int rep_i = 0; rep_i < VM_SPECIAL_TIES_PER_BLOCK / 256; ++rep_i) {
-    const int64_t u = u0 + (int64_t)blockIdx.x * VM_SPECIAL_TIES_PER_BLOCK + rep_i * 256 + threadIdx.x;
-    if (u >= u1) continue;
-    const int64_t lrow = c.u_lrow[u];
-    const int i = (int)(lrow - (int64_t)l * nloc) + (int)c.row0, j = c.u_col[u];
+  constexpr int TPT = VM_SPECIAL_TIES_PER_BLOCK / 256;
+  const int64_t ub = u0 + (int64_t)blockIdx.x * VM_SPECIAL_TIES_PER_BLOCK + threadIdx.x;
+  // index data of the first tie; the next tie's is fetched while the current one is processed
+  int n_lrow = 0, n_col = 0;
+  int64_t n_e0 = 0, n_e1 = 0;
+  if (ub < u1) {
+    n_lrow = c.u_lrow[ub];
+    n_col = c.u_col[ub];
+    n_e0 = c.u_ptr[ub];
+    n_e1 = c.u_ptr[ub + 1];
+  }
+#pragma unroll 1
+  for (int it = 0; it < TPT; ++it) {
+    const int64_t u = ub + it * 256;
+    if (u >= u1) break;
+    const int64_t lrow = n_lrow;
+    const int j = n_col;
+    const int64_t e0 = n_e0, e1 = n_e1;
+    const int64_t un = u + 256;
+    if (it + 1 < TPT && un < u1) {
+      n_lrow = c.u_lrow[un];
+      n_col = c.u_col[un];
+      n_e0 = c.u_ptr[un];
+      n_e1 = c.u_ptr[un + 1];
+    }
+    const int i = (int)(lrow - (int64_t)l * nloc) + (int)c.row0;
+    // independent loads first: prior, closed-form tables, reporter expectations
+    double logpr[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) logpr[k] = c.u_logpr[u * K + k];
+    float a[K];
+    vm_tie_logodds<K>(c, l, lrow, j, a);
     // S = sum over the tie's reporters of E[theta] * R.vals (model.py:766-792)
     double S;
     if (c.r_mode == VM_R_EGO) {
       const double ti = c.er_node[(int64_t)l * c.N + i];
-      S = (i == j) ? (c.ego_diag ? ti : 0.0) : ti + c.er_node[(int64_t)l * c.N + j];
+      const double tj = c.er_node[(int64_t)l * c.N + j];
+      S = (i == j) ? (c.ego_diag ? ti : 0.0) : ti + tj;
     } else if (c.r_mode == VM_R_ALL) {
       S = lc[VM_LC_SALL(K)];
     } else {
@@ -318,14 +346,12 @@ __global__ void __launch_bounds__(256) k_special(const __grid_constant__ vm_ctx 
       for (int64_t e = c.r_ptr[tie]; e < c.r_ptr[tie + 1]; ++e)
         S += c.E_theta[(int64_t)l * c.M + c.r_m[e]] * (double)c.r_val[e];
     }
-    double lw[K], logpr[K], Dz[K];
+    double lw[K], Dz[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      logpr[k] = c.u_logpr[u * K + k];
-      lw[k] = logpr[k] - S * El[k];
+      lw[k] = logpr[k] - S * s_El[k];
       Dz[k] = 0.0;
     }
-    const int64_t e0 = c.u_ptr[u], e1 = c.u_ptr[u + 1];
     for (int64_t e = e0; e < e1; ++e) {
       const int64_t lm = (int64_t)l * c.M + c.e_m[e];
       const double2 ge = *reinterpret_cast<const double2*>(c.GE_theta + 2 * lm);  // (G_theta, Elog_theta)
@@ -334,15 +360,15 @@ __global__ void __launch_bounds__(256) k_special(const __grid_constant__ vm_ctx 
         const double z2 = Gnu * (double)c.e_xT[e];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          const double z1 = ge.x * Gl[k];
+          const double z1 = ge.x * s_Gl[k];
           const double den = z1 + z2;
           const double xi = (den == 0.0) ? 0.0 : x / den;  // model.py:692 (Q5)
-          lw[k] += (xi * z1) * (ge.y + Ell[k]);
+          lw[k] += (xi * z1) * (ge.y + s_Ell[k]);
           Dz[k] += xi * z2;
         }
       } else {
 #pragma unroll
-        for (int k = 0; k < K; ++k) lw[k] += x * (ge.y + Ell[k]);
+        for (int k = 0; k < K; ++k) lw[k] += x * (ge.y + s_Ell[k]);
       }
     }
     double mx = lw[0];
@@ -354,22 +380,21 @@ __global__ void __launch_bounds__(256) k_special(const __grid_constant__ vm_ctx 
       for (int k = 0; k < K; ++k) rho[k] = 0.0;
       c.dev_flags[0] = 1;  // benign race: every writer stores the same value
     } else {
-      double s = 0.0;
+      double sum = 0.0;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         rho[k] = exp(lw[k] - mx);
-        s += rho[k];
+        sum += rho[k];
       }
-      const double inv = 1.0 / s;
+      const double inv = 1.0 / sum;
 #pragma unroll
       for (int k = 0; k < K; ++k) rho[k] *= inv;
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) nu_acc += Dz[k] * rho[k];  // sum_e sum_k dz2_k rho_k (model.py:822-825)
     // closed-form value the dense kernel uses for this tie: subtract it again from the statistics
-    float a[K], f[K], epsr;
+    float f[K], epsr;
     bool dead;
-    vm_tie_logodds<K>(c, l, lrow, j, a);
     vm_formula_rho<K>(a, may_dead, f, epsr, dead);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -390,7 +415,7 @@ __global__ void __launch_bounds__(256) k_special(const __grid_constant__ vm_ctx 
         double val = 0.0;
         if (c.e_flags[e] & 1) {
 #pragma unroll
-          for (int k = 0; k < K; ++k) val += erho[k] * (Gth * Gl[k] + z2);
+          for (int k = 0; k < K; ++k) val += erho[k] * (Gth * s_Gl[k] + z2);
         }
         t2_acc += x * log(val + c.eps);
       }
@@ -430,10 +455,12 @@ __global__ void __launch_bounds__(256) k_special(const __grid_constant__ vm_ctx 
 template <int K>
 struct DenseCfg {
   static constexpr int RB = (K <= 4) ? 8 : 4;  // rows per batch ((K-1)*RB KB of shared memory)
+  static constexpr int NBUF = (K <= 3) ? 2 : 1;  // row-partial buffers (2: one barrier per batch)
 };
 
 template <int K, bool ELBO, bool STORE, bool CSR>
-__global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constant__ vm_ctx c, double* catpart) {
+__device__ __forceinline__ void dense_generic(const vm_ctx& c, double* catpart, float (*rowbuf)[DenseCfg<K>::RB][VM_DENSE_THREADS],
+                                              int* rowdead, double* sm_red) {
   constexpr int RB = DenseCfg<K>::RB;
   constexpr int NW = VM_DENSE_THREADS / 32;
   const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
@@ -444,9 +471,6 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constan
   const int i_lo = rt * (int)c.tile_h, i_hi = min(i_lo + (int)c.tile_h, nloc);
   const bool may_dead = vm_may_dead<K>(c, l);
   const bool vec_ok = ((((int64_t)N * K) & 3) == 0) && (j0 + 3 < N);
-  __shared__ float rowbuf[K - 1][RB][VM_DENSE_THREADS];
-  __shared__ int rowdead[RB];
-  __shared__ double sm_red[8];
 
   const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
   const float lp0 = (float)lc[VM_LC_LP0(K)], lpk = (float)lc[VM_LC_LPK(K)], epsf = (float)c.eps;
@@ -576,6 +600,167 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constan
 }
 
 
+
+// Fast path of the dense kernel (separable mask, no ELBO, slab stored, no row of the layer can underflow completely):
+// ~10 instructions per tie.  Differences from the generic body: no dead-row bookkeeping, no per-tie validity tests
+// (a thread owns 4 valid columns or none), the row terms of a batch are fetched up front, and the patch data
+// (column + fp32 posterior of the first 64 special ties of the warp's row) is prefetched BEFORE the arithmetic, with the
+// tile pointers of the next batch, so that nothing but stores follows the barrier.
+template <int K>
+__device__ __forceinline__ void dense_fast(const vm_ctx& c, float (*rowbuf)[DenseCfg<K>::RB][VM_DENSE_THREADS]) {
+  constexpr int RB = DenseCfg<K>::RB;
+  constexpr int NW = VM_DENSE_THREADS / 32;
+  const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
+  const int ct = blockIdx.x;
+  const int l = blockIdx.y / nrt, rt = blockIdx.y - l * nrt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j0 = ct * VM_TILE_W + tid * 4;
+  const int i_lo = rt * (int)c.tile_h, i_hi = min(i_lo + (int)c.tile_h, nloc);
+  const bool have_cols = j0 + 3 < N;  // the caller guarantees N % 4 == 0: 4 valid columns or none
+
+  float q[K][4];
+#pragma unroll
+  for (int k = 1; k < K; ++k)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) q[k][t] = have_cols ? __ldg(&c.tab_q[((int64_t)l * N + j0 + t) * K + k]) : 0.f;
+  float colacc[K][4];
+#pragma unroll
+  for (int k = 1; k < K; ++k)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) colacc[k][t] = 0.f;
+
+  const int32_t* tp = c.utile_ptr + ((int64_t)l * nloc + i_lo + warp) * nct + ct;  // this warp's row of batch 0
+  int ua = 0, ub = 0;
+  if (warp < RB && i_lo + warp < i_hi) {
+    ua = __ldg(tp);
+    ub = __ldg(tp + 1);
+  }
+  for (int ib = i_lo; ib < i_hi; ib += RB) {
+    const bool my_row = warp < RB && ib + warp < i_hi;
+    const int64_t lrow_w = (int64_t)l * nloc + ib + warp;
+    // prefetch: patch data of this batch, tile pointers of the next one
+    int pc0 = 0, pc1 = 0;
+    float pv0[K], pv1[K];
+    const int u_0 = ua + lane, u_1 = ua + 32 + lane;
+    if (u_0 < ub) {
+      pc0 = __ldg(&c.u_col[u_0]);
+#pragma unroll
+      for (int k = 0; k < K; ++k) pv0[k] = __ldg(&c.rho_u32[(int64_t)u_0 * K + k]);
+    }
+    if (u_1 < ub) {
+      pc1 = __ldg(&c.u_col[u_1]);
+#pragma unroll
+      for (int k = 0; k < K; ++k) pv1[k] = __ldg(&c.rho_u32[(int64_t)u_1 * K + k]);
+    }
+    const int ua_cur = ua, ub_cur = ub;
+    if (warp < RB && ib + RB + warp < i_hi) {
+      ua = __ldg(tp + (int64_t)RB * nct);
+      ub = __ldg(tp + (int64_t)RB * nct + 1);
+    }
+    tp += (int64_t)RB * nct;
+    // row terms of the batch
+    float pb[RB][K];
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+#pragma unroll
+      for (int k = 1; k < K; ++k)
+        pb[r][k] = (ib + r < i_hi) ? __ldg(&c.tab_p[((int64_t)l * nloc + ib + r) * K + k]) : 0.f;
+    float* dst = c.rho + (((int64_t)l * nloc + ib) * N + j0) * K;
+    const int buf = ((ib - i_lo) / RB) & (DenseCfg<K>::NBUF - 1);
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      float rowacc[K];
+#pragma unroll
+      for (int k = 1; k < K; ++k) rowacc[k] = 0.f;
+      if (have_cols && ib + r < i_hi) {
+        float o[4 * K];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float e[K], s = 1.f;
+#pragma unroll
+          for (int k = 1; k < K; ++k) {
+            e[k] = vm_ex2(fminf(__fadd_rn(pb[r][k], q[k][t]), VM_CLAMP_LOG2));
+            s = __fadd_rn(s, e[k]);
+          }
+          // same operation order as vm_formula_rho: s = ((0 + e1) + e2 ...), then 1 + s
+          if (K > 2) {
+            s = e[1];
+#pragma unroll
+            for (int k = 2; k < K; ++k) s = __fadd_rn(s, e[k]);
+            s = __fadd_rn(1.f, s);
+          }
+          const float inv = vm_rcp(s);
+          o[t * K] = inv;
+#pragma unroll
+          for (int k = 1; k < K; ++k) {
+            const float v = __fmul_rn(e[k], inv);
+            o[t * K + k] = v;
+            colacc[k][t] += v;
+            rowacc[k] += v;
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < K; ++v)
+          reinterpret_cast<float4*>(dst + (int64_t)r * N * K)[v] =
+              make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+      }
+#pragma unroll
+      for (int k = 1; k < K; ++k) rowbuf[(k - 1) + buf * (K - 1)][r][tid] = rowacc[k];
+    }
+    __syncthreads();
+    if (my_row) {
+      float* rowdst = c.rho + lrow_w * N * K;
+      if (u_0 < ub_cur) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) rowdst[(int64_t)pc0 * K + k] = pv0[k];
+      }
+      if (u_1 < ub_cur) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) rowdst[(int64_t)pc1 * K + k] = pv1[k];
+      }
+      for (int u = ua_cur + 64 + lane; u < ub_cur; u += 32) {
+        const int col = c.u_col[u];
+#pragma unroll
+        for (int k = 0; k < K; ++k) rowdst[(int64_t)col * K + k] = c.rho_u32[(int64_t)u * K + k];
+      }
+#pragma unroll
+      for (int k = 1; k < K; ++k) {
+        float v = 0.f;
+#pragma unroll
+        for (int sgm = 0; sgm < NW; ++sgm) v += rowbuf[(k - 1) + buf * (K - 1)][warp][lane + 32 * sgm];
+        v = warp_sum(v);
+        if (lane == 0) c.rowpart[(lrow_w * nct + ct) * K + k] = v;
+      }
+      if (lane == 0) c.rowpart[(lrow_w * nct + ct) * K] = 0.f;
+    }
+    if (DenseCfg<K>::NBUF == 1) __syncthreads();
+  }
+  if (have_cols) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      c.colpart[(((int64_t)l * nrt + rt) * N + j0 + t) * K] = 0.f;
+#pragma unroll
+      for (int k = 1; k < K; ++k) c.colpart[(((int64_t)l * nrt + rt) * N + j0 + t) * K + k] = colacc[k][t];
+    }
+  }
+}
+
+template <int K, bool ELBO, bool STORE, bool CSR>
+__global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constant__ vm_ctx c, double* catpart) {
+  constexpr int RB = DenseCfg<K>::RB;
+  __shared__ float rowbuf[(K - 1) * DenseCfg<K>::NBUF][RB][VM_DENSE_THREADS];
+  __shared__ int rowdead[RB];
+  __shared__ double sm_red[8];
+  if (!ELBO && STORE && !CSR) {
+    const int l = blockIdx.y / (int)c.nrt;
+    if ((c.N & 3) == 0 && !vm_may_dead<K>(c, l)) {
+      dense_fast<K>(c, rowbuf);
+      return;
+    }
+  }
+  dense_generic<K, ELBO, STORE, CSR>(c, catpart, rowbuf, rowdead, sm_red);
+}
+
 // ---- statistics of the new rho: A[l,m,k] = sum of rho_k over the ties reported by (l,m) ------------------------
 // column partials of the dense kernel summed over the row tiles (coalesced: consecutive threads = consecutive (m,k))
 template <int K>
@@ -630,8 +815,10 @@ __global__ void __launch_bounds__(256) k_stats_ego(const __grid_constant__ vm_ct
       }
     }
   }
+  int ua = 0, ub = 0;  // special ties of row m (contiguous)
   if (local) {
-    const int ua = c.utile_ptr[lrow * nct], ub = c.utile_ptr[(lrow + 1) * nct];
+    ua = c.utile_ptr[lrow * nct];
+    ub = c.utile_ptr[(lrow + 1) * nct];
     for (int u = ua + lane; u < ub; u += 32) {
       if (!c.ego_diag && c.u_col[u] == m) continue;
 #pragma unroll
@@ -640,7 +827,7 @@ __global__ void __launch_bounds__(256) k_stats_ego(const __grid_constant__ vm_ct
   }
   for (int64_t p = c.ucol_ptr[(int64_t)l * N + m] + lane; p < c.ucol_ptr[(int64_t)l * N + m + 1]; p += 32) {
     const int u = c.ucol_perm[p];
-    if (local && c.u_lrow[u] == lrow) continue;  // the diagonal tie: counted (at most) once, above
+    if (u >= ua && u < ub) continue;  // the diagonal tie (row m, column m): counted (at most) once, above
 #pragma unroll
     for (int k = 0; k < K; ++k) d[k] += c.delta_u[(int64_t)u * K + k];
   }
