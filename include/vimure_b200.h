@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VM_ABI_VERSION 4
+#define VM_ABI_VERSION 5
 
 /* reporter-mask structure (how R[l,i,j,m] is represented) */
 #define VM_R_EGO 0 /* reporter m == node m reports row m and column m (vimure synthetic.py:1184-1204, _io.py:229-242) */
@@ -76,7 +76,7 @@ typedef struct vm_ctx {
   int64_t U;                /* special ties owned (union of X ties, all diagonal ties) */
   int64_t I;                /* X entries whose tie is owned */
   int64_t IT;               /* X entries whose TRANSPOSED tie is owned and reported (ELBO eta term) */
-  int64_t tile_w, tile_h;   /* dense tiling; tile_w must be 1024 */
+  int64_t tile_w, tile_h;   /* dense tiling; tile_w must be vm_dense_tile_w(K) */
   int64_t nct, nrt;         /* ceil(N/tile_w), ceil(nloc/tile_h) */
   int64_t n_gchunk;         /* reporter chunks (gamma pass) */
   int64_t phi_chunk;        /* entries per block in the phi pass */
@@ -167,6 +167,8 @@ typedef struct vm_ctx {
 /* sizeof(vm_ctx) and ABI version, for the host-side mirror to verify */
 int64_t vm_ctx_size(void);
 int64_t vm_abi_version(void);
+/* column-tile width of the dense kernel for a given K (the packer builds `utile_ptr` for this width) */
+int64_t vm_dense_tile_w(int64_t K);
 
 /* theta/lambda/nu caches (G_*, E_*, Elog_*) from the current shapes/rates: `_update_cache` (model.py:676-684) and the
  * cache part of `_initialize_priors` (model.py:596-605). Call once after injecting the initial state. */

@@ -85,6 +85,7 @@ def load():
     protos = {
         "vm_ctx_size": (i64, []),
         "vm_abi_version": (i64, []),
+        "vm_dense_tile_w": (i64, [i64]),
         "vm_refresh_cache": (i, [P, vp]),
         "vm_init_stats": (i, [P, vp]),
         "vm_phase_gamma": (i, [P, vp]),

@@ -14,7 +14,16 @@ Layout (see include/vimure_b200.h): this rank owns node rows [row0, row0+nloc) o
 import numpy as np
 import torch
 
-TILE_W = 1024
+
+def dense_tile_w(K):
+    """Column-tile width of the dense kernel (a K-dependent constant of the CUDA library)."""
+    from . import _capi
+
+    w = int(_capi.load().vm_dense_tile_w(int(K)))
+    if w <= 0:
+        raise ValueError("vimure_b200 supports 2 <= K <= 8 (got K=%d)" % K)
+    return w
+
 GAMMA_CHUNK = 256
 PHI_CHUNK = 4096
 SPECIAL_TIES_PER_BLOCK = 1024  # == VM_SPECIAL_TIES_PER_BLOCK of include/vimure_b200.h
@@ -46,6 +55,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64)
     nloc = N - row0 if nloc is None else int(nloc)
     P = Packed()
     P.L, P.N, P.M, P.K, P.row0, P.nloc = int(L), int(N), int(M), int(K), int(row0), nloc
+    TILE_W = dense_tile_w(K)
     P.tile_w, P.tile_h = TILE_W, int(tile_h)
     P.nct = (N + TILE_W - 1) // TILE_W
     P.nrt = (nloc + P.tile_h - 1) // P.tile_h

@@ -13,7 +13,6 @@
 #define VM_DEAD_LOG2 ((float)(VM_DEAD_LN * VM_LOG2E))
 #define VM_CLAMP_LOG2 120.0f
 
-#define VM_TILE_W 1024
 #define VM_DENSE_THREADS 256
 
 // ------------------------------------------------------------------ special functions (fp64)

@@ -445,320 +445,249 @@ __global__ void __launch_bounds__(256, (K <= 2 ? 3 : 2)) k_special(const __grid_
 }
 
 // ---- the per-tie dense kernel: every owned tie, closed form, fp32 slab write + statistics partials -------------
-// HBM-bound: writes 4*K bytes per tie, reads only the (L2-resident) tables.  256 threads x 4 consecutive ties
-// = one 1024-tie row segment per step, tile_h rows per CTA, processed in batches of RB rows.  Per batch:
-// (1) every thread evaluates the closed form for its 4 ties of each row, stores them with 128-bit stores, keeps the
-// column sums in registers and drops its per-row partial into shared memory; (2) after ONE barrier, warp w
-// patches the special ties of row w with their fp64-computed values (same CTA, after the barrier: the sectors are
-// still dirty in L2, so no extra DRAM traffic) and reduces row w's partials.  Column partials are written once
-// per CTA.  The tile pointers of the batch are prefetched before the arithmetic.
+// HBM-bound: writes 4*K bytes per tie, reads only the (L2-resident) tables and the special-tie patch data.
+// A CTA owns a tile of tile_h rows x TW columns; its 8 warps are AUTONOMOUS (no block barrier in the row loop):
+// warp w takes rows w, w+8, ...; for each row it sweeps the TW columns in NCH chunks of 128 (4 consecutive ties
+// per lane, 128-bit stores), keeps the row sums in registers (one shuffle reduction per row), keeps the column
+// sums of all its rows in registers, and finally overwrites the special ties of the row with their fp64-computed
+// values (same warp, after __syncwarp: the sectors are still dirty in L2, so no extra DRAM traffic).  The tile
+// pointers and row terms of the next row and the patch data of the current row are prefetched before the arithmetic.
+// Column partials of the 8 warps are combined through shared memory once, at the end of the CTA.
+// TW = 128*NCH depends on K so that the column accumulators (NCH*4*(K-1) registers) stay in registers.
 template <int K>
 struct DenseCfg {
-  static constexpr int RB = (K <= 4) ? 8 : 4;  // rows per batch ((K-1)*RB KB of shared memory)
-  static constexpr int NBUF = (K <= 3) ? 2 : 1;  // row-partial buffers (2: one barrier per batch)
+  static constexpr int NCH = (K <= 2) ? 8 : (K == 3) ? 4 : (K <= 5) ? 2 : 1;
+  static constexpr int TW = 128 * NCH;
 };
 
+// 4 consecutive ties of one lane. a[t][k] are the log2-odds; results in o[t*K+k].
+template <int K, bool ELBO, bool MD>
+__device__ __forceinline__ void dense_quad(const float (*a)[K], int nvalid, float* o, float* rowacc, float (*colacc)[4],
+                                           float* coldead, double& cat, float lp0, float lpk, float epsf) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    float epsr;
+    bool dead;
+    vm_formula_rho<K>(a[t], MD, &o[t * K], epsr, dead);
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+      colacc[k - 1][t] += o[t * K + k];
+      rowacc[k] += o[t * K + k];
+    }
+    if (MD && dead && t < nvalid) {
+      rowacc[0] += 1.f;
+      atomicAdd(&coldead[t], 1.f);  // integer-valued: exact in any order
+    }
+    if (ELBO && t < nvalid) cat += (double)vm_formula_cat<K>(&o[t * K], epsr, dead, lp0, lpk, epsf);
+  }
+}
+
 template <int K, bool ELBO, bool STORE, bool CSR>
-__device__ __forceinline__ void dense_generic(const vm_ctx& c, double* catpart, float (*rowbuf)[DenseCfg<K>::RB][VM_DENSE_THREADS],
-                                              int* rowdead, double* sm_red) {
-  constexpr int RB = DenseCfg<K>::RB;
-  constexpr int NW = VM_DENSE_THREADS / 32;
+__global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? 3 : 1) k_dense(const __grid_constant__ vm_ctx c, double* catpart) {
+  constexpr int NCH = DenseCfg<K>::NCH, TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32;
+  __shared__ __align__(16) float qs[K][TW];      // column terms of the tile (row 0: weight of k=0, dead check only)
+  __shared__ __align__(16) float colbuf[K][TW];  // cross-warp column sums (row 0: dead counts)
+  __shared__ double sm_red[8];
   const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
   const int ct = blockIdx.x;
   const int l = blockIdx.y / nrt, rt = blockIdx.y - l * nrt;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int j0 = ct * VM_TILE_W + tid * 4;
+  const int jt = ct * TW;
   const int i_lo = rt * (int)c.tile_h, i_hi = min(i_lo + (int)c.tile_h, nloc);
   const bool may_dead = vm_may_dead<K>(c, l);
-  const bool vec_ok = ((((int64_t)N * K) & 3) == 0) && (j0 + 3 < N);
-
+  const bool vec_ok = (((int64_t)N * K) & 3) == 0;
   const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
   const float lp0 = (float)lc[VM_LC_LP0(K)], lpk = (float)lc[VM_LC_LPK(K)], epsf = (float)c.eps;
-  float q[K][4], cc[K], dd[K];
+  float cc[K], dd[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     cc[k] = (float)lc[VM_LC_C(k)];
     dd[k] = (float)lc[VM_LC_D(K, k)];
-#pragma unroll
-    for (int t = 0; t < 4; ++t)
-      q[k][t] = (!CSR && j0 + t < N) ? __ldg(&c.tab_q[((int64_t)l * N + j0 + t) * K + k]) : -INFINITY;
   }
-  float colacc[K][4];
+  for (int idx = tid; idx < TW; idx += VM_DENSE_THREADS) {
+    const int j = jt + idx;
 #pragma unroll
-  for (int k = 0; k < K; ++k)
+    for (int k = 0; k < K; ++k) {
+      qs[k][idx] = (!CSR && j < N) ? __ldg(&c.tab_q[((int64_t)l * N + j) * K + k]) : -INFINITY;
+      colbuf[k][idx] = 0.f;
+    }
+  }
+  __syncthreads();
+
+  float colacc[NCH][K - 1][4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) colacc[k][t] = 0.f;
+  for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+    for (int k = 0; k < K - 1; ++k)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) colacc[ch][k][t] = 0.f;
   double cat = 0.0;
 
-  for (int ib = i_lo; ib < i_hi; ib += RB) {
-    // tile pointers of the row this warp will patch
-    int ua = 0, ub = 0;
-    const bool my_row = warp < RB && ib + warp < i_hi;
-    const int64_t lrow_w = (int64_t)l * nloc + ib + warp;
-    if (STORE && my_row) {
-      ua = __ldg(&c.utile_ptr[lrow_w * nct + ct]);
-      ub = __ldg(&c.utile_ptr[lrow_w * nct + ct + 1]);
+  int i = i_lo + warp;
+  int ua = 0, ub = 0;
+  float p[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) p[k] = 0.f;
+  if (i < i_hi) {
+    const int64_t lrow = (int64_t)l * nloc + i;
+    if (STORE) {
+      ua = __ldg(&c.utile_ptr[lrow * nct + ct]);
+      ub = __ldg(&c.utile_ptr[lrow * nct + ct + 1]);
     }
-    if (may_dead && tid < RB) rowdead[tid] = 0;
-    if (may_dead) __syncthreads();
+    if (!CSR) {
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      const int i = ib + r;
-      float rowacc[K];
+      for (int k = 0; k < K; ++k) p[k] = __ldg(&c.tab_p[lrow * K + k]);
+    }
+  }
+  for (; i < i_hi; i += NW) {
+    const int64_t lrow = (int64_t)l * nloc + i;
+    // ---- prefetch: next row's tile pointers and row terms, this row's patch data (first 64 special ties)
+    int ua2 = 0, ub2 = 0;
+    float p2[K];
 #pragma unroll
-      for (int k = 0; k < K; ++k) rowacc[k] = 0.f;
-      if (i < i_hi) {
-        const int64_t lrow = (int64_t)l * nloc + i;
-        float p[K];
+    for (int k = 0; k < K; ++k) p2[k] = 0.f;
+    if (i + NW < i_hi) {
+      const int64_t lrow2 = lrow + NW;
+      if (STORE) {
+        ua2 = __ldg(&c.utile_ptr[lrow2 * nct + ct]);
+        ub2 = __ldg(&c.utile_ptr[lrow2 * nct + ct + 1]);
+      }
+      if (!CSR) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) p[k] = CSR ? 0.f : __ldg(&c.tab_p[lrow * K + k]);
-        float o[4 * K];
+        for (int k = 0; k < K; ++k) p2[k] = __ldg(&c.tab_p[lrow2 * K + k]);
+      }
+    }
+    int pc0 = 0, pc1 = 0;
+    float pv0[K], pv1[K];
+    const int u_0 = ua + lane, u_1 = ua + 32 + lane;
+    if (STORE) {
+      if (u_0 < ub) {
+        pc0 = __ldg(&c.u_col[u_0]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) pv0[k] = __ldg(&c.rho_u32[(int64_t)u_0 * K + k]);
+      }
+      if (u_1 < ub) {
+        pc1 = __ldg(&c.u_col[u_1]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) pv1[k] = __ldg(&c.rho_u32[(int64_t)u_1 * K + k]);
+      }
+    }
+    // ---- the row
+    float rowacc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) rowacc[k] = 0.f;
+    float* rowdst = c.rho + lrow * N * K;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int jl = ch * 128 + lane * 4;
+      const int j = jt + jl;
+      const int nvalid = min(4, N - j);
+      if (nvalid <= 0) continue;
+      float a[4][K];
+      if (CSR) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const bool valid = j0 + t < N;
-          float a[K];
-          if (CSR) {
-            const float s = valid ? vm_csr_S32(c, l, lrow * N + j0 + t) : 0.f;
+          const float s = (t < nvalid) ? vm_csr_S32(c, l, lrow * N + j + t) : 0.f;
 #pragma unroll
-            for (int k = 0; k < K; ++k) a[k] = valid ? __fmaf_rn(-s, dd[k], cc[k]) : -INFINITY;
-          } else {
-#pragma unroll
-            for (int k = 0; k < K; ++k) a[k] = __fadd_rn(p[k], q[k][t]);
-          }
-          float epsr;
-          bool dead;
-          vm_formula_rho<K>(a, may_dead, &o[t * K], epsr, dead);
-          if (!CSR) {
-#pragma unroll
-            for (int k = 1; k < K; ++k) {
-              colacc[k][t] += o[t * K + k];
-              rowacc[k] += o[t * K + k];
-            }
-            if (may_dead && dead && valid) {
-              colacc[0][t] += 1.f;
-              atomicAdd(&rowdead[r], 1);
-            }
-          }
-          if (ELBO && valid) cat += (double)vm_formula_cat<K>(&o[t * K], epsr, dead, lp0, lpk, epsf);
+          for (int k = 0; k < K; ++k) a[t][k] = (t < nvalid) ? __fmaf_rn(-s, dd[k], cc[k]) : -INFINITY;
         }
-        if (STORE) {
-          float* dst = c.rho + (lrow * N + j0) * K;
-          if (vec_ok) {
-#pragma unroll
-            for (int v = 0; v < K; ++v)
-              reinterpret_cast<float4*>(dst)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
-          } else {
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-              if (j0 + t < N) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) dst[t * K + k] = o[t * K + k];
-              }
-          }
-        }
-      }
-      if (!CSR) {
-#pragma unroll
-        for (int k = 1; k < K; ++k) rowbuf[k - 1][r][tid] = rowacc[k];
-      }
-    }
-    __syncthreads();
-    if (my_row) {
-      if (STORE) {
-        for (int u = ua + lane; u < ub; u += 32) {
-          float* dst = c.rho + (lrow_w * N + c.u_col[u]) * K;
-#pragma unroll
-          for (int k = 0; k < K; ++k) dst[k] = c.rho_u32[(int64_t)u * K + k];
-        }
-      }
-      if (!CSR) {
+      } else {
 #pragma unroll
         for (int k = 1; k < K; ++k) {
-          float v = 0.f;
-#pragma unroll
-          for (int s = 0; s < NW; ++s) v += rowbuf[k - 1][warp][lane + 32 * s];
-          v = warp_sum(v);
-          if (lane == 0) c.rowpart[(lrow_w * nct + ct) * K + k] = v;
+          const float4 qv = *reinterpret_cast<const float4*>(&qs[k][jl]);
+          a[0][k] = __fadd_rn(p[k], qv.x);
+          a[1][k] = __fadd_rn(p[k], qv.y);
+          a[2][k] = __fadd_rn(p[k], qv.z);
+          a[3][k] = __fadd_rn(p[k], qv.w);
         }
-        if (lane == 0) c.rowpart[(lrow_w * nct + ct) * K] = may_dead ? (float)rowdead[warp] : 0.f;
+        if (may_dead) {
+          const float4 qv = *reinterpret_cast<const float4*>(&qs[0][jl]);
+          a[0][0] = __fadd_rn(p[0], qv.x);
+          a[1][0] = __fadd_rn(p[0], qv.y);
+          a[2][0] = __fadd_rn(p[0], qv.z);
+          a[3][0] = __fadd_rn(p[0], qv.w);
+        } else {
+          a[0][0] = a[1][0] = a[2][0] = a[3][0] = 0.f;
+        }
+      }
+      float o[4 * K];
+      if (may_dead)
+        dense_quad<K, ELBO, true>(a, nvalid, o, rowacc, colacc[ch], &colbuf[0][jl], cat, lp0, lpk, epsf);
+      else
+        dense_quad<K, ELBO, false>(a, nvalid, o, rowacc, colacc[ch], &colbuf[0][jl], cat, lp0, lpk, epsf);
+      if (STORE) {
+        float* dst = rowdst + (int64_t)j * K;
+        if (vec_ok && nvalid == 4) {
+#pragma unroll
+          for (int v = 0; v < K; ++v)
+            reinterpret_cast<float4*>(dst)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (t < nvalid) {
+#pragma unroll
+              for (int k = 0; k < K; ++k) dst[t * K + k] = o[t * K + k];
+            }
+        }
       }
     }
-    __syncthreads();
-  }
-  if (!CSR) {
+    // ---- row partials
+    if (!CSR) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
-      if (j0 + t < N) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) c.colpart[(((int64_t)l * nrt + rt) * N + j0 + t) * K + k] = colacc[k][t];
+      for (int k = 0; k < K; ++k) {
+        if (k == 0 && !may_dead) continue;
+        const float v = warp_sum(rowacc[k]);
+        if (lane == 0) c.rowpart[(lrow * nct + ct) * K + k] = v;
       }
+      if (!may_dead && lane == 0) c.rowpart[(lrow * nct + ct) * K] = 0.f;
+    }
+    // ---- patch the special ties of this row segment
+    if (STORE) {
+      __syncwarp();
+      if (u_0 < ub) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) rowdst[(int64_t)pc0 * K + k] = pv0[k];
+      }
+      if (u_1 < ub) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) rowdst[(int64_t)pc1 * K + k] = pv1[k];
+      }
+      for (int u = ua + 64 + lane; u < ub; u += 32) {
+        const int col = c.u_col[u];
+#pragma unroll
+        for (int k = 0; k < K; ++k) rowdst[(int64_t)col * K + k] = c.rho_u32[(int64_t)u * K + k];
+      }
+    }
+    ua = ua2;
+    ub = ub2;
+#pragma unroll
+    for (int k = 0; k < K; ++k) p[k] = p2[k];
+  }
+  // ---- column partials: combine the 8 warps in a fixed order
+  if (!CSR) {
+    for (int w = 0; w < NW; ++w) {
+      if (warp == w) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+          for (int k = 1; k < K; ++k)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) colbuf[k][ch * 128 + lane * 4 + t] += colacc[ch][k - 1][t];
+      }
+      __syncthreads();
+    }
+    for (int idx = tid; idx < TW; idx += VM_DENSE_THREADS) {
+      const int j = jt + idx;
+      if (j < N) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) c.colpart[(((int64_t)l * nrt + rt) * N + j) * K + k] = colbuf[k][idx];
+      }
+    }
   }
   if (ELBO) {
     const double v = block_sum<VM_DENSE_THREADS>(cat, sm_red);
     if (tid == 0) catpart[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
   }
-}
-
-
-
-// Fast path of the dense kernel (separable mask, no ELBO, slab stored, no row of the layer can underflow completely):
-// ~10 instructions per tie.  Differences from the generic body: no dead-row bookkeeping, no per-tie validity tests
-// (a thread owns 4 valid columns or none), the row terms of a batch are fetched up front, and the patch data
-// (column + fp32 posterior of the first 64 special ties of the warp's row) is prefetched BEFORE the arithmetic, with the
-// tile pointers of the next batch, so that nothing but stores follows the barrier.
-template <int K>
-__device__ __forceinline__ void dense_fast(const vm_ctx& c, float (*rowbuf)[DenseCfg<K>::RB][VM_DENSE_THREADS]) {
-  constexpr int RB = DenseCfg<K>::RB;
-  constexpr int NW = VM_DENSE_THREADS / 32;
-  const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
-  const int ct = blockIdx.x;
-  const int l = blockIdx.y / nrt, rt = blockIdx.y - l * nrt;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int j0 = ct * VM_TILE_W + tid * 4;
-  const int i_lo = rt * (int)c.tile_h, i_hi = min(i_lo + (int)c.tile_h, nloc);
-  const bool have_cols = j0 + 3 < N;  // the caller guarantees N % 4 == 0: 4 valid columns or none
-
-  float q[K][4];
-#pragma unroll
-  for (int k = 1; k < K; ++k)
-#pragma unroll
-    for (int t = 0; t < 4; ++t) q[k][t] = have_cols ? __ldg(&c.tab_q[((int64_t)l * N + j0 + t) * K + k]) : 0.f;
-  float colacc[K][4];
-#pragma unroll
-  for (int k = 1; k < K; ++k)
-#pragma unroll
-    for (int t = 0; t < 4; ++t) colacc[k][t] = 0.f;
-
-  const int32_t* tp = c.utile_ptr + ((int64_t)l * nloc + i_lo + warp) * nct + ct;  // this warp's row of batch 0
-  int ua = 0, ub = 0;
-  if (warp < RB && i_lo + warp < i_hi) {
-    ua = __ldg(tp);
-    ub = __ldg(tp + 1);
-  }
-  for (int ib = i_lo; ib < i_hi; ib += RB) {
-    const bool my_row = warp < RB && ib + warp < i_hi;
-    const int64_t lrow_w = (int64_t)l * nloc + ib + warp;
-    // prefetch: patch data of this batch, tile pointers of the next one
-    int pc0 = 0, pc1 = 0;
-    float pv0[K], pv1[K];
-    const int u_0 = ua + lane, u_1 = ua + 32 + lane;
-    if (u_0 < ub) {
-      pc0 = __ldg(&c.u_col[u_0]);
-#pragma unroll
-      for (int k = 0; k < K; ++k) pv0[k] = __ldg(&c.rho_u32[(int64_t)u_0 * K + k]);
-    }
-    if (u_1 < ub) {
-      pc1 = __ldg(&c.u_col[u_1]);
-#pragma unroll
-      for (int k = 0; k < K; ++k) pv1[k] = __ldg(&c.rho_u32[(int64_t)u_1 * K + k]);
-    }
-    const int ua_cur = ua, ub_cur = ub;
-    if (warp < RB && ib + RB + warp < i_hi) {
-      ua = __ldg(tp + (int64_t)RB * nct);
-      ub = __ldg(tp + (int64_t)RB * nct + 1);
-    }
-    tp += (int64_t)RB * nct;
-    // row terms of the batch
-    float pb[RB][K];
-#pragma unroll
-    for (int r = 0; r < RB; ++r)
-#pragma unroll
-      for (int k = 1; k < K; ++k)
-        pb[r][k] = (ib + r < i_hi) ? __ldg(&c.tab_p[((int64_t)l * nloc + ib + r) * K + k]) : 0.f;
-    float* dst = c.rho + (((int64_t)l * nloc + ib) * N + j0) * K;
-    const int buf = ((ib - i_lo) / RB) & (DenseCfg<K>::NBUF - 1);
-#pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      float rowacc[K];
-#pragma unroll
-      for (int k = 1; k < K; ++k) rowacc[k] = 0.f;
-      if (have_cols && ib + r < i_hi) {
-        float o[4 * K];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          float e[K], s = 1.f;
-#pragma unroll
-          for (int k = 1; k < K; ++k) {
-            e[k] = vm_ex2(fminf(__fadd_rn(pb[r][k], q[k][t]), VM_CLAMP_LOG2));
-            s = __fadd_rn(s, e[k]);
-          }
-          // same operation order as vm_formula_rho: s = ((0 + e1) + e2 ...), then 1 + s
-          if (K > 2) {
-            s = e[1];
-#pragma unroll
-            for (int k = 2; k < K; ++k) s = __fadd_rn(s, e[k]);
-            s = __fadd_rn(1.f, s);
-          }
-          const float inv = vm_rcp(s);
-          o[t * K] = inv;
-#pragma unroll
-          for (int k = 1; k < K; ++k) {
-            const float v = __fmul_rn(e[k], inv);
-            o[t * K + k] = v;
-            colacc[k][t] += v;
-            rowacc[k] += v;
-          }
-        }
-#pragma unroll
-        for (int v = 0; v < K; ++v)
-          reinterpret_cast<float4*>(dst + (int64_t)r * N * K)[v] =
-              make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
-      }
-#pragma unroll
-      for (int k = 1; k < K; ++k) rowbuf[(k - 1) + buf * (K - 1)][r][tid] = rowacc[k];
-    }
-    __syncthreads();
-    if (my_row) {
-      float* rowdst = c.rho + lrow_w * N * K;
-      if (u_0 < ub_cur) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) rowdst[(int64_t)pc0 * K + k] = pv0[k];
-      }
-      if (u_1 < ub_cur) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) rowdst[(int64_t)pc1 * K + k] = pv1[k];
-      }
-      for (int u = ua_cur + 64 + lane; u < ub_cur; u += 32) {
-        const int col = c.u_col[u];
-#pragma unroll
-        for (int k = 0; k < K; ++k) rowdst[(int64_t)col * K + k] = c.rho_u32[(int64_t)u * K + k];
-      }
-#pragma unroll
-      for (int k = 1; k < K; ++k) {
-        float v = 0.f;
-#pragma unroll
-        for (int sgm = 0; sgm < NW; ++sgm) v += rowbuf[(k - 1) + buf * (K - 1)][warp][lane + 32 * sgm];
-        v = warp_sum(v);
-        if (lane == 0) c.rowpart[(lrow_w * nct + ct) * K + k] = v;
-      }
-      if (lane == 0) c.rowpart[(lrow_w * nct + ct) * K] = 0.f;
-    }
-    if (DenseCfg<K>::NBUF == 1) __syncthreads();
-  }
-  if (have_cols) {
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      c.colpart[(((int64_t)l * nrt + rt) * N + j0 + t) * K] = 0.f;
-#pragma unroll
-      for (int k = 1; k < K; ++k) c.colpart[(((int64_t)l * nrt + rt) * N + j0 + t) * K + k] = colacc[k][t];
-    }
-  }
-}
-
-template <int K, bool ELBO, bool STORE, bool CSR>
-__global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constant__ vm_ctx c, double* catpart) {
-  constexpr int RB = DenseCfg<K>::RB;
-  __shared__ float rowbuf[(K - 1) * DenseCfg<K>::NBUF][RB][VM_DENSE_THREADS];
-  __shared__ int rowdead[RB];
-  __shared__ double sm_red[8];
-  if (!ELBO && STORE && !CSR) {
-    const int l = blockIdx.y / (int)c.nrt;
-    if ((c.N & 3) == 0 && !vm_may_dead<K>(c, l)) {
-      dense_fast<K>(c, rowbuf);
-      return;
-    }
-  }
-  dense_generic<K, ELBO, STORE, CSR>(c, catpart, rowbuf, rowdead, sm_red);
 }
 
 // ---- statistics of the new rho: A[l,m,k] = sum of rho_k over the ties reported by (l,m) ------------------------
@@ -1118,11 +1047,24 @@ static inline double* region_b(const vm_ctx* c) { return region_cat(c) + n_catpa
 #define VM_B_BLOCKS 128
 static inline double* region_ep(const vm_ctx* c) { return region_b(c) + VM_B_BLOCKS; }
 
+extern "C" int64_t vm_dense_tile_w(int64_t K) {
+  switch (K) {
+    case 2: return DenseCfg<2>::TW;
+    case 3: return DenseCfg<3>::TW;
+    case 4: return DenseCfg<4>::TW;
+    case 5: return DenseCfg<5>::TW;
+    case 6: return DenseCfg<6>::TW;
+    case 7: return DenseCfg<7>::TW;
+    case 8: return DenseCfg<8>::TW;
+    default: return VM_EINVAL;
+  }
+}
+
 static int check_ctx(const vm_ctx* c) {
   if (!c) return VM_EINVAL;
   if (c->K < 2 || c->K > VM_MAX_K) return VM_EINVAL;
-  if (c->tile_w != VM_TILE_W || c->tile_h < 1) return VM_EINVAL;
-  if (c->nct != cdiv(c->N, VM_TILE_W) || c->nrt != cdiv(c->nloc, c->tile_h)) return VM_EINVAL;
+  if (c->tile_w != vm_dense_tile_w(c->K) || c->tile_h < 1) return VM_EINVAL;
+  if (c->nct != cdiv(c->N, c->tile_w) || c->nrt != cdiv(c->nloc, c->tile_h)) return VM_EINVAL;
   if (c->r_mode < 0 || c->r_mode > 2) return VM_EINVAL;
   if (c->L * c->nrt > 65535 || c->L > 65535) return VM_EINVAL;
   return 0;
