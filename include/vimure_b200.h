@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VM_ABI_VERSION 5
+#define VM_ABI_VERSION 6
 
 /* reporter-mask structure (how R[l,i,j,m] is represented) */
 #define VM_R_EGO 0 /* reporter m == node m reports row m and column m (vimure synthetic.py:1184-1204, _io.py:229-242) */
@@ -91,6 +91,10 @@ typedef struct vm_ctx {
   const int32_t* u_col;     /* [U] */
   const int64_t* u_ptr;     /* [U+1] range of entries of the tie */
   const double* u_logpr;    /* [U*K] log(pr_rho+EPS) (model.py:559) */
+  const int32_t* u_cnt;     /* [U] number of X entries of the tie (0 for a bare diagonal tie) */
+  const int32_t* u_m0;      /* [U] reporter / count / reciprocal count of the tie's FIRST X entry, stored inline so that */
+  const float* u_x0;        /* [U]   the special-tie kernel needs no dependent load for single-entry ties */
+  const float* u_xT0;       /* [U] */
   const int32_t* utile_ptr; /* [L*nloc*nct+1] first special tie of each (lrow, column tile) */
   const int64_t* ucol_ptr;  /* [L*N+1] EGO: special ties grouped by (l, col) */
   const int32_t* ucol_perm; /* [U] */

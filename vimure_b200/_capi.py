@@ -10,7 +10,7 @@ import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(HERE), "include", "vimure_b200.h")
-LIB_PATH = os.path.join(HERE, "_lib", "libvimure_b200.so")
+LIB_PATH = os.environ.get("VIMURE_B200_LIB") or os.path.join(HERE, "_lib", "libvimure_b200.so")
 
 _lib = None
 _ctx_cls = None

@@ -95,7 +95,7 @@ class CaviEngine:
             self._keep.append(t)
             return t.data_ptr() if t.numel() else self._dummy.data_ptr()
 
-        for name in ("u_lrow", "u_col", "u_ptr", "utile_ptr", "ucol_ptr", "ucol_perm", "e_u", "e_m", "e_x", "e_xT",
+        for name in ("u_lrow", "u_col", "u_ptr", "u_cnt", "u_m0", "u_x0", "u_xT0", "utile_ptr", "ucol_ptr", "ucol_perm", "e_u", "e_m", "e_x", "e_xT",
                      "e_flags", "lay_eptr", "g_chunk_ptr", "g_chunk_lm", "g_u", "g_x", "g_xT", "g_lm_cptr", "t_u", "t_lrow",
                      "t_col", "t_x", "rep", "r_ptr", "r_m", "r_val", "c_ptr", "c_tie"):
             setattr(c, name, ptr(P.t[name]) if name in P.t else self._dummy.data_ptr())

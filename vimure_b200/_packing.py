@@ -120,6 +120,19 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64)
     P.t["e_x"] = xv[sel].to(torch.float32).contiguous()
     P.t["e_xT"] = xT[sel].to(torch.float32).contiguous()
     P.t["e_flags"] = (in_R[sel] > 0).to(torch.uint8).contiguous()
+    # first entry of every special tie, inline
+    cnt = u_ptr[1:] - u_ptr[:-1]
+    first = u_ptr[:-1].clamp(max=max(I - 1, 0))
+    has = cnt > 0
+    P.t["u_cnt"] = _i32(cnt)
+    if I:
+        P.t["u_m0"] = torch.where(has, P.t["e_m"][first], torch.zeros_like(P.t["e_m"][first])).contiguous()
+        P.t["u_x0"] = torch.where(has, P.t["e_x"][first], torch.zeros_like(P.t["e_x"][first])).contiguous()
+        P.t["u_xT0"] = torch.where(has, P.t["e_xT"][first], torch.zeros_like(P.t["e_xT"][first])).contiguous()
+    else:
+        P.t["u_m0"] = torch.zeros(U, dtype=torch.int32, device=dev)
+        P.t["u_x0"] = torch.zeros(U, dtype=torch.float32, device=dev)
+        P.t["u_xT0"] = torch.zeros(U, dtype=torch.float32, device=dev)
     # has this special tie any X entry / is it reported by anybody (model.py:536-556)
     u_l = u_lrow // nloc
     u_i = u_lrow - u_l * nloc + row0

@@ -96,6 +96,15 @@ __device__ __forceinline__ float vm_rcp(float x) {
   return y;
 }
 
+// fp64 reciprocal: hardware seed + two Newton steps (<= 1 ulp for normal positive inputs; ~3x cheaper than '/')
+__device__ __forceinline__ double vm_rcp64(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  r = fma(fma(-a, r, 1.0), r, r);
+  r = fma(fma(-a, r, 1.0), r, r);
+  return r;
+}
+
 // ------------------------------------------------------------------ the per-tie closed form
 // Posterior of a tie that carries no X entry (one-hot prior [1,0,..], model.py:536-556):
 //   rho_k  proportional to  (pr_k+EPS) * exp(-S * E[lambda_k]),   S = sum of E[theta_m] over the tie's reporters
@@ -160,10 +169,10 @@ __device__ __forceinline__ void vm_alloc(bool mut, double x, double xT, double G
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const double z1 = Gth * Gl[k];
-    double den = z1 + z2;
-    if (den == 0.0) den = 1.0;
-    dz1[k] = x * z1 / den;
-    dz2[k] = x * z2 / den;
+    const double den = z1 + z2;
+    const double xi = (den == 0.0) ? 0.0 : x * vm_rcp64(den);  // den == 0 => z1 == z2 == 0 (model.py:692)
+    dz1[k] = xi * z1;
+    dz2[k] = xi * z2;
   }
 }
 

@@ -46,12 +46,30 @@ __global__ void __launch_bounds__(256) k_gamma_partial(const __grid_constant__ v
   for (int k = 0; k < K; ++k) Gl[k] = c.G_lambda[l * K + k];
   double acc = 0.0;
   const int64_t p1 = c.g_chunk_ptr[chunk + 1];
-  for (int64_t p = c.g_chunk_ptr[chunk] + lane; p < p1; p += 32) {
-    const int64_t u = c.g_u[p];
-    double dz1[K], dz2[K];
-    vm_alloc<K>(mut, (double)c.g_x[p], (double)c.g_xT[p], Gth, Gl, Gnu, dz1, dz2);
+  // a chunk holds <= 256 entries = 8 per lane: two rounds of 4 independent gathers
+  for (int64_t pb = c.g_chunk_ptr[chunk] + lane; pb < p1; pb += 128) {
+    int64_t u[4];
+    float x[4], xT[4];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc += c.rho_u[u * K + k] * dz1[k];
+    for (int q = 0; q < 4; ++q) {
+      const int64_t p = pb + 32 * q;
+      const bool ok = p < p1;
+      u[q] = ok ? (int64_t)c.g_u[p] : 0;
+      x[q] = ok ? c.g_x[p] : 0.f;
+      xT[q] = ok ? c.g_xT[p] : 0.f;
+    }
+    double r[4][K];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int k = 0; k < K; ++k) r[q][k] = c.rho_u[u[q] * K + k];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double dz1[K], dz2[K];
+      vm_alloc<K>(mut, (double)x[q], (double)xT[q], Gth, Gl, Gnu, dz1, dz2);  // x == 0 for padding lanes
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc += r[q][k] * dz1[k];
+    }
   }
   acc = warp_sum(acc);
   if (lane == 0) part[chunk] = acc;
@@ -110,13 +128,33 @@ __global__ void __launch_bounds__(256) k_phi_partial(const __grid_constant__ vm_
     Gl[k] = c.G_lambda[l * K + k];
     acc[k] = 0.0;
   }
-  for (int64_t e = s0 + threadIdx.x; e < s1; e += 256) {
-    const int64_t u = c.e_u[e];
-    const double Gth = c.G_theta[(int64_t)l * c.M + c.e_m[e]];
-    double dz1[K], dz2[K];
-    vm_alloc<K>(mut, (double)c.e_x[e], (double)c.e_xT[e], Gth, Gl, Gnu, dz1, dz2);
+  for (int64_t eb = s0 + threadIdx.x; eb < s1; eb += 1024) {
+    int64_t u[4];
+    int m[4];
+    float x[4], xT[4];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] += c.rho_u[u * K + k] * dz1[k];
+    for (int q = 0; q < 4; ++q) {
+      const int64_t e = eb + 256 * q;
+      const bool ok = e < s1;
+      u[q] = ok ? (int64_t)c.e_u[e] : 0;
+      m[q] = ok ? c.e_m[e] : 0;
+      x[q] = ok ? c.e_x[e] : 0.f;
+      xT[q] = ok ? c.e_xT[e] : 0.f;
+    }
+    double r[4][K], Gth[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      Gth[q] = c.G_theta[(int64_t)l * c.M + m[q]];
+#pragma unroll
+      for (int k = 0; k < K; ++k) r[q][k] = c.rho_u[u[q] * K + k];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double dz1[K], dz2[K];
+      vm_alloc<K>(mut, (double)x[q], (double)xT[q], Gth[q], Gl, Gnu, dz1, dz2);  // x == 0 for padding
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] += r[q][k] * dz1[k];
+    }
   }
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -302,29 +340,37 @@ __global__ void __launch_bounds__(256, (K <= 2 ? 3 : 2)) k_special(const __grid_
 
   constexpr int TPT = VM_SPECIAL_TIES_PER_BLOCK / 256;
   const int64_t ub = u0 + (int64_t)blockIdx.x * VM_SPECIAL_TIES_PER_BLOCK + threadIdx.x;
-  // index data of the first tie; the next tie's is fetched while the current one is processed
-  int n_lrow = 0, n_col = 0;
-  int64_t n_e0 = 0, n_e1 = 0;
+  // per-tie data of the first tie (incl. its first X entry, stored inline); the next tie's is fetched while the
+  // current one is processed, so only ONE dependent gather level (tables indexed by node / reporter) is exposed
+  int n_lrow = 0, n_col = 0, n_m0 = 0, n_cnt = 0;
+  float n_x0 = 0.f, n_xT0 = 0.f;
   if (ub < u1) {
     n_lrow = c.u_lrow[ub];
     n_col = c.u_col[ub];
-    n_e0 = c.u_ptr[ub];
-    n_e1 = c.u_ptr[ub + 1];
+    n_cnt = c.u_cnt[ub];
+    n_m0 = c.u_m0[ub];
+    n_x0 = c.u_x0[ub];
+    n_xT0 = c.u_xT0[ub];
   }
 #pragma unroll 1
   for (int it = 0; it < TPT; ++it) {
     const int64_t u = ub + it * 256;
     if (u >= u1) break;
     const int64_t lrow = n_lrow;
-    const int j = n_col;
-    const int64_t e0 = n_e0, e1 = n_e1;
+    const int j = n_col, cnt = n_cnt, m0 = n_m0;
+    const float x0 = n_x0, xT0 = n_xT0;
     const int64_t un = u + 256;
     if (it + 1 < TPT && un < u1) {
       n_lrow = c.u_lrow[un];
       n_col = c.u_col[un];
-      n_e0 = c.u_ptr[un];
-      n_e1 = c.u_ptr[un + 1];
+      n_cnt = c.u_cnt[un];
+      n_m0 = c.u_m0[un];
+      n_x0 = c.u_x0[un];
+      n_xT0 = c.u_xT0[un];
     }
+    // the one dependent gather level
+    double2 ge0 = make_double2(0.0, 0.0);
+    if (cnt > 0) ge0 = *reinterpret_cast<const double2*>(c.GE_theta + 2 * ((int64_t)l * c.M + m0));
     const int i = (int)(lrow - (int64_t)l * nloc) + (int)c.row0;
     // independent loads first: prior, closed-form tables, reporter expectations
     double logpr[K];
@@ -352,17 +398,24 @@ __global__ void __launch_bounds__(256, (K <= 2 ? 3 : 2)) k_special(const __grid_
       lw[k] = logpr[k] - S * s_El[k];
       Dz[k] = 0.0;
     }
-    for (int64_t e = e0; e < e1; ++e) {
-      const int64_t lm = (int64_t)l * c.M + c.e_m[e];
-      const double2 ge = *reinterpret_cast<const double2*>(c.GE_theta + 2 * lm);  // (G_theta, Elog_theta)
-      const double x = (double)c.e_x[e];
+    int64_t e0 = 0;
+    if (cnt > 1) e0 = c.u_ptr[u];
+    for (int q = 0; q < cnt; ++q) {
+      double2 ge = ge0;  // (G_theta, Elog_theta)
+      double x = (double)x0, xT = (double)xT0;
+      if (q > 0) {
+        const int64_t e = e0 + q;
+        ge = *reinterpret_cast<const double2*>(c.GE_theta + 2 * ((int64_t)l * c.M + c.e_m[e]));
+        x = (double)c.e_x[e];
+        xT = (double)c.e_xT[e];
+      }
       if (mut) {
-        const double z2 = Gnu * (double)c.e_xT[e];
+        const double z2 = Gnu * xT;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           const double z1 = ge.x * s_Gl[k];
           const double den = z1 + z2;
-          const double xi = (den == 0.0) ? 0.0 : x / den;  // model.py:692 (Q5)
+          const double xi = (den == 0.0) ? 0.0 : x * vm_rcp64(den);  // model.py:692 (Q5)
           lw[k] += (xi * z1) * (ge.y + s_Ell[k]);
           Dz[k] += xi * z2;
         }
@@ -386,7 +439,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? 3 : 2)) k_special(const __grid_
         rho[k] = exp(lw[k] - mx);
         sum += rho[k];
       }
-      const double inv = 1.0 / sum;
+      const double inv = vm_rcp64(sum);
 #pragma unroll
       for (int k = 0; k < K; ++k) rho[k] *= inv;
     }
@@ -409,7 +462,8 @@ __global__ void __launch_bounds__(256, (K <= 2 ? 3 : 2)) k_special(const __grid_
       double erho[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) erho[k] = exp(rho[k]);
-      for (int64_t e = e0; e < e1; ++e) {
+      const int64_t ef = c.u_ptr[u];
+      for (int64_t e = ef; e < ef + cnt; ++e) {
         const int64_t lm = (int64_t)l * c.M + c.e_m[e];
         const double Gth = c.GE_theta[2 * lm], x = (double)c.e_x[e], z2 = Gnu * (double)c.e_xT[e];
         double val = 0.0;
@@ -454,11 +508,27 @@ __global__ void __launch_bounds__(256, (K <= 2 ? 3 : 2)) k_special(const __grid_
 // pointers and row terms of the next row and the patch data of the current row are prefetched before the arithmetic.
 // Column partials of the 8 warps are combined through shared memory once, at the end of the CTA.
 // TW = 128*NCH depends on K so that the column accumulators (NCH*4*(K-1) registers) stay in registers.
+#ifndef VM_NCH2
+#define VM_NCH2 8
+#endif
 template <int K>
 struct DenseCfg {
-  static constexpr int NCH = (K <= 2) ? 8 : (K == 3) ? 4 : (K <= 5) ? 2 : 1;
+  static constexpr int NCH = (K <= 2) ? VM_NCH2 : (K == 3) ? 4 : (K <= 5) ? 2 : 1;
   static constexpr int TW = 128 * NCH;
 };
+
+__device__ __forceinline__ void vm_cp_async4(void* smem, const void* g) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(g));
+}
+__device__ __forceinline__ void vm_cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void vm_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int K>
+__device__ __forceinline__ bool vm_fast_tile(const vm_ctx& c, int l, int ct) {
+  return (((c.N * K) & 3) == 0) && ((int64_t)(ct + 1) * DenseCfg<K>::TW <= c.N) && c.r_mode != VM_R_CSR &&
+         !vm_may_dead<K>(c, l);
+}
 
 // 4 consecutive ties of one lane. a[t][k] are the log2-odds; results in o[t*K+k].
 template <int K, bool ELBO, bool MD>
@@ -483,7 +553,7 @@ __device__ __forceinline__ void dense_quad(const float (*a)[K], int nvalid, floa
 }
 
 template <int K, bool ELBO, bool STORE, bool CSR>
-__global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? 3 : 1) k_dense(const __grid_constant__ vm_ctx c, double* catpart) {
+__global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constant__ vm_ctx c, double* catpart, int skip_fast) {
   constexpr int NCH = DenseCfg<K>::NCH, TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32;
   __shared__ __align__(16) float qs[K][TW];      // column terms of the tile (row 0: weight of k=0, dead check only)
   __shared__ __align__(16) float colbuf[K][TW];  // cross-warp column sums (row 0: dead counts)
@@ -492,6 +562,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? 3 : 1) k
   const int ct = blockIdx.x;
   const int l = blockIdx.y / nrt, rt = blockIdx.y - l * nrt;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (skip_fast && vm_fast_tile<K>(c, l, ct)) return;  // k_dense_fast has written this tile
   const int jt = ct * TW;
   const int i_lo = rt * (int)c.tile_h, i_hi = min(i_lo + (int)c.tile_h, nloc);
   const bool may_dead = vm_may_dead<K>(c, l);
@@ -687,6 +758,183 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? 3 : 1) k
   if (ELBO) {
     const double v = block_sum<VM_DENSE_THREADS>(cat, sm_red);
     if (tid == 0) catpart[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
+  }
+}
+
+// ---- fast variant of the dense kernel ---------------------------------------------------------------------------
+// Same tiling and warp-autonomous structure as k_dense, for the common case: separable mask (ego / all), slab stored,
+// no ELBO, N*K % 4 == 0, column tile entirely inside the matrix, and no row of the layer can underflow completely
+// (checked on the device; k_dense handles every tile this kernel skips).  ~10 instructions per tie, branch-free
+// chunk loop; the patch data of a row are staged with cp.async into shared memory (double-buffered by row), so
+// nothing in the row's arithmetic waits on their DRAM latency.
+#define VM_PATCH_STAGE 64  // special ties of a row segment staged per warp (the rest are fetched directly)
+
+#ifndef VM_FAST_MINBLK2
+#define VM_FAST_MINBLK2 3
+#endif
+#ifndef VM_NCH2
+#define VM_NCH2 8
+#endif
+template <int K>
+__global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2) ? VM_FAST_MINBLK2 : 2) k_dense_fast(const __grid_constant__ vm_ctx c) {
+  constexpr int NCH = DenseCfg<K>::NCH, TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32;
+  __shared__ __align__(16) float qs[K - 1][TW];
+  __shared__ __align__(16) float colbuf[K - 1][TW];
+  __shared__ int pcol[2][NW][VM_PATCH_STAGE];
+  __shared__ float pval[2][NW][VM_PATCH_STAGE][K];
+  const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
+  const int ct = blockIdx.x;
+  const int l = blockIdx.y / nrt, rt = blockIdx.y - l * nrt;
+  if (!vm_fast_tile<K>(c, l, ct)) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int jt = ct * TW;
+  const int i_lo = rt * (int)c.tile_h, i_hi = min(i_lo + (int)c.tile_h, nloc);
+  for (int idx = tid; idx < TW; idx += VM_DENSE_THREADS) {
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+      qs[k - 1][idx] = __ldg(&c.tab_q[((int64_t)l * N + jt + idx) * K + k]);
+      colbuf[k - 1][idx] = 0.f;
+    }
+  }
+  __syncthreads();
+
+  float colacc[NCH][K - 1][4];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+    for (int k = 0; k < K - 1; ++k)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) colacc[ch][k][t] = 0.f;
+
+  int i = i_lo + warp;
+  int ua = 0, ub = 0;
+  float p[K];
+#pragma unroll
+  for (int k = 1; k < K; ++k) p[k] = 0.f;
+  if (i < i_hi) {
+    const int64_t lrow = (int64_t)l * nloc + i;
+    ua = __ldg(&c.utile_ptr[lrow * nct + ct]);
+    ub = __ldg(&c.utile_ptr[lrow * nct + ct + 1]);
+#pragma unroll
+    for (int k = 1; k < K; ++k) p[k] = __ldg(&c.tab_p[lrow * K + k]);
+  }
+  int par = 0;
+  for (; i < i_hi; i += NW, par ^= 1) {
+    const int64_t lrow = (int64_t)l * nloc + i;
+    // ---- stage this row's patch data (asynchronously) and fetch the next row's pointers / row terms
+    const int u_0 = ua + lane, u_1 = ua + 32 + lane;
+    if (u_0 < ub) {
+      vm_cp_async4(&pcol[par][warp][lane], &c.u_col[u_0]);
+#pragma unroll
+      for (int k = 0; k < K; ++k) vm_cp_async4(&pval[par][warp][lane][k], &c.rho_u32[(int64_t)u_0 * K + k]);
+    }
+    if (u_1 < ub) {
+      vm_cp_async4(&pcol[par][warp][lane + 32], &c.u_col[u_1]);
+#pragma unroll
+      for (int k = 0; k < K; ++k) vm_cp_async4(&pval[par][warp][lane + 32][k], &c.rho_u32[(int64_t)u_1 * K + k]);
+    }
+    vm_cp_async_commit();
+    int ua2 = 0, ub2 = 0;
+    float p2[K];
+#pragma unroll
+    for (int k = 1; k < K; ++k) p2[k] = 0.f;
+    if (i + NW < i_hi) {
+      const int64_t lrow2 = lrow + NW;
+      ua2 = __ldg(&c.utile_ptr[lrow2 * nct + ct]);
+      ub2 = __ldg(&c.utile_ptr[lrow2 * nct + ct + 1]);
+#pragma unroll
+      for (int k = 1; k < K; ++k) p2[k] = __ldg(&c.tab_p[lrow2 * K + k]);
+    }
+    // ---- the row: NCH chunks of 128 ties, 4 per lane
+    float rowacc[K];
+#pragma unroll
+    for (int k = 1; k < K; ++k) rowacc[k] = 0.f;
+    float* rowdst = c.rho + lrow * N * K;
+    float* dst = rowdst + (int64_t)(jt + lane * 4) * K;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int jl = ch * 128 + lane * 4;
+      float qv[K][4];
+#pragma unroll
+      for (int k = 1; k < K; ++k) {
+        const float4 t4 = *reinterpret_cast<const float4*>(&qs[k - 1][jl]);
+        qv[k][0] = t4.x;
+        qv[k][1] = t4.y;
+        qv[k][2] = t4.z;
+        qv[k][3] = t4.w;
+      }
+      float o[4 * K];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        // identical operation order to vm_formula_rho: s = ((0 + e1) + e2) + ..., inv = rcp(1 + s)
+        float e[K], s = 0.f;
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+          e[k] = vm_ex2(fminf(__fadd_rn(p[k], qv[k][t]), VM_CLAMP_LOG2));
+          s = (k == 1) ? e[k] : __fadd_rn(s, e[k]);
+        }
+        const float inv = vm_rcp(__fadd_rn(1.f, s));
+        o[t * K] = inv;
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+          const float v = __fmul_rn(e[k], inv);
+          o[t * K + k] = v;
+          colacc[ch][k - 1][t] += v;
+          rowacc[k] += v;
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < K; ++v)
+        reinterpret_cast<float4*>(dst + (int64_t)ch * 128 * K)[v] =
+            make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+    }
+    // ---- row partials
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+      const float v = warp_sum(rowacc[k]);
+      if (lane == 0) c.rowpart[(lrow * nct + ct) * K + k] = v;
+    }
+    if (lane == 0) c.rowpart[(lrow * nct + ct) * K] = 0.f;
+    // ---- patch the special ties of this row segment (after the row's own stores)
+    vm_cp_async_wait_all();
+    __syncwarp();
+    if (u_0 < ub) {
+      float* d = rowdst + (int64_t)pcol[par][warp][lane] * K;
+#pragma unroll
+      for (int k = 0; k < K; ++k) d[k] = pval[par][warp][lane][k];
+    }
+    if (u_1 < ub) {
+      float* d = rowdst + (int64_t)pcol[par][warp][lane + 32] * K;
+#pragma unroll
+      for (int k = 0; k < K; ++k) d[k] = pval[par][warp][lane + 32][k];
+    }
+    for (int u = ua + VM_PATCH_STAGE + lane; u < ub; u += 32) {
+      const int col = c.u_col[u];
+#pragma unroll
+      for (int k = 0; k < K; ++k) rowdst[(int64_t)col * K + k] = c.rho_u32[(int64_t)u * K + k];
+    }
+    ua = ua2;
+    ub = ub2;
+#pragma unroll
+    for (int k = 1; k < K; ++k) p[k] = p2[k];
+  }
+  // ---- column partials: combine the 8 warps in a fixed order
+  for (int w = 0; w < NW; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+        for (int k = 1; k < K; ++k)
+#pragma unroll
+          for (int t = 0; t < 4; ++t) colbuf[k - 1][ch * 128 + lane * 4 + t] += colacc[ch][k - 1][t];
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < TW; idx += VM_DENSE_THREADS) {
+    float* cp = c.colpart + (((int64_t)l * nrt + rt) * N + jt + idx) * K;
+    cp[0] = 0.f;
+#pragma unroll
+    for (int k = 1; k < K; ++k) cp[k] = colbuf[k - 1][idx];
   }
 }
 
@@ -1087,7 +1335,9 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st) {
   const dim3 grid((unsigned)c->nct, (unsigned)(c->L * c->nrt));
   const bool elbo = flags & VM_F_ELBO, store = !(flags & VM_F_NO_STORE), csr = c->r_mode == VM_R_CSR;
   double* cp = region_cat(c);
-#define LD(E, S, C) k_dense<K, E, S, C><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp)
+  const bool fast = !elbo && store && !csr && ((c->N * K) & 3) == 0 && c->nct * c->tile_w > 0 && c->N >= c->tile_w;
+  if (fast) k_dense_fast<K><<<grid, VM_DENSE_THREADS, 0, st>>>(*c);
+#define LD(E, S, C) k_dense<K, E, S, C><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, fast ? 1 : 0)
   if (csr) {
     if (!store) return VM_ENOTSUP;  // the general-mask statistics gather the slab
     if (elbo) LD(true, true, true); else LD(false, true, true);
