@@ -72,7 +72,7 @@ class CaviEngine:
         self.dev_flags = torch.zeros(8, dtype=torch.int64, device=dev)
         assert _packing_const() == self.C["VM_SPECIAL_TIES_PER_BLOCK"]
         n_blk = max(P.n_gchunk, L * P.n_phichunk * K,
-                    L * P.n_ublk * (3 + self.C["VM_MAX_K"]) + P.nct * L * P.nrt + 128 + 2 * 64) + 64
+                    L * P.n_ublk * 8 * (3 + self.C["VM_MAX_K"]) + P.nct * L * P.nrt + 128 + 2 * 64) + 64
         self.blkpart = z(n_blk)
         self.red1, self.red2 = z(L * M), z(L * K)
         self.red3 = z(L * M * K + self.C["VM_R3_EXTRA"])

@@ -96,14 +96,9 @@ __device__ __forceinline__ float vm_rcp(float x) {
   return y;
 }
 
-// fp64 reciprocal: hardware seed + two Newton steps (<= 1 ulp for normal positive inputs; ~3x cheaper than '/')
-__device__ __forceinline__ double vm_rcp64(double a) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
-  r = fma(fma(-a, r, 1.0), r, r);
-  r = fma(fma(-a, r, 1.0), r, r);
-  return r;
-}
+// fp64 reciprocal (IEEE round-to-nearest; cheaper than a full division, no numerator scaling).  NOTE: a hand-rolled
+// `rcp.approx.ftz.f64` + Newton version was tried and miscompiled (register-pair clobber) with nvcc 12.9 -- keep this.
+__device__ __forceinline__ double vm_rcp64(double a) { return __drcp_rn(a); }
 
 // ------------------------------------------------------------------ the per-tie closed form
 // Posterior of a tie that carries no X entry (one-hot prior [1,0,..], model.py:536-556):
@@ -138,6 +133,15 @@ __device__ __forceinline__ void vm_formula_rho(const float* a, bool may_dead, fl
   }
 }
 
+// log1p for fp32: series below 0.05 (exact to ~1e-10 relative), MUFU-based above
+__device__ __forceinline__ float vm_log1p_fast(float x) {
+  if (fabsf(x) < 0.05f) {
+    const float t = -0.16666667f;
+    return x * (1.f + x * (-0.5f + x * (0.33333334f + x * (-0.25f + x * (0.2f + x * t)))));
+  }
+  return __logf(1.f + x);
+}
+
 // categorical ELBO term of such a tie: sum_k rho_k (log(pr_k+EPS) - log(rho_k+EPS)), model.py:1306-1313,
 // written so that the ~1e-12 contributions survive fp32 (log(rho_0+EPS) = log1p(EPS*s) - log1p(s-1)).
 template <int K>
@@ -145,9 +149,9 @@ __device__ __forceinline__ float vm_formula_cat(const float* out, float epsr, bo
                                                 float eps) {
   if (dead) return 0.f;
   const float s = __fadd_rn(1.f, epsr);
-  float t = __fmul_rn(out[0], __fsub_rn(lp0, __fsub_rn(log1pf(__fmul_rn(eps, s)), log1pf(epsr))));
+  float t = __fmul_rn(out[0], __fsub_rn(lp0, __fsub_rn(vm_log1p_fast(__fmul_rn(eps, s)), vm_log1p_fast(epsr))));
 #pragma unroll
-  for (int k = 1; k < K; ++k) t = __fadd_rn(t, __fmul_rn(out[k], __fsub_rn(lpk, logf(__fadd_rn(out[k], eps)))));
+  for (int k = 1; k < K; ++k) t = __fadd_rn(t, __fmul_rn(out[k], __fsub_rn(lpk, __logf(__fadd_rn(out[k], eps)))));
   return t;
 }
 

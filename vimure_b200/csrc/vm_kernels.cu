@@ -9,13 +9,27 @@
 // All reductions are two-pass (block partials, then a fixed-order second pass): results are bit-reproducible
 // run to run. No floating-point atomics anywhere.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "vm_common.cuh"
 
-#define VM_CHECK_LAUNCH()                        \
-  do {                                           \
-    cudaError_t e__ = cudaGetLastError();        \
-    if (e__ != cudaSuccess) return (int)e__;     \
+// VM_DEBUG_SYNC=1 in the environment: synchronise after every launch and report the failing launch site
+static bool vm_debug_sync() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VM_DEBUG_SYNC");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+#define VM_CHECK_LAUNCH()                                                                          \
+  do {                                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                                          \
+    if (e__ == cudaSuccess && vm_debug_sync()) e__ = cudaDeviceSynchronize();                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      if (vm_debug_sync()) fprintf(stderr, "vimure_b200: launch before line %d failed: %s\n", __LINE__, cudaGetErrorString(e__)); \
+      return (int)e__;                                                                             \
+    }                                                                                              \
   } while (0)
 
 // slots of the special-tie block partials, stored slot-major: part[slot * n_upart + block]
@@ -315,14 +329,13 @@ __device__ __forceinline__ void vm_tie_logodds(const vm_ctx& c, int l, int64_t l
 // log rho_k = log(pr_k+EPS) + sum_{entries} dz1_k (E[log theta_m] + E[log lambda_k]) - S E[lambda_k]   (model.py:800-804,
 // 911-921), softmax over k (model.py:807-811), nu statistic (model.py:822-825), ELBO pieces (model.py:967-995, 1306-1313).
 // One thread per tie, VM_SPECIAL_TIES_PER_BLOCK ties per block (4 per thread, strided for coalescing).
-template <int K>
-__global__ void __launch_bounds__(256, (K <= 2 ? 3 : 2)) k_special(const __grid_constant__ vm_ctx c, int flags, double* part) {
-  __shared__ double sm[8];
+template <int K, bool ELBO, int RMODE>
+__global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(const __grid_constant__ vm_ctx c, double* part) {
   __shared__ double s_Gl[K], s_Ell[K], s_El[K];
   const int l = blockIdx.y;
   const int nloc = (int)c.nloc, nct = (int)c.nct;
   const int64_t u0 = c.utile_ptr[(int64_t)l * nloc * nct], u1 = c.utile_ptr[(int64_t)(l + 1) * nloc * nct];
-  const bool elbo = flags & VM_F_ELBO;
+  constexpr bool elbo = ELBO;
   const bool mut = c.mutuality != 0;
   const bool may_dead = vm_may_dead<K>(c, l);
   const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
@@ -380,11 +393,11 @@ __global__ void __launch_bounds__(256, (K <= 2 ? 3 : 2)) k_special(const __grid_
     vm_tie_logodds<K>(c, l, lrow, j, a);
     // S = sum over the tie's reporters of E[theta] * R.vals (model.py:766-792)
     double S;
-    if (c.r_mode == VM_R_EGO) {
+    if (RMODE == VM_R_EGO) {
       const double ti = c.er_node[(int64_t)l * c.N + i];
       const double tj = c.er_node[(int64_t)l * c.N + j];
       S = (i == j) ? (c.ego_diag ? ti : 0.0) : ti + tj;
-    } else if (c.r_mode == VM_R_ALL) {
+    } else if (RMODE == VM_R_ALL) {
       S = lc[VM_LC_SALL(K)];
     } else {
       S = 0.0;
@@ -479,21 +492,23 @@ __global__ void __launch_bounds__(256, (K <= 2 ? 3 : 2)) k_special(const __grid_
                                             (float)c.eps);
     }
   }
-  const int64_t nup = c.L * c.n_ublk, b = (int64_t)l * c.n_ublk + blockIdx.x;
+  // per-WARP partials (no block barrier: a warp retires as soon as its own ties are done)
+  const int64_t nup = c.L * c.n_ublk * 8, b = ((int64_t)l * c.n_ublk + blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   double v;
-  v = block_sum<256>(nu_acc, sm);
-  if (threadIdx.x == 0) part[UP_NU * nup + b] = v;
+  v = warp_sum(nu_acc);
+  if (lane == 0) part[UP_NU * nup + b] = v;
   if (elbo) {
-    v = block_sum<256>(cat_acc, sm);
-    if (threadIdx.x == 0) part[UP_CAT * nup + b] = v;
-    v = block_sum<256>(t2_acc, sm);
-    if (threadIdx.x == 0) part[UP_T2 * nup + b] = v;
+    v = warp_sum(cat_acc);
+    if (lane == 0) part[UP_CAT * nup + b] = v;
+    v = warp_sum(t2_acc);
+    if (lane == 0) part[UP_T2 * nup + b] = v;
   }
-  if (c.r_mode == VM_R_ALL) {  // the all-reporter statistics only need per-layer totals of delta
+  if (RMODE == VM_R_ALL) {  // the all-reporter statistics only need per-layer totals of delta
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      v = block_sum<256>(dsum[k], sm);
-      if (threadIdx.x == 0) part[(UP_DELTA + k) * nup + b] = v;
+      v = warp_sum(dsum[k]);
+      if (lane == 0) part[(UP_DELTA + k) * nup + b] = v;
     }
   }
 }
@@ -509,7 +524,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? 3 : 2)) k_special(const __grid_
 // Column partials of the 8 warps are combined through shared memory once, at the end of the CTA.
 // TW = 128*NCH depends on K so that the column accumulators (NCH*4*(K-1) registers) stay in registers.
 #ifndef VM_NCH2
-#define VM_NCH2 8
+#define VM_NCH2 4
 #endif
 template <int K>
 struct DenseCfg {
@@ -530,10 +545,62 @@ __device__ __forceinline__ bool vm_fast_tile(const vm_ctx& c, int l, int ct) {
          !vm_may_dead<K>(c, l);
 }
 
-// 4 consecutive ties of one lane. a[t][k] are the log2-odds; results in o[t*K+k].
+// ---- lane <-> tie mapping inside a 128-tie chunk ------------------------------------------------------------------
+// Measured on B200 (tools/write_bw.cu): a warp store instruction whose 32 lanes write 16 B each at a 32 B stride
+// (every lane owning 32 contiguous bytes) reaches only 3.8 TB/s, while fully contiguous 512 B per instruction reaches
+// 6.8-7.1 TB/s.  So the 4 ties of a lane are chosen such that EVERY 128-bit store instruction of the warp covers 512
+// contiguous bytes: K=2 -> ties {2i, 2i+1, 64+2i, 64+2i+1};  K=4 -> ties {i, 32+i, 64+i, 96+i};  other K -> the natural
+// {4i..4i+3} with a transpose through a per-warp shared-memory stage.
+template <int K>
+__device__ __forceinline__ int vm_tie_of(int lane, int t) {
+  if (K == 2) return (t < 2) ? (2 * lane + t) : (64 + 2 * lane + (t - 2));
+  if (K == 4) return 32 * t + lane;
+  return 4 * lane + t;
+}
+template <int K>
+__device__ __forceinline__ void vm_load_q4(const float* qrow_chunk, int lane, float* out) {
+  if (K == 2) {
+    const float2 a = *reinterpret_cast<const float2*>(qrow_chunk + 2 * lane);
+    const float2 b = *reinterpret_cast<const float2*>(qrow_chunk + 64 + 2 * lane);
+    out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+  } else if (K == 4) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) out[t] = qrow_chunk[32 * t + lane];
+  } else {
+    const float4 v = *reinterpret_cast<const float4*>(qrow_chunk + 4 * lane);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+  }
+}
+// store the 4 ties of every lane (o[t*K+k]) of one chunk; `dst` = first float of the chunk (16-byte aligned)
+template <int K>
+__device__ __forceinline__ void vm_store_chunk(float* dst, int lane, const float* o, float* stage) {
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  if (K == 2) {
+    d4[lane] = make_float4(o[0], o[1], o[2], o[3]);
+    d4[32 + lane] = make_float4(o[4], o[5], o[6], o[7]);
+  } else if (K == 4) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) d4[32 * t + lane] = make_float4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
+  } else {
+    float4* s4 = reinterpret_cast<float4*>(stage);
+#pragma unroll
+    for (int v = 0; v < K; ++v) s4[K * lane + v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int v = 0; v < K; ++v) d4[32 * v + lane] = s4[32 * v + lane];
+    __syncwarp();
+  }
+}
+template <int K>
+struct StageCfg {
+  static constexpr int FLOATS = (K == 2 || K == 4) ? 4 : 128 * K;  // per-warp stage (unused for K = 2, 4)
+};
+
+// 4 ties of one lane. a[t][k] are the log2-odds; results in o[t*K+k].
 template <int K, bool ELBO, bool MD>
-__device__ __forceinline__ void dense_quad(const float (*a)[K], int nvalid, float* o, float* rowacc, float (*colacc)[4],
-                                           float* coldead, double& cat, float lp0, float lpk, float epsf) {
+__device__ __forceinline__ void dense_quad(const float (*a)[K], const bool* valid, float* o, float* rowacc,
+                                           float (*colacc)[4], float* coldead_chunk, int lane, double& cat, float lp0,
+                                           float lpk, float epsf) {
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     float epsr;
@@ -544,19 +611,21 @@ __device__ __forceinline__ void dense_quad(const float (*a)[K], int nvalid, floa
       colacc[k - 1][t] += o[t * K + k];
       rowacc[k] += o[t * K + k];
     }
-    if (MD && dead && t < nvalid) {
+    if (MD && dead && valid[t]) {
       rowacc[0] += 1.f;
-      atomicAdd(&coldead[t], 1.f);  // integer-valued: exact in any order
+      atomicAdd(&coldead_chunk[vm_tie_of<K>(lane, t)], 1.f);  // integer-valued: exact in any order
     }
-    if (ELBO && t < nvalid) cat += (double)vm_formula_cat<K>(&o[t * K], epsr, dead, lp0, lpk, epsf);
+    if (ELBO && valid[t]) cat += (double)vm_formula_cat<K>(&o[t * K], epsr, dead, lp0, lpk, epsf);
   }
 }
 
+// Generic dense kernel: any mask structure, ELBO partials, dead-row bookkeeping, partial tiles.
 template <int K, bool ELBO, bool STORE, bool CSR>
 __global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constant__ vm_ctx c, double* catpart, int skip_fast) {
   constexpr int NCH = DenseCfg<K>::NCH, TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32;
   __shared__ __align__(16) float qs[K][TW];      // column terms of the tile (row 0: weight of k=0, dead check only)
   __shared__ __align__(16) float colbuf[K][TW];  // cross-warp column sums (row 0: dead counts)
+  __shared__ __align__(16) float stage[NW][StageCfg<K>::FLOATS];
   __shared__ double sm_red[8];
   const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
   const int ct = blockIdx.x;
@@ -594,110 +663,69 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constan
       for (int t = 0; t < 4; ++t) colacc[ch][k][t] = 0.f;
   double cat = 0.0;
 
-  int i = i_lo + warp;
-  int ua = 0, ub = 0;
-  float p[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) p[k] = 0.f;
-  if (i < i_hi) {
+  for (int i = i_lo + warp; i < i_hi; i += NW) {
     const int64_t lrow = (int64_t)l * nloc + i;
+    int ua = 0, ub = 0;
     if (STORE) {
       ua = __ldg(&c.utile_ptr[lrow * nct + ct]);
       ub = __ldg(&c.utile_ptr[lrow * nct + ct + 1]);
     }
-    if (!CSR) {
+    float p[K];
 #pragma unroll
-      for (int k = 0; k < K; ++k) p[k] = __ldg(&c.tab_p[lrow * K + k]);
-    }
-  }
-  for (; i < i_hi; i += NW) {
-    const int64_t lrow = (int64_t)l * nloc + i;
-    // ---- prefetch: next row's tile pointers and row terms, this row's patch data (first 64 special ties)
-    int ua2 = 0, ub2 = 0;
-    float p2[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) p2[k] = 0.f;
-    if (i + NW < i_hi) {
-      const int64_t lrow2 = lrow + NW;
-      if (STORE) {
-        ua2 = __ldg(&c.utile_ptr[lrow2 * nct + ct]);
-        ub2 = __ldg(&c.utile_ptr[lrow2 * nct + ct + 1]);
-      }
-      if (!CSR) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) p2[k] = __ldg(&c.tab_p[lrow2 * K + k]);
-      }
-    }
-    int pc0 = 0, pc1 = 0;
-    float pv0[K], pv1[K];
-    const int u_0 = ua + lane, u_1 = ua + 32 + lane;
-    if (STORE) {
-      if (u_0 < ub) {
-        pc0 = __ldg(&c.u_col[u_0]);
-#pragma unroll
-        for (int k = 0; k < K; ++k) pv0[k] = __ldg(&c.rho_u32[(int64_t)u_0 * K + k]);
-      }
-      if (u_1 < ub) {
-        pc1 = __ldg(&c.u_col[u_1]);
-#pragma unroll
-        for (int k = 0; k < K; ++k) pv1[k] = __ldg(&c.rho_u32[(int64_t)u_1 * K + k]);
-      }
-    }
-    // ---- the row
+    for (int k = 0; k < K; ++k) p[k] = CSR ? 0.f : __ldg(&c.tab_p[lrow * K + k]);
     float rowacc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) rowacc[k] = 0.f;
     float* rowdst = c.rho + lrow * N * K;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
-      const int jl = ch * 128 + lane * 4;
-      const int j = jt + jl;
-      const int nvalid = min(4, N - j);
-      if (nvalid <= 0) continue;
+      const int jc = jt + ch * 128;  // first column of the chunk
+      if (jc >= N) continue;         // warp-uniform
+      bool valid[4];
+      int jj[4];
+      bool all_valid = true;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        jj[t] = jc + vm_tie_of<K>(lane, t);
+        valid[t] = jj[t] < N;
+        all_valid = all_valid && valid[t];
+      }
       float a[4][K];
       if (CSR) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const float s = (t < nvalid) ? vm_csr_S32(c, l, lrow * N + j + t) : 0.f;
+          const float sv = valid[t] ? vm_csr_S32(c, l, lrow * N + jj[t]) : 0.f;
 #pragma unroll
-          for (int k = 0; k < K; ++k) a[t][k] = (t < nvalid) ? __fmaf_rn(-s, dd[k], cc[k]) : -INFINITY;
+          for (int k = 0; k < K; ++k) a[t][k] = valid[t] ? __fmaf_rn(-sv, dd[k], cc[k]) : -INFINITY;
         }
       } else {
 #pragma unroll
-        for (int k = 1; k < K; ++k) {
-          const float4 qv = *reinterpret_cast<const float4*>(&qs[k][jl]);
-          a[0][k] = __fadd_rn(p[k], qv.x);
-          a[1][k] = __fadd_rn(p[k], qv.y);
-          a[2][k] = __fadd_rn(p[k], qv.z);
-          a[3][k] = __fadd_rn(p[k], qv.w);
-        }
-        if (may_dead) {
-          const float4 qv = *reinterpret_cast<const float4*>(&qs[0][jl]);
-          a[0][0] = __fadd_rn(p[0], qv.x);
-          a[1][0] = __fadd_rn(p[0], qv.y);
-          a[2][0] = __fadd_rn(p[0], qv.z);
-          a[3][0] = __fadd_rn(p[0], qv.w);
-        } else {
-          a[0][0] = a[1][0] = a[2][0] = a[3][0] = 0.f;
+        for (int k = 0; k < K; ++k) {
+          if (k == 0 && !may_dead) {
+            a[0][0] = a[1][0] = a[2][0] = a[3][0] = 0.f;
+            continue;
+          }
+          float qv[4];
+          vm_load_q4<K>(&qs[k][ch * 128], lane, qv);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) a[t][k] = __fadd_rn(p[k], qv[t]);
         }
       }
       float o[4 * K];
       if (may_dead)
-        dense_quad<K, ELBO, true>(a, nvalid, o, rowacc, colacc[ch], &colbuf[0][jl], cat, lp0, lpk, epsf);
+        dense_quad<K, ELBO, true>(a, valid, o, rowacc, colacc[ch], &colbuf[0][ch * 128], lane, cat, lp0, lpk, epsf);
       else
-        dense_quad<K, ELBO, false>(a, nvalid, o, rowacc, colacc[ch], &colbuf[0][jl], cat, lp0, lpk, epsf);
+        dense_quad<K, ELBO, false>(a, valid, o, rowacc, colacc[ch], &colbuf[0][ch * 128], lane, cat, lp0, lpk, epsf);
       if (STORE) {
-        float* dst = rowdst + (int64_t)j * K;
-        if (vec_ok && nvalid == 4) {
-#pragma unroll
-          for (int v = 0; v < K; ++v)
-            reinterpret_cast<float4*>(dst)[v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+        const bool chunk_full = jc + 128 <= N;  // warp-uniform
+        if (vec_ok && chunk_full) {
+          vm_store_chunk<K>(rowdst + (int64_t)jc * K, lane, o, stage[warp]);
         } else {
 #pragma unroll
           for (int t = 0; t < 4; ++t)
-            if (t < nvalid) {
+            if (valid[t]) {
 #pragma unroll
-              for (int k = 0; k < K; ++k) dst[t * K + k] = o[t * K + k];
+              for (int k = 0; k < K; ++k) rowdst[(int64_t)jj[t] * K + k] = o[t * K + k];
             }
         }
       }
@@ -715,24 +743,12 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constan
     // ---- patch the special ties of this row segment
     if (STORE) {
       __syncwarp();
-      if (u_0 < ub) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) rowdst[(int64_t)pc0 * K + k] = pv0[k];
-      }
-      if (u_1 < ub) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) rowdst[(int64_t)pc1 * K + k] = pv1[k];
-      }
-      for (int u = ua + 64 + lane; u < ub; u += 32) {
+      for (int u = ua + lane; u < ub; u += 32) {
         const int col = c.u_col[u];
 #pragma unroll
         for (int k = 0; k < K; ++k) rowdst[(int64_t)col * K + k] = c.rho_u32[(int64_t)u * K + k];
       }
     }
-    ua = ua2;
-    ub = ub2;
-#pragma unroll
-    for (int k = 0; k < K; ++k) p[k] = p2[k];
   }
   // ---- column partials: combine the 8 warps in a fixed order
   if (!CSR) {
@@ -743,7 +759,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constan
 #pragma unroll
           for (int k = 1; k < K; ++k)
 #pragma unroll
-            for (int t = 0; t < 4; ++t) colbuf[k][ch * 128 + lane * 4 + t] += colacc[ch][k - 1][t];
+            for (int t = 0; t < 4; ++t) colbuf[k][ch * 128 + vm_tie_of<K>(lane, t)] += colacc[ch][k - 1][t];
       }
       __syncthreads();
     }
@@ -765,30 +781,39 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constan
 // Same tiling and warp-autonomous structure as k_dense, for the common case: separable mask (ego / all), slab stored,
 // no ELBO, N*K % 4 == 0, column tile entirely inside the matrix, and no row of the layer can underflow completely
 // (checked on the device; k_dense handles every tile this kernel skips).  ~10 instructions per tie, branch-free
-// chunk loop; the patch data of a row are staged with cp.async into shared memory (double-buffered by row), so
-// nothing in the row's arithmetic waits on their DRAM latency.
-#define VM_PATCH_STAGE 64  // special ties of a row segment staged per warp (the rest are fetched directly)
+// chunk loop.  Everything the row loop needs from global memory (column/row terms, tile pointers) is fetched once
+// per CTA, and the patch data of the warp's rows are staged with cp.async into shared memory up front, so nothing
+// in the row loop waits on a load.
+#define VM_FAST_MAX_TILE_H 128
+
+template <int K>
+struct FastCfg {
+  // special ties staged per warp (all the rows of the warp); the rest are fetched directly
+  static constexpr int CAPW = (K <= 2) ? 384 : (K == 4) ? 192 : 64;
+};
 
 #ifndef VM_FAST_MINBLK2
-#define VM_FAST_MINBLK2 3
-#endif
-#ifndef VM_NCH2
-#define VM_NCH2 8
+#define VM_FAST_MINBLK2 4
 #endif
 template <int K>
 __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2) ? VM_FAST_MINBLK2 : 2) k_dense_fast(const __grid_constant__ vm_ctx c) {
-  constexpr int NCH = DenseCfg<K>::NCH, TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32;
+  constexpr int NCH = DenseCfg<K>::NCH, TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32, CAPW = FastCfg<K>::CAPW;
   __shared__ __align__(16) float qs[K - 1][TW];
   __shared__ __align__(16) float colbuf[K - 1][TW];
-  __shared__ int pcol[2][NW][VM_PATCH_STAGE];
-  __shared__ float pval[2][NW][VM_PATCH_STAGE][K];
+  __shared__ __align__(16) float stage[NW][StageCfg<K>::FLOATS];
+  __shared__ float ps[K - 1][VM_FAST_MAX_TILE_H];
+  __shared__ int tp0[VM_FAST_MAX_TILE_H], tp1[VM_FAST_MAX_TILE_H];
+  __shared__ int pcol[NW][CAPW];
+  __shared__ float pval[NW][CAPW][K];
   const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
   const int ct = blockIdx.x;
   const int l = blockIdx.y / nrt, rt = blockIdx.y - l * nrt;
   if (!vm_fast_tile<K>(c, l, ct)) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int jt = ct * TW;
-  const int i_lo = rt * (int)c.tile_h, i_hi = min(i_lo + (int)c.tile_h, nloc);
+  const int i_lo = rt * (int)c.tile_h;
+  const int nrows = min((int)c.tile_h, nloc - i_lo);
+  // ---- phase 0: everything the row loop reads from global memory, once per CTA
   for (int idx = tid; idx < TW; idx += VM_DENSE_THREADS) {
 #pragma unroll
     for (int k = 1; k < K; ++k) {
@@ -796,8 +821,30 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2) ? VM_FAST_MINBLK2 :
       colbuf[k - 1][idx] = 0.f;
     }
   }
+  for (int r = tid; r < nrows; r += VM_DENSE_THREADS) {
+    const int64_t lrow = (int64_t)l * nloc + i_lo + r;
+#pragma unroll
+    for (int k = 1; k < K; ++k) ps[k - 1][r] = __ldg(&c.tab_p[lrow * K + k]);
+    tp0[r] = __ldg(&c.utile_ptr[lrow * nct + ct]);
+    tp1[r] = __ldg(&c.utile_ptr[lrow * nct + ct + 1]);
+  }
   __syncthreads();
-
+  // ---- phase 1: stage the patch data of this warp's rows asynchronously
+  {
+    int off = 0;
+    for (int r = warp; r < nrows; r += NW) {
+      const int ua = tp0[r], n = tp1[r] - ua;
+      const int take = min(n, CAPW - off);
+      for (int e = lane; e < take; e += 32) {
+        vm_cp_async4(&pcol[warp][off + e], &c.u_col[ua + e]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) vm_cp_async4(&pval[warp][off + e][k], &c.rho_u32[(int64_t)(ua + e) * K + k]);
+      }
+      off += take;
+    }
+    vm_cp_async_commit();
+  }
+  // ---- phase 2: the rows (no global loads on the critical path)
   float colacc[NCH][K - 1][4];
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch)
@@ -805,64 +852,23 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2) ? VM_FAST_MINBLK2 :
     for (int k = 0; k < K - 1; ++k)
 #pragma unroll
       for (int t = 0; t < 4; ++t) colacc[ch][k][t] = 0.f;
-
-  int i = i_lo + warp;
-  int ua = 0, ub = 0;
-  float p[K];
+  int off = 0;
+  bool waited = false;
+  for (int r = warp; r < nrows; r += NW) {
+    const int64_t lrow = (int64_t)l * nloc + i_lo + r;
+    float p[K];
 #pragma unroll
-  for (int k = 1; k < K; ++k) p[k] = 0.f;
-  if (i < i_hi) {
-    const int64_t lrow = (int64_t)l * nloc + i;
-    ua = __ldg(&c.utile_ptr[lrow * nct + ct]);
-    ub = __ldg(&c.utile_ptr[lrow * nct + ct + 1]);
-#pragma unroll
-    for (int k = 1; k < K; ++k) p[k] = __ldg(&c.tab_p[lrow * K + k]);
-  }
-  int par = 0;
-  for (; i < i_hi; i += NW, par ^= 1) {
-    const int64_t lrow = (int64_t)l * nloc + i;
-    // ---- stage this row's patch data (asynchronously) and fetch the next row's pointers / row terms
-    const int u_0 = ua + lane, u_1 = ua + 32 + lane;
-    if (u_0 < ub) {
-      vm_cp_async4(&pcol[par][warp][lane], &c.u_col[u_0]);
-#pragma unroll
-      for (int k = 0; k < K; ++k) vm_cp_async4(&pval[par][warp][lane][k], &c.rho_u32[(int64_t)u_0 * K + k]);
-    }
-    if (u_1 < ub) {
-      vm_cp_async4(&pcol[par][warp][lane + 32], &c.u_col[u_1]);
-#pragma unroll
-      for (int k = 0; k < K; ++k) vm_cp_async4(&pval[par][warp][lane + 32][k], &c.rho_u32[(int64_t)u_1 * K + k]);
-    }
-    vm_cp_async_commit();
-    int ua2 = 0, ub2 = 0;
-    float p2[K];
-#pragma unroll
-    for (int k = 1; k < K; ++k) p2[k] = 0.f;
-    if (i + NW < i_hi) {
-      const int64_t lrow2 = lrow + NW;
-      ua2 = __ldg(&c.utile_ptr[lrow2 * nct + ct]);
-      ub2 = __ldg(&c.utile_ptr[lrow2 * nct + ct + 1]);
-#pragma unroll
-      for (int k = 1; k < K; ++k) p2[k] = __ldg(&c.tab_p[lrow2 * K + k]);
-    }
-    // ---- the row: NCH chunks of 128 ties, 4 per lane
+    for (int k = 1; k < K; ++k) p[k] = ps[k - 1][r];
     float rowacc[K];
 #pragma unroll
     for (int k = 1; k < K; ++k) rowacc[k] = 0.f;
     float* rowdst = c.rho + lrow * N * K;
-    float* dst = rowdst + (int64_t)(jt + lane * 4) * K;
+    float* dst = rowdst + (int64_t)jt * K;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
-      const int jl = ch * 128 + lane * 4;
       float qv[K][4];
 #pragma unroll
-      for (int k = 1; k < K; ++k) {
-        const float4 t4 = *reinterpret_cast<const float4*>(&qs[k - 1][jl]);
-        qv[k][0] = t4.x;
-        qv[k][1] = t4.y;
-        qv[k][2] = t4.z;
-        qv[k][3] = t4.w;
-      }
+      for (int k = 1; k < K; ++k) vm_load_q4<K>(&qs[k - 1][ch * 128], lane, qv[k]);
       float o[4 * K];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -883,10 +889,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2) ? VM_FAST_MINBLK2 :
           rowacc[k] += v;
         }
       }
-#pragma unroll
-      for (int v = 0; v < K; ++v)
-        reinterpret_cast<float4*>(dst + (int64_t)ch * 128 * K)[v] =
-            make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+      vm_store_chunk<K>(dst + (int64_t)ch * 128 * K, lane, o, stage[warp]);
     }
     // ---- row partials
 #pragma unroll
@@ -896,27 +899,24 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2) ? VM_FAST_MINBLK2 :
     }
     if (lane == 0) c.rowpart[(lrow * nct + ct) * K] = 0.f;
     // ---- patch the special ties of this row segment (after the row's own stores)
-    vm_cp_async_wait_all();
+    if (!waited) {
+      vm_cp_async_wait_all();
+      waited = true;
+    }
     __syncwarp();
-    if (u_0 < ub) {
-      float* d = rowdst + (int64_t)pcol[par][warp][lane] * K;
+    const int ua = tp0[r], n = tp1[r] - ua;
+    const int take = min(n, CAPW - off);
+    for (int e = lane; e < take; e += 32) {
+      float* d = rowdst + (int64_t)pcol[warp][off + e] * K;
 #pragma unroll
-      for (int k = 0; k < K; ++k) d[k] = pval[par][warp][lane][k];
+      for (int k = 0; k < K; ++k) d[k] = pval[warp][off + e][k];
     }
-    if (u_1 < ub) {
-      float* d = rowdst + (int64_t)pcol[par][warp][lane + 32] * K;
+    for (int e = take + lane; e < n; e += 32) {
+      const int col = c.u_col[ua + e];
 #pragma unroll
-      for (int k = 0; k < K; ++k) d[k] = pval[par][warp][lane + 32][k];
+      for (int k = 0; k < K; ++k) rowdst[(int64_t)col * K + k] = c.rho_u32[(int64_t)(ua + e) * K + k];
     }
-    for (int u = ua + VM_PATCH_STAGE + lane; u < ub; u += 32) {
-      const int col = c.u_col[u];
-#pragma unroll
-      for (int k = 0; k < K; ++k) rowdst[(int64_t)col * K + k] = c.rho_u32[(int64_t)u * K + k];
-    }
-    ua = ua2;
-    ub = ub2;
-#pragma unroll
-    for (int k = 1; k < K; ++k) p[k] = p2[k];
+    off += take;
   }
   // ---- column partials: combine the 8 warps in a fixed order
   for (int w = 0; w < NW; ++w) {
@@ -926,7 +926,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2) ? VM_FAST_MINBLK2 :
 #pragma unroll
         for (int k = 1; k < K; ++k)
 #pragma unroll
-          for (int t = 0; t < 4; ++t) colbuf[k - 1][ch * 128 + lane * 4 + t] += colacc[ch][k - 1][t];
+          for (int t = 0; t < 4; ++t) colbuf[k - 1][ch * 128 + vm_tie_of<K>(lane, t)] += colacc[ch][k - 1][t];
     }
     __syncthreads();
   }
@@ -1030,7 +1030,7 @@ __global__ void __launch_bounds__(256) k_stats_all(const __grid_constant__ vm_ct
   __shared__ double sm[8];
   __shared__ double tot[K];
   const int l = blockIdx.x;
-  const int64_t nrow = c.nloc * c.nct, nup = c.L * c.n_ublk;
+  const int64_t nrow = c.nloc * c.nct, nup = c.L * c.n_ublk * 8, nwl = c.n_ublk * 8;
   double f[K], d[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) f[k] = d[k] = 0.0;
@@ -1039,9 +1039,9 @@ __global__ void __launch_bounds__(256) k_stats_all(const __grid_constant__ vm_ct
 #pragma unroll
       for (int k = 0; k < K; ++k) f[k] += (double)c.rowpart[((int64_t)l * nrow + t) * K + k];
     }
-  for (int64_t b = threadIdx.x; b < c.n_ublk; b += 256) {
+  for (int64_t b = threadIdx.x; b < nwl; b += 256) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) d[k] += upart[(UP_DELTA + k) * nup + (int64_t)l * c.n_ublk + b];
+    for (int k = 0; k < K; ++k) d[k] += upart[(UP_DELTA + k) * nup + (int64_t)l * nwl + b];
   }
   double fs[K], ds[K];
 #pragma unroll
@@ -1097,7 +1097,7 @@ __global__ void __launch_bounds__(256) k_init_delta_all(const __grid_constant__ 
   __shared__ double sm[8];
   const int l = blockIdx.y;
   const int64_t u0 = c.utile_ptr[(int64_t)l * c.nloc * c.nct], u1 = c.utile_ptr[(int64_t)(l + 1) * c.nloc * c.nct];
-  const int64_t nup = c.L * c.n_ublk;
+  const int64_t nup = c.L * c.n_ublk * 8;
   for (int k = 0; k < (int)c.K; ++k) {
     double acc = 0.0;
     for (int r = 0; r < VM_SPECIAL_TIES_PER_BLOCK / 256; ++r) {
@@ -1105,7 +1105,8 @@ __global__ void __launch_bounds__(256) k_init_delta_all(const __grid_constant__ 
       if (u < u1) acc += c.delta_u[u * c.K + k];
     }
     const double v = block_sum<256>(acc, sm);
-    if (threadIdx.x == 0) upart[(UP_DELTA + k) * nup + (int64_t)l * c.n_ublk + blockIdx.x] = v;
+    if (threadIdx.x < 8)  // warp-partial layout of k_special: the block total goes to warp slot 0
+      upart[(UP_DELTA + k) * nup + ((int64_t)l * c.n_ublk + blockIdx.x) * 8 + threadIdx.x] = threadIdx.x == 0 ? v : 0.0;
   }
 }
 
@@ -1288,7 +1289,7 @@ static inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 
 // blkpart regions (doubles)
 static inline double* region_u(const vm_ctx* c) { return c->blkpart; }  // special-tie block partials
-static inline int64_t n_upart(const vm_ctx* c) { return c->L * c->n_ublk; }
+static inline int64_t n_upart(const vm_ctx* c) { return c->L * c->n_ublk * 8; }  // one partial per warp
 static inline double* region_cat(const vm_ctx* c) { return c->blkpart + n_upart(c) * UP_SLOTS; }
 static inline int64_t n_catpart(const vm_ctx* c) { return c->nct * c->L * c->nrt; }
 static inline double* region_b(const vm_ctx* c) { return region_cat(c) + n_catpart(c); }
@@ -1335,8 +1336,9 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st) {
   const dim3 grid((unsigned)c->nct, (unsigned)(c->L * c->nrt));
   const bool elbo = flags & VM_F_ELBO, store = !(flags & VM_F_NO_STORE), csr = c->r_mode == VM_R_CSR;
   double* cp = region_cat(c);
-  const bool fast = !elbo && store && !csr && ((c->N * K) & 3) == 0 && c->nct * c->tile_w > 0 && c->N >= c->tile_w;
-  if (fast) k_dense_fast<K><<<grid, VM_DENSE_THREADS, 0, st>>>(*c);
+  const bool fast = K <= 4 && !elbo && store && !csr && ((c->N * K) & 3) == 0 && c->N >= c->tile_w &&
+                    c->tile_h <= VM_FAST_MAX_TILE_H;
+  if (fast) k_dense_fast<(K <= 4 ? K : 2)><<<grid, VM_DENSE_THREADS, 0, st>>>(*c);
 #define LD(E, S, C) k_dense<K, E, S, C><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, fast ? 1 : 0)
   if (csr) {
     if (!store) return VM_ENOTSUP;  // the general-mask statistics gather the slab
@@ -1347,6 +1349,22 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st) {
     if (store) LD(false, true, false); else LD(false, false, false);
   }
 #undef LD
+  return 0;
+}
+
+template <int K>
+static int launch_special(const vm_ctx* c, int flags, cudaStream_t st) {
+  const dim3 grid((unsigned)c->n_ublk, (unsigned)c->L);
+  const bool elbo = flags & VM_F_ELBO;
+#define LS(E, M) k_special<K, E, M><<<grid, 256, 0, st>>>(*c, region_u(c))
+  if (c->r_mode == VM_R_EGO) {
+    if (elbo) LS(true, VM_R_EGO); else LS(false, VM_R_EGO);
+  } else if (c->r_mode == VM_R_ALL) {
+    if (elbo) LS(true, VM_R_ALL); else LS(false, VM_R_ALL);
+  } else {
+    if (elbo) LS(true, VM_R_CSR); else LS(false, VM_R_CSR);
+  }
+#undef LS
   return 0;
 }
 
@@ -1446,7 +1464,7 @@ extern "C" int vm_phase_rho(const vm_ctx* c, int flags, void* stream) {
     DISPATCH_K(c->K, (k_tables<K><<<(unsigned)cdiv(c->L * c->N, 256), 256, 0, st>>>(*c)));
     VM_CHECK_LAUNCH();
   }
-  DISPATCH_K(c->K, (k_special<K><<<dim3((unsigned)c->n_ublk, (unsigned)c->L), 256, 0, st>>>(*c, flags, region_u(c))));
+  DISPATCH_K(c->K, launch_special<K>(c, flags, st));
   VM_CHECK_LAUNCH();
   DISPATCH_K(c->K, rc = launch_dense<K>(c, flags, st));
   if (rc) return rc;
