@@ -140,41 +140,49 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.samples, self.stop = index, [], False
-        self.th = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        while not self.stop:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.samples.append([x.strip() for x in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        self.index, self.samples, self.proc = index, [], None
 
     def __enter__(self):
-        self.th.start()
+        # ONE long-lived nvidia-smi sampling every 20 ms (spawning one per sample is too slow for a ~0.1 s region)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)  # let it start emitting before the timed region opens
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop = True
-        self.th.join(timeout=6)
+        if self.proc is None:
+            return
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        for line in out.strip().splitlines():
+            self.samples.append([x.strip() for x in line.split(",")])
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        rows, reasons = [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for s in self.samples:
             try:
-                sm.append(float(s[0]))
-                mx.append(float(s[1]))
+                rows.append((float(s[0]), float(s[1]), float(s[2])))
                 for nm, v in zip(names, s[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        pmax = max(r[2] for r in rows)
+        load = [r for r in rows if r[2] >= 0.6 * pmax] or rows  # samples taken under load
+        return {"sm_mhz": float(np.median([r[0] for r in load])), "sm_max_mhz": max(r[1] for r in rows),
+                "power_w_max": pmax, "reasons": sorted(reasons), "samples": len(rows), "samples_under_load": len(load)}
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
@@ -310,6 +318,7 @@ def run_ours(args):
             wall = float(t.item())
         e2e = {"value": args.steps * T / wall, "unit": "ties/s", "h2d_bytes_per_step": h2d / args.steps,
                "d2h_bytes_per_step": d2h / args.steps, "wall_s": wall, "pack_s": model.pack_time,
+               "timings_s": {k: round(v, 4) for k, v in model.timings.items()},
                "what": "VimureModel.fit(X host COO, R=EgoMask, max_iter=steps): pack + H2D + CAVI + ELBO + D2H of "
                        "gamma/phi/nu posteriors; rho stays on the device"}
         del model

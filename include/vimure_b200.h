@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VM_ABI_VERSION 6
+#define VM_ABI_VERSION 7
 
 /* reporter-mask structure (how R[l,i,j,m] is represented) */
 #define VM_R_EGO 0 /* reporter m == node m reports row m and column m (vimure synthetic.py:1184-1204, _io.py:229-242) */
@@ -161,6 +161,9 @@ typedef struct vm_ctx {
   double* er_node;          /* [L*N] EGO: E[theta] of node n acting as reporter (0 if not an active reporter) */
   double* colsum;           /* [L*M*K] column partials reduced over the row tiles */
   int64_t* dev_flags;       /* [8] [0]: a special tie underflowed completely in the last rho update */
+  int64_t* fixA;            /* [L*M*K] EGO: per-reporter sums of (special - closed form), fixed point 2^-44, accumulated
+                               with integer atomics (order-independent => bit-reproducible); slot k=0 holds only the
+                               residual count (live special) - (live closed form) */
   double* blkpart;          /* [max(n_ublk, nct*L*nrt, L*n_phichunk*K, n_gchunk, ...)*4] */
   double* red1;             /* [L*M] gamma-shape sums (all-reduced by the host between phases when sharded) */
   double* red2;             /* [L*K] phi-shape sums */

@@ -70,6 +70,7 @@ class CaviEngine:
         self.er_node = z(L * N)
         self.colsum = z(L * M * K)
         self.dev_flags = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.fixA = torch.zeros(L * M * K, dtype=torch.int64, device=dev)
         assert _packing_const() == self.C["VM_SPECIAL_TIES_PER_BLOCK"]
         n_blk = max(P.n_gchunk, L * P.n_phichunk * K,
                     L * P.n_ublk * 8 * (3 + self.C["VM_MAX_K"]) + P.nct * L * P.nrt + 128 + 2 * 64) + 64
@@ -102,7 +103,7 @@ class CaviEngine:
         for name in ("u_logpr", "alpha_theta", "beta_theta", "alpha_lambda", "beta_lambda", "gamma_shp", "gamma_rte",
                      "phi_shp", "phi_rte", "nu", "G_theta", "E_theta", "Elog_theta", "G_lambda", "E_lambda",
                      "Elog_lambda", "GE_theta", "rho_u", "rho_u32", "delta_u", "rho", "layer_consts", "tab_p", "tab_q",
-                     "rowpart", "colpart", "er_node", "colsum", "dev_flags", "blkpart", "red1", "red2", "red3",
+                     "rowpart", "colpart", "er_node", "colsum", "dev_flags", "fixA", "blkpart", "red1", "red2", "red3",
                      "elbo_out"):
             setattr(c, name, ptr(getattr(self, name)))
         c.A = self.red3.data_ptr()  # A aliases the (all-reduced) statistics vector
@@ -139,7 +140,7 @@ class CaviEngine:
         nu[self.C["VM_NU_SHP"]], nu[self.C["VM_NU_RTE"]] = float(nu_shp), float(nu_rte)
         self.nu.copy_(torch.as_tensor(nu, **f64))
         if P.U:
-            pr = torch.as_tensor(pr_u, **f64).reshape(P.U, P.K)
+            pr = (pr_u.to(**f64) if torch.is_tensor(pr_u) else torch.as_tensor(pr_u, **f64)).reshape(P.U, P.K)
             self.rho_u.copy_(pr)
             self.u_logpr.copy_(torch.log(pr + float(eps)))
         st = self._stream()

@@ -61,12 +61,23 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64)
     P.nrt = (nloc + P.tile_h - 1) // P.tile_h
     P.mask = mask
 
-    subs = torch.as_tensor(np.ascontiguousarray(np.asarray(X_subs)), device=dev).to(torch.int64)
-    xl, xi, xj, xm = subs[0], subs[1], subs[2], subs[3]
-    xv = torch.as_tensor(np.ascontiguousarray(np.asarray(X_vals)), device=dev).to(torch.float64)
+    def _up(a, small):
+        """host array -> device int64/float64 tensor, moving as few bytes as possible over PCIe"""
+        if torch.is_tensor(a):
+            return a.to(dev)
+        a = np.asarray(a)
+        if small and a.dtype.kind in "iu" and a.dtype.itemsize > 4:
+            a = a.astype(np.int32)
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    small = max(L, N, M) < 2**31
+    xl, xi, xj, xm = (_up(X_subs[d], small).to(torch.int64) for d in range(4))
+    xv = _up(X_vals, small and np.asarray(X_vals).dtype.kind in "iu").to(torch.float64)
     I_all = xv.numel()
     if I_all:
-        if int(xl.max()) >= L or int(max(xi.max(), xj.max())) >= N or int(xm.max()) >= M or int(subs.min()) < 0:
+        mx = torch.stack([xl.max(), xi.max(), xj.max(), xm.max(), -torch.stack([xl.min(), xi.min(), xj.min(), xm.min()]).min()])
+        mx = mx.cpu().numpy()
+        if mx[0] >= L or mx[1] >= N or mx[2] >= N or mx[3] >= M or mx[4] > 0:
             raise ValueError("X has subscripts outside its shape")
 
     # ---- reciprocal pairing: xT[I] = X[l, j, i, m]   (model.py:152-161)

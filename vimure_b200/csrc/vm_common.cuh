@@ -14,6 +14,9 @@
 #define VM_CLAMP_LOG2 120.0f
 
 #define VM_DENSE_THREADS 256
+// fixed-point scale of the integer-atomic per-reporter accumulators (2^44: |sum| < 1.3e5 fits, 5.7e-14 resolution)
+#define VM_FIX_SCALE 17592186044416.0
+#define VM_FIX_INV (1.0 / 17592186044416.0)
 
 // ------------------------------------------------------------------ special functions (fp64)
 // digamma: recurrence up to x >= 10, then the asymptotic series (truncation error < 1e-16 there).

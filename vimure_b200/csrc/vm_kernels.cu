@@ -218,6 +218,8 @@ __global__ void __launch_bounds__(256) k_phi_finish(const __grid_constant__ vm_c
     if (threadIdx.x == 0) rte_s[k] = v;
   }
   emax = block_max<256>(emax, sm);
+  if (c.r_mode == VM_R_EGO)
+    for (int64_t t = threadIdx.x; t < M * K; t += 256) c.fixA[(int64_t)l * M * K + t] = 0;
   if (threadIdx.x == 0) {
     if (l == 0) c.dev_flags[0] = 0;
     double El[K];
@@ -325,6 +327,31 @@ __device__ __forceinline__ void vm_tie_logodds(const vm_ctx& c, int l, int64_t l
   }
 }
 
+// Per-reporter accumulation of d[k] = (posterior of a special tie) - (closed form the dense kernel counts for it),
+// ego mask: the tie (i,j) is reported by i and by j (the diagonal tie once, and only if the mask contains it).
+// Fixed point + integer atomics: the sum is exact in any order, so the result is bit-reproducible.
+// d[0] is not accumulated: sum_k d[k] = (special tie alive) - (closed form alive), which is 0 unless a row
+// underflowed completely; only that residual goes to slot 0 and k_stats_ego rebuilds d[0] = resid - sum_{k>=1} d[k].
+template <int K>
+__device__ __forceinline__ void vm_fix_accumulate(const vm_ctx& c, int l, int i, int j, double ti, double tj,
+                                                  const double* d, int resid) {
+  const bool diag = (i == j);
+  if (diag && !c.ego_diag) return;
+  unsigned long long* base = reinterpret_cast<unsigned long long*>(c.fixA);
+  const bool act_i = ti > 0.0, act_j = (!diag) && tj > 0.0;  // E[theta] > 0 <=> active reporter (er_node)
+#pragma unroll
+  for (int k = 1; k < K; ++k) {
+    const unsigned long long q = (unsigned long long)__double2ll_rn(d[k] * VM_FIX_SCALE);
+    if (act_i) atomicAdd(base + ((int64_t)l * c.M + i) * K + k, q);
+    if (act_j) atomicAdd(base + ((int64_t)l * c.M + j) * K + k, q);
+  }
+  if (resid != 0) {
+    const unsigned long long q = (unsigned long long)((long long)resid * (long long)VM_FIX_SCALE);
+    if (act_i) atomicAdd(base + ((int64_t)l * c.M + i) * K, q);
+    if (act_j) atomicAdd(base + ((int64_t)l * c.M + j) * K, q);
+  }
+}
+
 // ---- special ties (ties that carry X entries, and the diagonal): the full `_update_rho` in fp64 -------------
 // log rho_k = log(pr_k+EPS) + sum_{entries} dz1_k (E[log theta_m] + E[log lambda_k]) - S E[lambda_k]   (model.py:800-804,
 // 911-921), softmax over k (model.py:807-811), nu statistic (model.py:822-825), ELBO pieces (model.py:967-995, 1306-1313).
@@ -392,10 +419,10 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
     float a[K];
     vm_tie_logodds<K>(c, l, lrow, j, a);
     // S = sum over the tie's reporters of E[theta] * R.vals (model.py:766-792)
-    double S;
+    double S, ti = 0.0, tj = 0.0;
     if (RMODE == VM_R_EGO) {
-      const double ti = c.er_node[(int64_t)l * c.N + i];
-      const double tj = c.er_node[(int64_t)l * c.N + j];
+      ti = c.er_node[(int64_t)l * c.N + i];
+      tj = c.er_node[(int64_t)l * c.N + j];
       S = (i == j) ? (c.ego_diag ? ti : 0.0) : ti + tj;
     } else if (RMODE == VM_R_ALL) {
       S = lc[VM_LC_SALL(K)];
@@ -462,13 +489,21 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
     float f[K], epsr;
     bool dead;
     vm_formula_rho<K>(a, may_dead, f, epsr, dead);
+    {
+      // closed-form k=0 as the statistics count it: the exact complement of the others (F_0 = n - dead - sum F_k)
+      double fk = 0.0, dk[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const double d = rho[k] - (double)f[k];
-      c.rho_u[u * K + k] = rho[k];
-      c.rho_u32[u * K + k] = (float)rho[k];
-      c.delta_u[u * K + k] = d;
-      dsum[k] += d;
+      for (int k = 1; k < K; ++k) fk += (double)f[k];
+      const bool alive_u = mx >= VM_DEAD_LN;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const double fv = (k == 0) ? (dead ? 0.0 : 1.0 - fk) : (double)f[k];
+        dk[k] = rho[k] - fv;
+        c.rho_u[u * K + k] = rho[k];
+        c.rho_u32[u * K + k] = (float)rho[k];
+        dsum[k] += dk[k];
+      }
+      if (RMODE == VM_R_EGO) vm_fix_accumulate<K>(c, l, i, j, ti, tj, dk, (alive_u ? 1 : 0) - (dead ? 0 : 1));
     }
     if (elbo) {
       // log-Poisson-mean term: uses exp(rho) (Q1) and only the entries that are also in R (model.py:967-995)
@@ -992,21 +1027,15 @@ __global__ void __launch_bounds__(256) k_stats_ego(const __grid_constant__ vm_ct
       }
     }
   }
-  int ua = 0, ub = 0;  // special ties of row m (contiguous)
-  if (local) {
-    ua = c.utile_ptr[lrow * nct];
-    ub = c.utile_ptr[(lrow + 1) * nct];
-    for (int u = ua + lane; u < ub; u += 32) {
-      if (!c.ego_diag && c.u_col[u] == m) continue;
+  // special-tie corrections: accumulated by k_special / k_init_delta in fixed point
+  if (lane == 0) {
+    double rest = 0.0;
 #pragma unroll
-      for (int k = 0; k < K; ++k) d[k] += c.delta_u[(int64_t)u * K + k];
+    for (int k = 1; k < K; ++k) {
+      d[k] = (double)c.fixA[lm * K + k] * VM_FIX_INV;
+      rest += d[k];
     }
-  }
-  for (int64_t p = c.ucol_ptr[(int64_t)l * N + m] + lane; p < c.ucol_ptr[(int64_t)l * N + m + 1]; p += 32) {
-    const int u = c.ucol_perm[p];
-    if (u >= ua && u < ub) continue;  // the diagonal tie (row m, column m): counted (at most) once, above
-#pragma unroll
-    for (int k = 0; k < K; ++k) d[k] += c.delta_u[(int64_t)u * K + k];
+    d[0] = (double)c.fixA[lm * K] * VM_FIX_INV - rest;
   }
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -1083,14 +1112,28 @@ __global__ void __launch_bounds__(256) k_stats_csc(const __grid_constant__ vm_ct
   }
 }
 
-// delta_u = rho_u - onehot for the initial statistics (rho = pr_rho, model.py:602)
+// initial statistics (rho = pr_rho, model.py:602): delta = rho_u - onehot per special tie
+template <int K>
 __global__ void k_init_delta(const __grid_constant__ vm_ctx c) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= c.U * c.K) return;
-  const int k = (int)(t % c.K);
-  const double r = c.rho_u[t];
-  c.delta_u[t] = r - (k == 0 ? 1.0 : 0.0);
-  c.rho_u32[t] = (float)r;
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= c.U) return;
+  double d[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double r = c.rho_u[u * K + k];
+    d[k] = r - (k == 0 ? 1.0 : 0.0);
+    c.delta_u[u * K + k] = d[k];
+    c.rho_u32[u * K + k] = (float)r;
+  }
+  if (c.r_mode == VM_R_EGO) {
+    const int64_t lrow = c.u_lrow[u];
+    const int l = (int)(lrow / c.nloc);
+    const int i = (int)(lrow - (int64_t)l * c.nloc) + (int)c.row0, j = c.u_col[u];
+    // activity flags from the mask itself (the caches may not be final yet)
+    const double ti = (i < (int)c.M && c.rep[(int64_t)l * c.M + i]) ? 1.0 : 0.0;
+    const double tj = (j < (int)c.M && c.rep[(int64_t)l * c.M + j]) ? 1.0 : 0.0;
+    vm_fix_accumulate<K>(c, l, i, j, ti, tj, d, 0);
+  }
 }
 // per-layer totals of delta_u, for the all-reporter initial statistics
 __global__ void __launch_bounds__(256) k_init_delta_all(const __grid_constant__ vm_ctx c, double* upart) {
@@ -1410,8 +1453,14 @@ extern "C" int vm_init_stats(const vm_ctx* c, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (c->U > 0) k_init_delta<<<(unsigned)cdiv(c->U * c->K, 256), 256, 0, st>>>(*c);
-  VM_CHECK_LAUNCH();
+  if (c->r_mode == VM_R_EGO) {
+    cudaMemsetAsync(c->fixA, 0, (size_t)(c->L * c->M * c->K) * sizeof(int64_t), st);
+    VM_CHECK_LAUNCH();
+  }
+  if (c->U > 0) {
+    DISPATCH_K(c->K, (k_init_delta<K><<<(unsigned)cdiv(c->U, 256), 256, 0, st>>>(*c)));
+    VM_CHECK_LAUNCH();
+  }
   if (c->r_mode == VM_R_ALL) {
     k_init_delta_all<<<dim3((unsigned)c->n_ublk, (unsigned)c->L), 256, 0, st>>>(*c, region_u(c));
     VM_CHECK_LAUNCH();

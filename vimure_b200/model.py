@@ -201,8 +201,10 @@ class VimureModel(TransformerMixin, BaseEstimator):
     def fit(self, X, theta_prior=(0.1, 0.1), lambda_prior=(10.0, 10.0), eta_prior=(0.5, 1.0), rho_prior=None,
             seed: int = None, **extra_params):
         """Fit the model (reference model.py:327-448).  Returns self."""
+        t_fit = time.time()
         self._check_fit_params(X, lambda_prior=lambda_prior, theta_prior=theta_prior, eta_prior=eta_prior,
                                rho_prior=rho_prior, seed=seed, **extra_params)
+        t_check = time.time() - t_fit
         dev = extra_params.get("device", None)
         if not torch.cuda.is_available():
             raise RuntimeError("vimure_b200.VimureModel.fit needs a CUDA device (B200); there is no CPU fallback")
@@ -219,6 +221,7 @@ class VimureModel(TransformerMixin, BaseEstimator):
         self._world, self._rank = world, rank
         row0, nloc = shard_rows(self.N, world, rank)
 
+        self.timings = {"check_params": t_check}
         with torch.cuda.device(dev):
             t0 = time.time()
             self._packed = P = _packing.pack(self.X.subs, self.X.vals, self.L, self.N, self.M, self.K, self.R, dev,
@@ -231,7 +234,8 @@ class VimureModel(TransformerMixin, BaseEstimator):
             priors = dict(alpha_theta=self.alpha_theta, beta_theta=self.beta_theta, alpha_lambda=self.alpha_lambda,
                           beta_lambda=self.beta_lambda, alpha_eta=self.alpha_mutuality, beta_eta=self.beta_mutuality)
             self._engine = eng = CaviEngine(P, priors, mutuality=self.mutuality, eps=self.EPS, group=group)
-            self.pack_time = time.time() - t0
+            torch.cuda.synchronize(dev)
+            self.pack_time = self.timings["pack+engine"] = time.time() - t0
 
             maxL = -INF
             trace = []
@@ -240,13 +244,19 @@ class VimureModel(TransformerMixin, BaseEstimator):
             init_mode = extra_params.get("init", "auto")
             for r in range(self.num_realisations):
                 bias0 = DEFAULT_BIAS0 if r < 5 else (r - 4) * self.bias0  # model.py:390-394
+                t1 = time.time()
                 if injected is not None and r == 0:
                     st = self._state_from_injection(injected)
                 else:
                     st = self._draw_initial_state(bias0, init_mode)
+                self.timings["draw_init"] = self.timings.get("draw_init", 0.0) + time.time() - t1
+                t1 = time.time()
                 eng.set_state(st["gamma_shp"], st["gamma_rte"], st["phi_shp"], st["phi_rte"], st["nu_shp"],
                               st["nu_rte"], st["pr_u"], self.EPS)
                 self._pr_u = st["pr_u"]
+                torch.cuda.synchronize(dev)
+                self.timings["init_state"] = self.timings.get("init_state", 0.0) + time.time() - t1
+                t_loop = time.time()
 
                 coincide, it, reached, elbo = 0, 1, False, -INF
                 while not reached and it <= self.max_iter:
@@ -274,6 +284,7 @@ class VimureModel(TransformerMixin, BaseEstimator):
                     if (it - 1) % 10 == 0:  # model.py:423-426
                         trace.append((r, self.seed, it - 1, elbo, runtime, reached))
                 self.n_iter_ = it - 1
+                self.timings["cavi_loop"] = self.timings.get("cavi_loop", 0.0) + time.time() - t_loop
                 self._fetch_params()
                 if maxL < elbo:
                     self._update_optimal_parameters()
@@ -298,14 +309,29 @@ class VimureModel(TransformerMixin, BaseEstimator):
         reference's RNG stream in the reference's order when init == "reference"."""
         L, N, M, K = self.L, self.N, self.M, self.K
         P = self._packed
-        flat, keep = self._special_tie_info()
         U = P.U
-        pr_u = np.zeros((U, K))
-        pr_u[:, 0] = 1.0
         if init_mode == "auto":
             init_mode = "reference" if float(L) * N * N * K <= AUTO_REFERENCE_INIT_LIMIT else "fast"
         if init_mode not in ("reference", "fast"):
             raise ValueError("init must be 'reference', 'fast' or 'auto'")
+        if init_mode == "fast" and self.rho_prior is None and not self.undirected:
+            # device-side draw: only the ties that keep a random prior, nothing crosses PCIe
+            dev = P.t["u_lrow"].device
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(int(self.prng.randint(0, 2**31 - 1)))
+            keep_d = P.t["u_has_x"] & P.t["u_reported"]
+            pr = 1 + 0.01 * torch.rand((int(keep_d.sum()), K), generator=gen, dtype=torch.float64, device=dev)
+            pr[:, 0] += bias0
+            pr /= pr.sum(dim=-1, keepdim=True)
+            pr_u = torch.zeros((U, K), dtype=torch.float64, device=dev)
+            pr_u[:, 0] = 1.0
+            pr_u[keep_d] = pr
+            st = dict(pr_u=pr_u)
+            self._draw_small_params(st)
+            return st
+        flat, keep = self._special_tie_info()
+        pr_u = np.zeros((U, K))
+        pr_u[:, 0] = 1.0
         kidx = np.nonzero(keep)[0]
         if self.rho_prior is None:
             if init_mode == "reference":
@@ -360,7 +386,12 @@ class VimureModel(TransformerMixin, BaseEstimator):
                 hit = nz_flat[pos] == flat[kidx]
                 pr_u[kidx[hit]] = dense_pr[pos[hit]]
         st = dict(pr_u=pr_u)
-        # model.py:570-600
+        self._draw_small_params(st)
+        return st
+
+    def _draw_small_params(self, st):
+        """`_initialize_priors` (reference model.py:570-600): gamma/phi shapes and rates, nu."""
+        L, M, K = self.L, self.M, self.K
         rs = self.prng.random_sample
         st["gamma_shp"] = self.alpha_theta * rs(size=(L, M)) + self.alpha_theta
         st["phi_shp"] = self.alpha_lambda * rs(size=(L, K)) + self.alpha_lambda
@@ -472,7 +503,8 @@ class VimureModel(TransformerMixin, BaseEstimator):
             pr = np.zeros((self.L, self.N, self.N, self.K))
             pr[..., 0] = 1.0
             flat, _ = self._special_tie_info()
-            pr.reshape(-1, self.K)[flat] = self._pr_u
+            pr_u = self._pr_u.cpu().numpy() if torch.is_tensor(self._pr_u) else self._pr_u
+            pr.reshape(-1, self.K)[flat] = pr_u
             self._pr_rho_cache = pr
         return self._pr_rho_cache
 
