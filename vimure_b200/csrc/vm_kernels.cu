@@ -333,19 +333,40 @@ __device__ __forceinline__ void vm_tie_logodds(const vm_ctx& c, int l, int64_t l
 // d[0] is not accumulated: sum_k d[k] = (special tie alive) - (closed form alive), which is 0 unless a row
 // underflowed completely; only that residual goes to slot 0 and k_stats_ego rebuilds d[0] = resid - sum_{k>=1} d[k].
 template <int K>
-__device__ __forceinline__ void vm_fix_accumulate(const vm_ctx& c, int l, int i, int j, double ti, double tj,
-                                                  const double* d, int resid) {
+__device__ __forceinline__ void vm_fix_accumulate(const vm_ctx& c, bool valid, int l, int64_t lrow, int i, int j,
+                                                  double ti, double tj, const double* d, int resid) {
+  // WARP-COLLECTIVE: every lane of the warp must call it (valid = false for lanes without a tie).
+  // Consecutive lanes hold consecutive special ties, i.e. mostly the SAME row: the row-reporter contributions are
+  // combined with a segmented warp scan first (one atomic per row segment instead of 32 on one address); the
+  // column-reporter contributions go to distinct addresses and are issued directly.
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   const bool diag = (i == j);
-  if (diag && !c.ego_diag) return;
+  const bool use = valid && !(diag && !c.ego_diag);
+  const bool act_i = use && ti > 0.0, act_j = use && !diag && tj > 0.0;  // E[theta] > 0 <=> active reporter
+  const long long key = valid ? (long long)lrow : (long long)(-1 - lane);
+  bool same[5];
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const long long kn = __shfl_up_sync(full, key, 1 << s);
+    same[s] = (lane >= (1 << s)) && (kn == key);
+  }
+  const long long knext = __shfl_down_sync(full, key, 1);
+  const bool tail = valid && ((lane == 31) || (knext != key));
   unsigned long long* base = reinterpret_cast<unsigned long long*>(c.fixA);
-  const bool act_i = ti > 0.0, act_j = (!diag) && tj > 0.0;  // E[theta] > 0 <=> active reporter (er_node)
 #pragma unroll
   for (int k = 1; k < K; ++k) {
-    const unsigned long long q = (unsigned long long)__double2ll_rn(d[k] * VM_FIX_SCALE);
-    if (act_i) atomicAdd(base + ((int64_t)l * c.M + i) * K + k, q);
-    if (act_j) atomicAdd(base + ((int64_t)l * c.M + j) * K + k, q);
+    const long long q = valid ? __double2ll_rn(d[k] * VM_FIX_SCALE) : 0ll;
+    long long qr = act_i ? q : 0ll;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      const long long qn = __shfl_up_sync(full, qr, 1 << s);
+      if (same[s]) qr += qn;
+    }
+    if (tail && qr != 0) atomicAdd(base + ((int64_t)l * c.M + i) * K + k, (unsigned long long)qr);
+    if (act_j && q != 0) atomicAdd(base + ((int64_t)l * c.M + j) * K + k, (unsigned long long)q);
   }
-  if (resid != 0) {
+  if (resid != 0) {  // rare: a row underflowed completely
     const unsigned long long q = (unsigned long long)((long long)resid * (long long)VM_FIX_SCALE);
     if (act_i) atomicAdd(base + ((int64_t)l * c.M + i) * K, q);
     if (act_j) atomicAdd(base + ((int64_t)l * c.M + j) * K, q);
@@ -395,7 +416,14 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
 #pragma unroll 1
   for (int it = 0; it < TPT; ++it) {
     const int64_t u = ub + it * 256;
-    if (u >= u1) break;
+    const bool valid = u < u1;
+    // outputs of the per-tie block that the warp-collective accumulation below needs
+    int64_t o_lrow = 0;
+    int o_i = 0, o_j = 0, o_resid = 0;
+    double o_ti = 0.0, o_tj = 0.0, o_dk[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) o_dk[k] = 0.0;
+    if (valid) {
     const int64_t lrow = n_lrow;
     const int j = n_col, cnt = n_cnt, m0 = n_m0;
     const float x0 = n_x0, xT0 = n_xT0;
@@ -503,7 +531,14 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
         c.rho_u32[u * K + k] = (float)rho[k];
         dsum[k] += dk[k];
       }
-      if (RMODE == VM_R_EGO) vm_fix_accumulate<K>(c, l, i, j, ti, tj, dk, (alive_u ? 1 : 0) - (dead ? 0 : 1));
+      o_lrow = lrow;
+      o_i = i;
+      o_j = j;
+      o_ti = ti;
+      o_tj = tj;
+      o_resid = (alive_u ? 1 : 0) - (dead ? 0 : 1);
+#pragma unroll
+      for (int k = 0; k < K; ++k) o_dk[k] = dk[k];
     }
     if (elbo) {
       // log-Poisson-mean term: uses exp(rho) (Q1) and only the entries that are also in R (model.py:967-995)
@@ -526,6 +561,8 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
       cat_acc -= (double)vm_formula_cat<K>(f, epsr, dead, (float)lc[VM_LC_LP0(K)], (float)lc[VM_LC_LPK(K)],
                                             (float)c.eps);
     }
+    }  // valid
+    if (RMODE == VM_R_EGO) vm_fix_accumulate<K>(c, valid, l, o_lrow, o_i, o_j, o_ti, o_tj, o_dk, o_resid);
   }
   // per-WARP partials (no block barrier: a warp retires as soon as its own ties are done)
   const int64_t nup = c.L * c.n_ublk * 8, b = ((int64_t)l * c.n_ublk + blockIdx.x) * 8 + (threadIdx.x >> 5);
@@ -1116,24 +1153,32 @@ __global__ void __launch_bounds__(256) k_stats_csc(const __grid_constant__ vm_ct
 template <int K>
 __global__ void k_init_delta(const __grid_constant__ vm_ctx c) {
   const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= c.U) return;
+  const bool valid = u < c.U;
   double d[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const double r = c.rho_u[u * K + k];
-    d[k] = r - (k == 0 ? 1.0 : 0.0);
-    c.delta_u[u * K + k] = d[k];
-    c.rho_u32[u * K + k] = (float)r;
+  for (int k = 0; k < K; ++k) d[k] = 0.0;
+  int l = 0, i = 0, j = 0;
+  int64_t lrow = 0;
+  double ti = 0.0, tj = 0.0;
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double r = c.rho_u[u * K + k];
+      d[k] = r - (k == 0 ? 1.0 : 0.0);
+      c.delta_u[u * K + k] = d[k];
+      c.rho_u32[u * K + k] = (float)r;
+    }
+    if (c.r_mode == VM_R_EGO) {
+      lrow = c.u_lrow[u];
+      l = (int)(lrow / c.nloc);
+      i = (int)(lrow - (int64_t)l * c.nloc) + (int)c.row0;
+      j = c.u_col[u];
+      // activity flags from the mask itself (the caches may not be final yet)
+      ti = (i < (int)c.M && c.rep[(int64_t)l * c.M + i]) ? 1.0 : 0.0;
+      tj = (j < (int)c.M && c.rep[(int64_t)l * c.M + j]) ? 1.0 : 0.0;
+    }
   }
-  if (c.r_mode == VM_R_EGO) {
-    const int64_t lrow = c.u_lrow[u];
-    const int l = (int)(lrow / c.nloc);
-    const int i = (int)(lrow - (int64_t)l * c.nloc) + (int)c.row0, j = c.u_col[u];
-    // activity flags from the mask itself (the caches may not be final yet)
-    const double ti = (i < (int)c.M && c.rep[(int64_t)l * c.M + i]) ? 1.0 : 0.0;
-    const double tj = (j < (int)c.M && c.rep[(int64_t)l * c.M + j]) ? 1.0 : 0.0;
-    vm_fix_accumulate<K>(c, l, i, j, ti, tj, d, 0);
-  }
+  if (c.r_mode == VM_R_EGO) vm_fix_accumulate<K>(c, valid, l, lrow, i, j, ti, tj, d, 0);
 }
 // per-layer totals of delta_u, for the all-reporter initial statistics
 __global__ void __launch_bounds__(256) k_init_delta_all(const __grid_constant__ vm_ctx c, double* upart) {
