@@ -1,0 +1,147 @@
+"""Scaled-down versions of BASELINE configs 3-5 against the CPU oracle, and size-independent properties at the
+full config-3 size (N = 20 000), all through the C ABI."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PRIORS = dict(alpha_theta=0.1, beta_theta=0.1, alpha_lambda=10.0, beta_lambda=10.0, alpha_eta=0.5, beta_eta=1.0)
+
+
+def _cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch
+
+
+def _engine_and_oracle(net, mask, spec, K, mutuality=True, seed=3, tile_h=64, row0=0, nloc=None):
+    _cuda()
+    from oracle.cavi_numpy import OracleCAVI
+    from vimure_b200 import _packing
+    from vimure_b200._engine import CaviEngine
+
+    L, N, M = net.X.shape[0], net.X.shape[1], net.X.shape[3]
+    subs = np.stack(net.X.subs)
+    P = _packing.pack(subs, net.X.vals, L, N, M, K, mask, "cuda", row0=row0, nloc=nloc, tile_h=tile_h)
+    eng = CaviEngine(P, PRIORS, mutuality=mutuality, eps=1e-12)
+    prng = np.random.RandomState(seed)
+    rs = prng.random_sample
+    st = dict(gamma_shp=0.1 * rs((L, M)) + 0.1, phi_shp=10.0 * rs((L, K)) + 10.0, gamma_rte=0.1 * rs((L, M)) + 0.1,
+              phi_rte=10.0 * rs((L, K)) + 10.0, nu_shp=0.5 * rs(1)[0] + 0.5)
+    keep = (P.t["u_has_x"] & P.t["u_reported"]).cpu().numpy()
+    pr_u = np.zeros((P.U, K))
+    pr_u[:, 0] = 1.0
+    pr = 1 + 0.01 * rs((int(keep.sum()), K))
+    pr_u[keep] = pr / pr.sum(axis=1)[:, None]
+    nu_rte = PRIORS["beta_eta"] + float(net.X.vals.sum())
+    eng.set_state(st["gamma_shp"], st["gamma_rte"], st["phi_shp"], st["phi_rte"], st["nu_shp"] if mutuality else 1e-6,
+                  nu_rte if mutuality else 1.0, pr_u, 1e-12)
+    o = None
+    if spec is not None:
+        o = OracleCAVI(L, N, M, K, subs, net.X.vals, spec, mutuality=mutuality, **PRIORS)
+        flat = P.t["u_gflat"].cpu().numpy()[keep]
+        ties = np.stack([flat // (N * N), (flat // N) % N, flat % N], axis=1)
+        o.set_state(st["gamma_shp"], st["gamma_rte"], st["phi_shp"], st["phi_rte"], st["nu_shp"],
+                    o.default_pr_rho(ties, pr_u[keep]))
+    return eng, o, P
+
+
+def _compare(eng, o, iters):
+    for it in range(iters):
+        eng.iterate(1, elbo_last=True)
+        o.iterate()
+        p = eng.params()
+        np.testing.assert_allclose(p["gamma_shp"], o.gamma_shp, rtol=1e-5, err_msg=f"it{it}")
+        np.testing.assert_allclose(p["gamma_rte"], o.gamma_rte, rtol=1e-5, err_msg=f"it{it}")
+        np.testing.assert_allclose(p["phi_shp"], o.phi_shp, rtol=1e-5, err_msg=f"it{it}")
+        np.testing.assert_allclose(p["phi_rte"], o.phi_rte, rtol=1e-5, err_msg=f"it{it}")
+        if o.mutuality:
+            np.testing.assert_allclose(p["nu_shp"], o.nu_shp, rtol=1e-5, err_msg=f"it{it}")
+        np.testing.assert_allclose(eng.elbo(), o.elbo(), rtol=1e-6, err_msg=f"it{it}")
+    rho = eng.rho_slab().cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(rho, o.rho, rtol=2e-5, atol=1e-30)
+
+
+def test_config3_scaled_sbm_ego_k2():
+    """config 3 law (StandardSBM, ego-only, K=2) at N=1100: two column tiles (one partial), several row tiles."""
+    import vimure_b200.synthetic as syn
+
+    net = syn.StandardSBM(N=1100, L=1, K=2, C=2, avg_degree=10, seed=10).build_X(mutuality=0.5, seed=20)
+    spec = {"kind": "ego", "rep": np.ones((1, 1100), dtype=np.uint8), "diag": True}
+    eng, o, _ = _engine_and_oracle(net, net.R, spec, 2)
+    _compare(eng, o, 4)
+
+
+def test_config4_scaled_dense_reporting():
+    """config 4 law (every reporter reports every tie, L=2, K=2) at N=300, M=16: the reporter-reduction heavy case."""
+    import vimure_b200 as vm
+    import vimure_b200.synthetic as syn
+
+    y = syn.StandardSBM(N=300, M=16, L=2, K=2, C=2, avg_degree=8, seed=5)
+    X, theta = syn.dense_reporting_X(y, M=16, mutuality=0.4, seed=6)
+
+    class Net:
+        pass
+
+    net = Net()
+    net.X = X
+    eng, o, _ = _engine_and_oracle(net, vm.masks.AllMask(2, 300, 16), {"kind": "all", "dense_input": True}, 2)
+    _compare(eng, o, 4)
+
+
+def test_config5_scaled_gm_l2_k3():
+    """config 5 law (Multitensor/GMReciprocity, ego-only, K=3, several layers) at N=640, L=2 (N % 4 == 0: fast kernel)."""
+    import vimure_b200.synthetic as syn
+
+    net = syn.Multitensor(N=640, L=2, K=3, C=2, avg_degree=10, eta=0.5, seed=7).build_X(mutuality=0.5, seed=8)
+    spec = {"kind": "ego", "rep": np.ones((2, 640), dtype=np.uint8), "diag": True}
+    eng, o, _ = _engine_and_oracle(net, net.R, spec, 3)
+    _compare(eng, o, 4)
+
+
+def test_k4_and_k5_paths():
+    """K=4 (strided lane mapping) and K=5 (generic kernel only) against the oracle."""
+    import vimure_b200.synthetic as syn
+
+    for K, N in ((4, 520), (5, 260)):
+        net = syn.Multitensor(N=N, L=1, K=K, C=2, avg_degree=12, eta=0.3, seed=K).build_X(mutuality=0.3, seed=K + 1)
+        spec = {"kind": "ego", "rep": np.ones((1, N), dtype=np.uint8), "diag": True}
+        eng, o, _ = _engine_and_oracle(net, net.R, spec, K)
+        _compare(eng, o, 3)
+
+
+def test_full_size_properties_config3():
+    """N = 20 000 (4e8 ties): properties that do not need the oracle."""
+    torch = _cuda()
+    import vimure_b200.synthetic as syn
+
+    N, K = 20000, 2
+    net = syn.StandardSBM(N=N, L=1, K=K, C=2, avg_degree=10, seed=10).build_X(mutuality=0.5, seed=20)
+    runs = []
+    for rep in range(2):
+        eng, _, P = _engine_and_oracle(net, net.R, None, K)
+        eng.iterate(3, elbo_last=True)
+        p = eng.params()
+        runs.append((p, eng.elbo()))
+        if rep == 0:
+            # (i) the reporter statistic conserves the number of reported ties: sum_k A[l,m,k] = 2N-1
+            A = eng.red3[: N * K].cpu().numpy().reshape(N, K)
+            np.testing.assert_allclose(A.sum(axis=1), 2 * N - 1, rtol=0, atol=1e-6)
+            # (ii) every stored tie is a probability vector; special ties carry their fp64-computed posterior
+            slab = eng.rho_slab()
+            rows = torch.randint(0, N, (64,), device=slab.device)
+            s = slab[0, rows].sum(dim=-1)
+            assert float((s - 1).abs().max()) < 1e-6
+            u = torch.randint(0, P.U, (100000,), device=slab.device)
+            got = slab[0, P.t["u_lrow"][u].long(), P.t["u_col"][u].long()]
+            assert torch.equal(got, eng.rho_u32[u])
+            # (iii) the ELBO is finite
+            assert np.isfinite(eng.elbo())
+        del eng
+        torch.cuda.empty_cache()
+    # (iv) bit-reproducible run to run (deterministic two-pass reductions + integer atomics)
+    for k in ("gamma_shp", "gamma_rte", "phi_shp", "phi_rte", "nu_shp"):
+        assert np.array_equal(runs[0][0][k], runs[1][0][k]), k
+    assert runs[0][1] == runs[1][1]
