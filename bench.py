@@ -299,8 +299,11 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         barrier()
-        subs_host = [np.ascontiguousarray(s) for s in net.X.subs]
-        vals_host = np.ascontiguousarray(net.X.vals)
+        # host inputs in PINNED memory (int32 indices / counts), as the contract asks
+        pinned = [torch.from_numpy(np.ascontiguousarray(s).astype(np.int32)).pin_memory() for s in net.X.subs]
+        pinned.append(torch.from_numpy(np.ascontiguousarray(net.X.vals).astype(np.int32)).pin_memory())
+        subs_host = [t.numpy() for t in pinned[:4]]
+        vals_host = pinned[4].numpy()
         h2d = sum(s.nbytes for s in subs_host) + vals_host.nbytes
         from vimure_b200.sptensor import sptensor
 

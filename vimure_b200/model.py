@@ -94,8 +94,12 @@ class VimureModel(TransformerMixin, BaseEstimator):
         # ---- X -> COO
         if is_sparse_like(X):
             shape = tuple(int(d) for d in X.shape)
-            subs = np.stack([np.asarray(s).astype(np.int64) for s in X.subs]) if len(X.vals) else np.zeros((4, 0), np.int64)
+            # no copies here: the packer moves each index array to the device in the narrowest integer type
+            subs = tuple(np.asarray(s) for s in X.subs) if len(X.vals) else tuple(np.zeros(0, np.int64) for _ in range(4))
             vals = np.asarray(X.vals)
+            for s_ in subs:
+                if s_.dtype.kind not in "iu":
+                    raise ValueError("Subscripts must be integers")
         elif isinstance(X, np.ndarray):
             Xd = np.asarray(X)
             if Xd.ndim != 4:
@@ -104,7 +108,7 @@ class VimureModel(TransformerMixin, BaseEstimator):
                 Xd = Xd.astype(int)  # preprocess(), utils.py:241-242
             shape = Xd.shape
             nz = np.nonzero(Xd)
-            subs = np.stack(nz).astype(np.int64)
+            subs = tuple(nz)
             vals = Xd[nz]
         else:
             raise ValueError("X must be a DataFrame, a numpy array or a sparse tensor with .subs/.vals/.shape")
