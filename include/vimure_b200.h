@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VM_ABI_VERSION 7
+#define VM_ABI_VERSION 8
 
 /* reporter-mask structure (how R[l,i,j,m] is represented) */
 #define VM_R_EGO 0 /* reporter m == node m reports row m and column m (vimure synthetic.py:1184-1204, _io.py:229-242) */
@@ -61,7 +61,7 @@ extern "C" {
 #define VM_R3_EXTRA 4
 
 /* maximum K compiled in */
-#define VM_MAX_K 8
+#define VM_MAX_K 32
 /* special ties handled by one block of the special-tie kernel (n_ublk = ceil(max per layer / this)) */
 #define VM_SPECIAL_TIES_PER_BLOCK 1024
 

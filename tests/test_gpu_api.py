@@ -1,0 +1,152 @@
+"""The reference's own API tests (test/test_model.py) re-expressed against vimure_b200.VimureModel (GPU)."""
+import warnings
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from tests.golden_util import Golden
+from tests.test_gpu_parity import build_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def check_final_parameters(model, L, N, M, K):
+    """reference test_model.py:15-52"""
+    assert type(model.rho) == np.ndarray and model.rho.shape == (L, N, N, K) and model.rho.sum() != 0
+    for nm, shape in (("gamma_shp", (L, M)), ("gamma_rte", (L, M)), ("phi_shp", (L, K)), ("phi_rte", (L, K))):
+        v = getattr(model, nm)
+        assert type(v) == np.ndarray and v.shape == shape and v.sum() > 0
+    assert type(model.nu_shp) == np.float64 and model.nu_shp >= 0
+    assert type(model.nu_rte) == np.float64 and model.nu_rte >= 0
+
+
+@pytest.fixture(scope="module")
+def fitted():
+    _cuda()
+    import vimure_b200 as vm
+    import vimure_b200.synthetic as syn
+
+    net = syn.StandardSBM(N=100, M=100, L=1, K=2, C=2, avg_degree=4, seed=3).build_X(mutuality=0.5, seed=4)
+    models = {}
+    for mut in (True, False):
+        m = vm.VimureModel(mutuality=mut)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m.fit(net.X, K=2, R=net.R, num_realisations=1, max_iter=100, seed=1)
+        models[mut] = m
+    return net, models
+
+
+def test_parameters_and_warnings():
+    """reference test_model.py:59-115"""
+    _cuda()
+    import vimure_b200 as vm
+    import vimure_b200.synthetic as syn
+
+    net = syn.StandardSBM(N=20, M=20, L=1, K=3, C=2, avg_degree=2, seed=1).build_X(seed=2)
+    model = vm.VimureModel()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model.fit(net.X, K=3, R=net.R, max_iter=30)
+    check_final_parameters(model, 1, 20, 20, 3)
+    with pytest.warns(UserWarning, match="Reporters Mask was not informed"):
+        vm.VimureModel().fit(net.X, K=3, max_iter=2)
+    with pytest.warns(UserWarning, match="Parameter K was None"):
+        vm.VimureModel().fit(net.X, R=net.R, max_iter=2)
+    with pytest.raises(ValueError, match="Dimensions of reporter mask"):
+        vm.VimureModel().fit(net.X, K=3, R=np.ones((1, 20, 20, 3)), max_iter=2)
+    with pytest.raises(ValueError, match="theta_prior must be a 2D tuple"):
+        vm.VimureModel().fit(net.X, K=3, R=net.R, theta_prior=[0.1, 0.1])
+    with pytest.raises(ValueError, match="alpha_lambda matrix is not valid"):
+        vm.VimureModel().fit(net.X, K=3, R=net.R, alpha_lambda=np.ones((1, 2)), beta_lambda=np.ones((1, 3)))
+    with pytest.raises(ValueError, match="rho_prior has to have shape"):
+        vm.VimureModel().fit(net.X, K=3, R=net.R, rho_prior=np.ones((1, 20, 19)))
+    with pytest.warns(UserWarning, match="Overriding mutuality"):
+        m = vm.VimureModel(undirected=True)
+    assert m.mutuality is False
+    with pytest.raises(ValueError, match="has to be symmetric"):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m.fit(net.X, K=3, R=net.R, max_iter=2)
+
+
+def test_inferred_model_methods(fitted):
+    """reference test_model.py:362-447"""
+    net, models = fitted
+    for mut, model in models.items():
+        with pytest.raises(ValueError, match="'method' should be one of"):
+            model.get_inferred_model(method="NotImplemented")
+        Y = model.get_inferred_model(method="rho_max")
+        assert Y.shape == (model.L, model.N, model.N) and Y.sum() > 0
+        assert np.array_equal(Y, np.argmax(model.rho_f, axis=-1))
+    model = models[True]
+    with pytest.raises(ValueError, match="you must set the threshold"):
+        model.get_inferred_model(method="fixed_threshold")
+    with pytest.raises(ValueError, match="you must set the threshold"):
+        model.get_inferred_model(method="fixed_threshold", threshold=2)
+    Y = model.get_inferred_model(method="fixed_threshold", threshold=0.5)
+    assert Y.shape == (1, 100, 100) and Y.sum() > 0
+    assert np.array_equal(Y, (model.rho_f[..., 1] >= 0.5).astype(float))
+    Ym = model.get_inferred_model(method="rho_mean")
+    np.testing.assert_allclose(Ym, model.rho_f[..., 1])
+    Yh = model.get_inferred_model(method="heuristic_threshold")
+    assert Yh.shape == (1, 100, 100)
+    thr = 0.54 * model.G_exp_nu - 0.01
+    assert np.array_equal(Yh, (model.rho_f[..., 1] >= thr).astype(int))
+    with pytest.warns(UserWarning, match="threshold methods is incompatible"):
+        Y2 = models[False].get_inferred_model(method="heuristic_threshold")
+    assert np.array_equal(Y2, models[False].get_inferred_model("rho_max"))
+    post = model.get_posterior_estimates()
+    assert set(post) == {"nu", "theta", "lambda", "rho"}
+    assert post["theta"].shape == (1, 100) and post["lambda"].shape == (1, 2) and post["rho"].shape == (1, 100, 100, 2)
+
+
+def test_sample_inferred_model(fitted):
+    """reference test_model.py:430-438"""
+    net, models = fitted
+    Y = models[True].sample_inferred_model(N=10)
+    assert len(Y) == 10
+    for y in Y:
+        assert y.shape == (1, 100, 100)
+
+
+def test_reference_compatible_attributes(fitted):
+    net, models = fitted
+    m = models[True]
+    assert m.pr_rho.shape == (1, 100, 100, 2) and np.allclose(m.pr_rho.sum(-1), 1.0)
+    assert m.logpr_rho.shape == m.pr_rho.shape
+    assert m.data_T_vals.shape == net.X.vals.shape
+    Xd = net.X.toarray()
+    l, i, j, r = net.X.subs
+    assert np.array_equal(m.data_T_vals, Xd[l, j, i, r])
+    assert list(m.trace.columns) == ["realisation", "seed", "iter", "elbo", "runtime", "reached_convergence"]
+    assert m.G_exp_theta_f.shape == (1, 100) and m.G_exp_lambda_f.shape == (1, 2)
+    assert m.get_params()["mutuality"] is True  # sklearn BaseEstimator surface
+
+
+def test_dataframe_input_equals_tensor_input():
+    """reference test_model.py:450-481: fitting a DataFrame == fitting the parsed tensors."""
+    _cuda()
+    import vimure_b200 as vm
+    from vimure_b200.io import read_from_edgelist
+
+    g = Golden("f1_over")
+    l, i, j, m = g.X_subs
+    df = pd.DataFrame({"ego": i, "alter": j, "reporter": m, "layer": l, "weight": g.X_vals})
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = vm.VimureModel().fit(df, seed=1, num_realisations=1, max_iter=30)
+        net = read_from_edgelist(df, K=2)
+        b = vm.VimureModel().fit(net.X, K=net.K, R=net.R, seed=1, num_realisations=1, max_iter=30)
+    assert a.K == b.K == 2
+    np.testing.assert_array_equal(a.gamma_shp, b.gamma_shp)
+    np.testing.assert_array_equal(a.trace["elbo"].to_numpy(), b.trace["elbo"].to_numpy())
+    check_final_parameters(a, net.L, net.N, net.N, 2)

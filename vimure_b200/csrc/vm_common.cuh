@@ -14,6 +14,36 @@
 #define VM_CLAMP_LOG2 120.0f
 
 #define VM_DENSE_THREADS 256
+
+// per-TU function table (see vm_kernels.cu / vm_api.cu)
+struct vm_tu_api {
+  int (*materialize_prior)(const vm_ctx*, void*);
+  int (*refresh_cache)(const vm_ctx*, void*);
+  int (*init_stats)(const vm_ctx*, void*);
+  int (*phase_gamma)(const vm_ctx*, void*);
+  int (*phase_phi)(const vm_ctx*, void*);
+  int (*phase_rho)(const vm_ctx*, int, void*);
+  int (*dense_only)(const vm_ctx*, int, void*);
+  int (*phase_finish)(const vm_ctx*, int, void*);
+  int (*iteration)(const vm_ctx*, int, void*);
+  int (*run)(const vm_ctx*, int, int, int, void*);
+  int (*infer)(const vm_ctx*, int, double, uint8_t*, void*);
+};
+
+// Column tile of the dense kernels: TW = 128*NCH columns; NCH is K-dependent so that the per-lane column accumulators
+// (NCH*4*(K-1) registers) stay in registers.
+#ifndef VM_NCH2
+#define VM_NCH2 4
+#endif
+template <int K>
+struct DenseCfg {
+  static constexpr int NCH = (K <= 2) ? VM_NCH2 : (K == 3) ? 4 : (K <= 5) ? 2 : 1;
+  static constexpr int TW = 128 * NCH;
+};
+static inline int64_t vm_dense_tile_w_host(int64_t K) {
+  if (K < 2 || K > VM_MAX_K) return VM_EINVAL;
+  return K <= 2 ? DenseCfg<2>::TW : K == 3 ? DenseCfg<3>::TW : K <= 5 ? DenseCfg<4>::TW : DenseCfg<6>::TW;
+}
 // fixed-point scale of the integer-atomic per-reporter accumulators (2^44: |sum| < 1.3e5 fits, 5.7e-14 resolution)
 #define VM_FIX_SCALE 17592186044416.0
 #define VM_FIX_INV (1.0 / 17592186044416.0)

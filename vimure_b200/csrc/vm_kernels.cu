@@ -13,6 +13,16 @@
 
 #include "vm_common.cuh"
 
+// This file is compiled once per translation unit (TU), each TU instantiating the kernels for a few values of K
+// (vimure_b200/build.py generates `_gen/vm_tu_<id>.cu`, which defines VM_TU_ID and VM_DISPATCH_CASES and includes
+// this file).  csrc/vm_api.cu holds the extern "C" entry points and routes to the TU that owns ctx->K.
+#ifndef VM_TU_ID
+#error "compile through vimure_b200/build.py (VM_TU_ID / VM_DISPATCH_CASES must be defined)"
+#endif
+#define VM_PASTE2(a, b) a##b
+#define VM_PASTE(a, b) VM_PASTE2(a, b)
+namespace VM_PASTE(vmtu, VM_TU_ID) {
+
 // VM_DEBUG_SYNC=1 in the environment: synchronise after every launch and report the failing launch site
 static bool vm_debug_sync() {
   static int v = -1;
@@ -595,15 +605,6 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
 // pointers and row terms of the next row and the patch data of the current row are prefetched before the arithmetic.
 // Column partials of the 8 warps are combined through shared memory once, at the end of the CTA.
 // TW = 128*NCH depends on K so that the column accumulators (NCH*4*(K-1) registers) stay in registers.
-#ifndef VM_NCH2
-#define VM_NCH2 4
-#endif
-template <int K>
-struct DenseCfg {
-  static constexpr int NCH = (K <= 2) ? VM_NCH2 : (K == 3) ? 4 : (K <= 5) ? 2 : 1;
-  static constexpr int TW = 128 * NCH;
-};
-
 __device__ __forceinline__ void vm_cp_async4(void* smem, const void* g) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(g));
@@ -611,6 +612,7 @@ __device__ __forceinline__ void vm_cp_async4(void* smem, const void* g) {
 __device__ __forceinline__ void vm_cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void vm_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// does k_dense_fast handle this (layer, column tile)?  (everything else is k_dense's)
 template <int K>
 __device__ __forceinline__ bool vm_fast_tile(const vm_ctx& c, int l, int ct) {
   return (((c.N * K) & 3) == 0) && ((int64_t)(ct + 1) * DenseCfg<K>::TW <= c.N) && c.r_mode != VM_R_CSR &&
@@ -653,6 +655,9 @@ __device__ __forceinline__ void vm_store_chunk(float* dst, int lane, const float
   } else if (K == 4) {
 #pragma unroll
     for (int t = 0; t < 4; ++t) d4[32 * t + lane] = make_float4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
+  } else if (K > 8) {  // many categories: natural layout (every lane owns 16*K contiguous bytes), no stage
+#pragma unroll
+    for (int v = 0; v < K; ++v) d4[K * lane + v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
   } else {
     float4* s4 = reinterpret_cast<float4*>(stage);
 #pragma unroll
@@ -665,7 +670,7 @@ __device__ __forceinline__ void vm_store_chunk(float* dst, int lane, const float
 }
 template <int K>
 struct StageCfg {
-  static constexpr int FLOATS = (K == 2 || K == 4) ? 4 : 128 * K;  // per-warp stage (unused for K = 2, 4)
+  static constexpr int FLOATS = (K == 2 || K == 4 || K > 8) ? 4 : 128 * K;  // per-warp stage (unused for K = 2, 4, > 8)
 };
 
 // 4 ties of one lane. a[t][k] are the log2-odds; results in o[t*K+k].
@@ -1362,13 +1367,6 @@ __global__ void k_infer(const float* rho, int64_t T, int K, int mode, float thr,
     }
   }
 }
-__global__ void k_test_special(const double* x, double* dg, double* lg, int64_t n) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  dg[t] = vm_digamma(x[t]);
-  lg[t] = lgamma(x[t]);
-}
-
 // =====================================================================================================
 // host-side launchers
 // =====================================================================================================
@@ -1384,39 +1382,26 @@ static inline double* region_b(const vm_ctx* c) { return region_cat(c) + n_catpa
 #define VM_B_BLOCKS 128
 static inline double* region_ep(const vm_ctx* c) { return region_b(c) + VM_B_BLOCKS; }
 
-extern "C" int64_t vm_dense_tile_w(int64_t K) {
-  switch (K) {
-    case 2: return DenseCfg<2>::TW;
-    case 3: return DenseCfg<3>::TW;
-    case 4: return DenseCfg<4>::TW;
-    case 5: return DenseCfg<5>::TW;
-    case 6: return DenseCfg<6>::TW;
-    case 7: return DenseCfg<7>::TW;
-    case 8: return DenseCfg<8>::TW;
-    default: return VM_EINVAL;
-  }
-}
-
 static int check_ctx(const vm_ctx* c) {
   if (!c) return VM_EINVAL;
   if (c->K < 2 || c->K > VM_MAX_K) return VM_EINVAL;
-  if (c->tile_w != vm_dense_tile_w(c->K) || c->tile_h < 1) return VM_EINVAL;
+  if (c->tile_w != vm_dense_tile_w_host(c->K) || c->tile_h < 1) return VM_EINVAL;
   if (c->nct != cdiv(c->N, c->tile_w) || c->nrt != cdiv(c->nloc, c->tile_h)) return VM_EINVAL;
   if (c->r_mode < 0 || c->r_mode > 2) return VM_EINVAL;
   if (c->L * c->nrt > 65535 || c->L > 65535) return VM_EINVAL;
   return 0;
 }
 
-#define DISPATCH_K(KV, ...)     \
-  switch (KV) {                 \
-    case 2: { constexpr int K = 2; __VA_ARGS__; } break; \
-    case 3: { constexpr int K = 3; __VA_ARGS__; } break; \
-    case 4: { constexpr int K = 4; __VA_ARGS__; } break; \
-    case 5: { constexpr int K = 5; __VA_ARGS__; } break; \
-    case 6: { constexpr int K = 6; __VA_ARGS__; } break; \
-    case 7: { constexpr int K = 7; __VA_ARGS__; } break; \
-    case 8: { constexpr int K = 8; __VA_ARGS__; } break; \
-    default: return VM_EINVAL;  \
+#define VM_CASE(k, ...)        \
+  case k: {                    \
+    constexpr int K = k;       \
+    __VA_ARGS__;               \
+  } break;
+#define DISPATCH_K(KV, ...)                       \
+  switch (KV) {                                   \
+    VM_DISPATCH_CASES(VM_CASE, __VA_ARGS__)       \
+    default:                                      \
+      return VM_EINVAL;                           \
   }
 
 template <int K>
@@ -1470,10 +1455,8 @@ static int launch_stats(const vm_ctx* c, int init, cudaStream_t st) {
   return 0;
 }
 
-extern "C" int64_t vm_ctx_size(void) { return (int64_t)sizeof(vm_ctx); }
-extern "C" int64_t vm_abi_version(void) { return VM_ABI_VERSION; }
 
-extern "C" int vm_materialize_prior(const vm_ctx* c, void* stream) {
+static int tu_materialize_prior(const vm_ctx* c, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1485,7 +1468,7 @@ extern "C" int vm_materialize_prior(const vm_ctx* c, void* stream) {
   return 0;
 }
 
-extern "C" int vm_refresh_cache(const vm_ctx* c, void* stream) {
+static int tu_refresh_cache(const vm_ctx* c, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
   const int64_t n = c->L * (c->M > c->K ? c->M : c->K);
@@ -1494,7 +1477,7 @@ extern "C" int vm_refresh_cache(const vm_ctx* c, void* stream) {
   return 0;
 }
 
-extern "C" int vm_init_stats(const vm_ctx* c, void* stream) {
+static int tu_init_stats(const vm_ctx* c, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1511,7 +1494,7 @@ extern "C" int vm_init_stats(const vm_ctx* c, void* stream) {
     VM_CHECK_LAUNCH();
   }
   if (c->r_mode == VM_R_CSR) {  // gather needs the slab
-    rc = vm_materialize_prior(c, stream);
+    rc = tu_materialize_prior(c, stream);
     if (rc) return rc;
   }
   DISPATCH_K(c->K, launch_stats<K>(c, 1, st));
@@ -1522,7 +1505,7 @@ extern "C" int vm_init_stats(const vm_ctx* c, void* stream) {
   return 0;
 }
 
-extern "C" int vm_phase_gamma(const vm_ctx* c, void* stream) {
+static int tu_phase_gamma(const vm_ctx* c, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1535,7 +1518,7 @@ extern "C" int vm_phase_gamma(const vm_ctx* c, void* stream) {
   return 0;
 }
 
-extern "C" int vm_phase_phi(const vm_ctx* c, void* stream) {
+static int tu_phase_phi(const vm_ctx* c, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1548,7 +1531,7 @@ extern "C" int vm_phase_phi(const vm_ctx* c, void* stream) {
   return 0;
 }
 
-extern "C" int vm_phase_rho(const vm_ctx* c, int flags, void* stream) {
+static int tu_phase_rho(const vm_ctx* c, int flags, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1575,7 +1558,7 @@ extern "C" int vm_phase_rho(const vm_ctx* c, int flags, void* stream) {
   return 0;
 }
 
-extern "C" int vm_dense_only(const vm_ctx* c, int flags, void* stream) {
+static int tu_dense_only(const vm_ctx* c, int flags, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
   DISPATCH_K(c->K, rc = launch_dense<K>(c, flags, (cudaStream_t)stream));
@@ -1584,7 +1567,7 @@ extern "C" int vm_dense_only(const vm_ctx* c, int flags, void* stream) {
   return 0;
 }
 
-extern "C" int vm_phase_finish(const vm_ctx* c, int flags, void* stream) {
+static int tu_phase_finish(const vm_ctx* c, int flags, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1602,23 +1585,23 @@ extern "C" int vm_phase_finish(const vm_ctx* c, int flags, void* stream) {
   return 0;
 }
 
-extern "C" int vm_iteration(const vm_ctx* c, int flags, void* stream) {
+static int tu_iteration(const vm_ctx* c, int flags, void* stream) {
   int rc;
-  if ((rc = vm_phase_gamma(c, stream))) return rc;
-  if ((rc = vm_phase_phi(c, stream))) return rc;
-  if ((rc = vm_phase_rho(c, flags, stream))) return rc;
-  return vm_phase_finish(c, flags, stream);
+  if ((rc = tu_phase_gamma(c, stream))) return rc;
+  if ((rc = tu_phase_phi(c, stream))) return rc;
+  if ((rc = tu_phase_rho(c, flags, stream))) return rc;
+  return tu_phase_finish(c, flags, stream);
 }
 
-extern "C" int vm_run(const vm_ctx* c, int n_iter, int flags, int last_flags, void* stream) {
+static int tu_run(const vm_ctx* c, int n_iter, int flags, int last_flags, void* stream) {
   for (int it = 0; it < n_iter; ++it) {
-    int rc = vm_iteration(c, it == n_iter - 1 ? last_flags : flags, stream);
+    int rc = tu_iteration(c, it == n_iter - 1 ? last_flags : flags, stream);
     if (rc) return rc;
   }
   return 0;
 }
 
-extern "C" int vm_infer(const vm_ctx* c, int mode, double threshold, uint8_t* out, void* stream) {
+static int tu_infer(const vm_ctx* c, int mode, double threshold, uint8_t* out, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
   if (mode == 1 && c->K < 2) return VM_EINVAL;
@@ -1629,9 +1612,12 @@ extern "C" int vm_infer(const vm_ctx* c, int mode, double threshold, uint8_t* ou
   return 0;
 }
 
-extern "C" int vm_test_special(const double* x, double* dg, double* lg, int64_t n, void* stream) {
-  if (n <= 0) return 0;
-  k_test_special<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, dg, lg, n);
-  VM_CHECK_LAUNCH();
-  return 0;
+
+}  // namespace
+
+extern "C" const vm_tu_api* VM_PASTE(vm_tu_api_, VM_TU_ID)(void) {
+  using namespace VM_PASTE(vmtu, VM_TU_ID);
+  static const vm_tu_api api = {tu_materialize_prior, tu_refresh_cache, tu_init_stats, tu_phase_gamma, tu_phase_phi,
+                                tu_phase_rho,         tu_dense_only,    tu_phase_finish, tu_iteration, tu_run, tu_infer};
+  return &api;
 }
