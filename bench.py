@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--cpu-nodes", type=int, default=1500, help="nodes of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--tile-h", type=int, default=64)
+    ap.add_argument("--tile-h", type=int, default=128)
     return ap.parse_args()
 
 

@@ -229,7 +229,7 @@ class VimureModel(TransformerMixin, BaseEstimator):
         with torch.cuda.device(dev):
             t0 = time.time()
             self._packed = P = _packing.pack(self.X.subs, self.X.vals, self.L, self.N, self.M, self.K, self.R, dev,
-                                             row0=row0, nloc=nloc, tile_h=int(extra_params.get("tile_h", 64)))
+                                             row0=row0, nloc=nloc, tile_h=int(extra_params.get("tile_h", 128)))
             if self.undirected:  # model.py:127-132: X must be symmetric in (i, j)
                 if not bool(torch.all(P.t["e_xT"] == P.t["e_x"])):
                     msg = "If undirected is True, the given network has to be symmetric wrt l and m!"
