@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tile-h", type=int, default=128)
+    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5s"],
+                    help="c3: StandardSBM ego N=20k L=1 K=2 (headline); c4: dense reporting N=8k M=64 L=2 K=2; "
+                         "c5s: GMReciprocity ego L=4 K=3 at N=16k (config 5 scaled to one GPU)")
     return ap.parse_args()
 
 
@@ -52,10 +55,20 @@ def n_nodes_for(gpus, override):
     return (n + 3) // 4 * 4
 
 
-def make_network(N, L, K, seed_y=10, seed_x=20):
+def make_network(N, L, K, seed_y=10, seed_x=20, config="c3"):
+    from vimure_b200 import masks
     from vimure_b200 import synthetic as syn
 
-    net = syn.StandardSBM(N=N, L=L, K=K, C=2, avg_degree=10, seed=seed_y)
+    if config == "c4":  # every one of M=64 reporters reports every tie
+        net = syn.StandardSBM(N=N, M=64, L=L, K=K, C=2, avg_degree=10, seed=seed_y)
+        net.X, net.theta = syn.dense_reporting_X(net, M=64, mutuality=0.5, seed=seed_x)
+        net.R = masks.AllMask(L, N, 64)
+        net.M = 64
+        return net
+    if config == "c5s":
+        net = syn.Multitensor(N=N, L=L, K=K, C=2, avg_degree=10, eta=0.5, seed=seed_y)
+    else:
+        net = syn.StandardSBM(N=N, L=L, K=K, C=2, avg_degree=10, seed=seed_y)
     net.build_X(mutuality=0.5, seed=seed_x)
     return net
 
@@ -207,7 +220,11 @@ def run_ours(args):
 
     L, K = args.L, args.K
     N = n_nodes_for(world, args.nodes)
-    net = make_network(N, L, K)
+    if args.config == "c4":
+        L, K, N = 2, 2, args.nodes or 8000
+    elif args.config == "c5s":
+        L, K, N = 4, 3, args.nodes or 16000
+    net = make_network(N, L, K, config=args.config)
     T = float(L) * N * N
     nnzX = len(net.X.vals)
 
@@ -274,6 +291,15 @@ def run_ours(args):
     d1.record()
     torch.cuda.synchronize(dev)
     dense_ms = d0.elapsed_time(d1) / reps
+    # the same iteration without the slab write (fit(store_rho=False): rho materialised at ELBO iterations only)
+    torch.cuda.synchronize(dev)
+    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.iterate(2, store=False, store_last=False)
+    n0.record()
+    eng.iterate(10, store=False, store_last=True)
+    n1.record()
+    torch.cuda.synchronize(dev)
+    ms_nostore = n0.elapsed_time(n1) / 10
     ties_local = float(L) * nloc * N
     alg_bytes = 4.0 * K * ties_local
     achieved = alg_bytes / (dense_ms * 1e-3) / 1e9
@@ -338,13 +364,16 @@ def run_ours(args):
             "metric": "cavi_ties_per_s", "value": value, "unit": "ties/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 storage / f64 accumulate", "data": "synthetic",
-            "config": {"workload": "StandardSBM ego-only N=%d M=N L=%d K=%d mutuality (config 3 of BASELINE.json%s)"
-                                   % (N, L, K, "" if world == 1 else ", grown to keep 4e8 ties per GPU"),
+            "config": {"workload": {"c3": "StandardSBM ego-only N=%d M=N L=%d K=%d mutuality (config 3 of BASELINE.json%s)"
+                                         % (N, L, K, "" if world == 1 else ", grown to keep 4e8 ties per GPU"),
+                                   "c4": "dense reporting N=%d M=64 all-report-all L=%d K=%d (config 4 of BASELINE.json)" % (N, L, K),
+                                   "c5s": "GMReciprocity ego-only N=%d L=%d K=%d (config 5 of BASELINE.json scaled to one GPU)" % (N, L, K),
+                                   }[args.config],
                        "nnz_X": nnzX, "special_ties_rank0": P.U, "ties": T, "row_block_sharding": world,
                        "l2": "per-iteration output (%.1f GB slab) exceeds L2" % (alg_bytes / 1e9),
                        "elbo_cadence": "iter 1, every 10th, last (inside the timed region)"},
-            "iter_per_s": args.steps / (ms * 1e-3), "reports_per_s": args.steps * (2.0 * N - 1) * net.M * L / (ms * 1e-3),
-            "elbo_final": elbo_final, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "iter_per_s": args.steps / (ms * 1e-3), "reports_per_s": args.steps * ((2.0 * N - 1) * net.M * L if args.config != "c4" else float(N) * N * net.M * L) / (ms * 1e-3),
+            "elbo_final": elbo_final, "ms_per_step_store_rho_false": ms_nostore, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clk.summary(),
         }
         print(json.dumps(line))
