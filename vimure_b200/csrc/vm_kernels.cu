@@ -343,27 +343,26 @@ __device__ __forceinline__ void vm_tie_logodds(const vm_ctx& c, int l, int64_t l
 // d[0] is not accumulated: sum_k d[k] = (special tie alive) - (closed form alive), which is 0 unless a row
 // underflowed completely; only that residual goes to slot 0 and k_stats_ego rebuilds d[0] = resid - sum_{k>=1} d[k].
 template <int K>
-__device__ __forceinline__ void vm_fix_accumulate(const vm_ctx& c, bool valid, int l, int64_t lrow, int i, int j,
-                                                  double ti, double tj, const double* d, int resid) {
+__device__ __forceinline__ void vm_fix_accumulate(unsigned long long* fix_l, bool ego_diag, bool valid, int lrow, int i,
+                                                  int j, double ti, double tj, const double* d, int resid) {
   // WARP-COLLECTIVE: every lane of the warp must call it (valid = false for lanes without a tie).
   // Consecutive lanes hold consecutive special ties, i.e. mostly the SAME row: the row-reporter contributions are
   // combined with a segmented warp scan first (one atomic per row segment instead of 32 on one address); the
-  // column-reporter contributions go to distinct addresses and are issued directly.
+  // column-reporter contributions go to distinct addresses and are issued directly.  `fix_l` = fixA of the layer.
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const bool diag = (i == j);
-  const bool use = valid && !(diag && !c.ego_diag);
+  const bool use = valid && !(diag && !ego_diag);
   const bool act_i = use && ti > 0.0, act_j = use && !diag && tj > 0.0;  // E[theta] > 0 <=> active reporter
-  const long long key = valid ? (long long)lrow : (long long)(-1 - lane);
+  const int key = valid ? lrow : (-1 - lane);
   bool same[5];
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
-    const long long kn = __shfl_up_sync(full, key, 1 << s);
+    const int kn = __shfl_up_sync(full, key, 1 << s);
     same[s] = (lane >= (1 << s)) && (kn == key);
   }
-  const long long knext = __shfl_down_sync(full, key, 1);
+  const int knext = __shfl_down_sync(full, key, 1);
   const bool tail = valid && ((lane == 31) || (knext != key));
-  unsigned long long* base = reinterpret_cast<unsigned long long*>(c.fixA);
 #pragma unroll
   for (int k = 1; k < K; ++k) {
     const long long q = valid ? __double2ll_rn(d[k] * VM_FIX_SCALE) : 0ll;
@@ -373,13 +372,13 @@ __device__ __forceinline__ void vm_fix_accumulate(const vm_ctx& c, bool valid, i
       const long long qn = __shfl_up_sync(full, qr, 1 << s);
       if (same[s]) qr += qn;
     }
-    if (tail && qr != 0) atomicAdd(base + ((int64_t)l * c.M + i) * K + k, (unsigned long long)qr);
-    if (act_j && q != 0) atomicAdd(base + ((int64_t)l * c.M + j) * K + k, (unsigned long long)q);
+    if (tail && qr != 0) atomicAdd(fix_l + i * K + k, (unsigned long long)qr);
+    if (act_j && q != 0) atomicAdd(fix_l + j * K + k, (unsigned long long)q);
   }
   if (resid != 0) {  // rare: a row underflowed completely
     const unsigned long long q = (unsigned long long)((long long)resid * (long long)VM_FIX_SCALE);
-    if (act_i) atomicAdd(base + ((int64_t)l * c.M + i) * K, q);
-    if (act_j) atomicAdd(base + ((int64_t)l * c.M + j) * K, q);
+    if (act_i) atomicAdd(fix_l + i * K, q);
+    if (act_j) atomicAdd(fix_l + j * K, q);
   }
 }
 
@@ -387,17 +386,29 @@ __device__ __forceinline__ void vm_fix_accumulate(const vm_ctx& c, bool valid, i
 // log rho_k = log(pr_k+EPS) + sum_{entries} dz1_k (E[log theta_m] + E[log lambda_k]) - S E[lambda_k]   (model.py:800-804,
 // 911-921), softmax over k (model.py:807-811), nu statistic (model.py:822-825), ELBO pieces (model.py:967-995, 1306-1313).
 // One thread per tie, VM_SPECIAL_TIES_PER_BLOCK ties per block (4 per thread, strided for coalescing).
+// All per-layer base pointers are hoisted and the per-tie indices are 32-bit: the kernel is issue-bound, and 64-bit
+// index arithmetic was ~1/4 of its instructions.
 template <int K, bool ELBO, int RMODE>
 __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(const __grid_constant__ vm_ctx c, double* part) {
   __shared__ double s_Gl[K], s_Ell[K], s_El[K];
   const int l = blockIdx.y;
-  const int nloc = (int)c.nloc, nct = (int)c.nct;
-  const int64_t u0 = c.utile_ptr[(int64_t)l * nloc * nct], u1 = c.utile_ptr[(int64_t)(l + 1) * nloc * nct];
+  const int nloc = (int)c.nloc, nct = (int)c.nct, N = (int)c.N, M = (int)c.M, row0 = (int)c.row0;
+  const int u0 = c.utile_ptr[(int64_t)l * nloc * nct], u1 = c.utile_ptr[(int64_t)(l + 1) * nloc * nct];
   constexpr bool elbo = ELBO;
   const bool mut = c.mutuality != 0;
   const bool may_dead = vm_may_dead<K>(c, l);
+  const bool ego_diag = c.ego_diag != 0;
+  const double eps = c.eps;
   const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
   const double Gnu = c.nu[VM_NU_G];
+  // per-layer bases
+  const double* er_l = c.er_node + (int64_t)l * N;
+  const double* ge_l = c.GE_theta + 2 * (int64_t)l * M;
+  const double* et_l = c.E_theta + (int64_t)l * M;
+  const float* tabq_l = c.tab_q + (int64_t)l * N * K;
+  const float* tabp = c.tab_p;
+  unsigned long long* fix_l = reinterpret_cast<unsigned long long*>(c.fixA) + (int64_t)l * M * K;
+  const float cat_lp0 = (float)lc[VM_LC_LP0(K)], cat_lpk = (float)lc[VM_LC_LPK(K)], epsf = (float)eps;
   if (threadIdx.x < K) {
     s_Gl[threadIdx.x] = c.G_lambda[l * K + threadIdx.x];
     s_Ell[threadIdx.x] = c.Elog_lambda[l * K + threadIdx.x];
@@ -410,7 +421,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
   for (int k = 0; k < K; ++k) dsum[k] = 0.0;
 
   constexpr int TPT = VM_SPECIAL_TIES_PER_BLOCK / 256;
-  const int64_t ub = u0 + (int64_t)blockIdx.x * VM_SPECIAL_TIES_PER_BLOCK + threadIdx.x;
+  const int ub = u0 + blockIdx.x * VM_SPECIAL_TIES_PER_BLOCK + threadIdx.x;
   // per-tie data of the first tie (incl. its first X entry, stored inline); the next tie's is fetched while the
   // current one is processed, so only ONE dependent gather level (tables indexed by node / reporter) is exposed
   int n_lrow = 0, n_col = 0, n_m0 = 0, n_cnt = 0;
@@ -425,154 +436,156 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
   }
 #pragma unroll 1
   for (int it = 0; it < TPT; ++it) {
-    const int64_t u = ub + it * 256;
+    const int u = ub + it * 256;
     const bool valid = u < u1;
     // outputs of the per-tie block that the warp-collective accumulation below needs
-    int64_t o_lrow = 0;
-    int o_i = 0, o_j = 0, o_resid = 0;
+    int o_lrow = 0, o_i = 0, o_j = 0, o_resid = 0;
     double o_ti = 0.0, o_tj = 0.0, o_dk[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) o_dk[k] = 0.0;
     if (valid) {
-    const int64_t lrow = n_lrow;
-    const int j = n_col, cnt = n_cnt, m0 = n_m0;
-    const float x0 = n_x0, xT0 = n_xT0;
-    const int64_t un = u + 256;
-    if (it + 1 < TPT && un < u1) {
-      n_lrow = c.u_lrow[un];
-      n_col = c.u_col[un];
-      n_cnt = c.u_cnt[un];
-      n_m0 = c.u_m0[un];
-      n_x0 = c.u_x0[un];
-      n_xT0 = c.u_xT0[un];
-    }
-    // the one dependent gather level
-    double2 ge0 = make_double2(0.0, 0.0);
-    if (cnt > 0) ge0 = *reinterpret_cast<const double2*>(c.GE_theta + 2 * ((int64_t)l * c.M + m0));
-    const int i = (int)(lrow - (int64_t)l * nloc) + (int)c.row0;
-    // independent loads first: prior, closed-form tables, reporter expectations
-    double logpr[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) logpr[k] = c.u_logpr[u * K + k];
-    float a[K];
-    vm_tie_logodds<K>(c, l, lrow, j, a);
-    // S = sum over the tie's reporters of E[theta] * R.vals (model.py:766-792)
-    double S, ti = 0.0, tj = 0.0;
-    if (RMODE == VM_R_EGO) {
-      ti = c.er_node[(int64_t)l * c.N + i];
-      tj = c.er_node[(int64_t)l * c.N + j];
-      S = (i == j) ? (c.ego_diag ? ti : 0.0) : ti + tj;
-    } else if (RMODE == VM_R_ALL) {
-      S = lc[VM_LC_SALL(K)];
-    } else {
-      S = 0.0;
-      const int64_t tie = lrow * c.N + j;
-      for (int64_t e = c.r_ptr[tie]; e < c.r_ptr[tie + 1]; ++e)
-        S += c.E_theta[(int64_t)l * c.M + c.r_m[e]] * (double)c.r_val[e];
-    }
-    double lw[K], Dz[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      lw[k] = logpr[k] - S * s_El[k];
-      Dz[k] = 0.0;
-    }
-    int64_t e0 = 0;
-    if (cnt > 1) e0 = c.u_ptr[u];
-    for (int q = 0; q < cnt; ++q) {
-      double2 ge = ge0;  // (G_theta, Elog_theta)
-      double x = (double)x0, xT = (double)xT0;
-      if (q > 0) {
-        const int64_t e = e0 + q;
-        ge = *reinterpret_cast<const double2*>(c.GE_theta + 2 * ((int64_t)l * c.M + c.e_m[e]));
-        x = (double)c.e_x[e];
-        xT = (double)c.e_xT[e];
+      const int lrow = n_lrow;
+      const int j = n_col, cnt = n_cnt, m0 = n_m0;
+      const float x0 = n_x0, xT0 = n_xT0;
+      const int un = u + 256;
+      if (it + 1 < TPT && un < u1) {
+        n_lrow = c.u_lrow[un];
+        n_col = c.u_col[un];
+        n_cnt = c.u_cnt[un];
+        n_m0 = c.u_m0[un];
+        n_x0 = c.u_x0[un];
+        n_xT0 = c.u_xT0[un];
       }
-      if (mut) {
-        const double z2 = Gnu * xT;
+      const int i = lrow - l * nloc + row0;
+      // the one dependent gather level: reporter cache of the first entry, prior, closed-form tables, S
+      double2 ge0 = make_double2(0.0, 0.0);
+      if (cnt > 0) ge0 = *reinterpret_cast<const double2*>(ge_l + 2 * m0);
+      double logpr[K];
+      const double* lp = c.u_logpr + (size_t)u * K;
+#pragma unroll
+      for (int k = 0; k < K; ++k) logpr[k] = lp[k];
+      float a[K];
+      if (RMODE == VM_R_CSR) {
+        vm_tie_logodds<K>(c, l, lrow, j, a);
+      } else {
+        const float* tp = tabp + lrow * K;
+        const float* tq = tabq_l + j * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) a[k] = __fadd_rn(tp[k], tq[k]);
+      }
+      // S = sum over the tie's reporters of E[theta] * R.vals (model.py:766-792)
+      double S, ti = 0.0, tj = 0.0;
+      if (RMODE == VM_R_EGO) {
+        ti = er_l[i];
+        tj = er_l[j];
+        S = (i == j) ? (ego_diag ? ti : 0.0) : ti + tj;
+      } else if (RMODE == VM_R_ALL) {
+        S = lc[VM_LC_SALL(K)];
+      } else {
+        S = 0.0;
+        const int64_t tie = (int64_t)lrow * N + j;
+        for (int64_t e = c.r_ptr[tie]; e < c.r_ptr[tie + 1]; ++e) S += et_l[c.r_m[e]] * (double)c.r_val[e];
+      }
+      double lw[K], Dz[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        lw[k] = logpr[k] - S * s_El[k];
+        Dz[k] = 0.0;
+      }
+      int64_t e0 = 0;
+      if (cnt > 1 || elbo) e0 = c.u_ptr[u];
+      for (int q = 0; q < cnt; ++q) {
+        double2 ge = ge0;  // (G_theta, Elog_theta)
+        double x = (double)x0, xT = (double)xT0;
+        if (q > 0) {
+          const int64_t e = e0 + q;
+          ge = *reinterpret_cast<const double2*>(ge_l + 2 * c.e_m[e]);
+          x = (double)c.e_x[e];
+          xT = (double)c.e_xT[e];
+        }
+        if (mut) {
+          const double z2 = Gnu * xT;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const double z1 = ge.x * s_Gl[k];
+            const double den = z1 + z2;
+            const double xi = (den == 0.0) ? 0.0 : x * vm_rcp64(den);  // model.py:692 (Q5)
+            lw[k] += (xi * z1) * (ge.y + s_Ell[k]);
+            Dz[k] += xi * z2;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < K; ++k) lw[k] += x * (ge.y + s_Ell[k]);
+        }
+      }
+      double mx = lw[0];
+#pragma unroll
+      for (int k = 1; k < K; ++k) mx = fmax(mx, lw[k]);
+      double rho[K];
+      const bool alive_u = mx >= VM_DEAD_LN;
+      if (!alive_u) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) rho[k] = 0.0;
+        c.dev_flags[0] = 1;  // benign race: every writer stores the same value
+      } else {
+        double sum = 0.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          const double z1 = ge.x * s_Gl[k];
-          const double den = z1 + z2;
-          const double xi = (den == 0.0) ? 0.0 : x * vm_rcp64(den);  // model.py:692 (Q5)
-          lw[k] += (xi * z1) * (ge.y + s_Ell[k]);
-          Dz[k] += xi * z2;
+          rho[k] = exp(lw[k] - mx);
+          sum += rho[k];
         }
-      } else {
+        const double inv = vm_rcp64(sum);
 #pragma unroll
-        for (int k = 0; k < K; ++k) lw[k] += x * (ge.y + s_Ell[k]);
+        for (int k = 0; k < K; ++k) rho[k] *= inv;
       }
-    }
-    double mx = lw[0];
 #pragma unroll
-    for (int k = 1; k < K; ++k) mx = fmax(mx, lw[k]);
-    double rho[K];
-    if (mx < VM_DEAD_LN) {
+      for (int k = 0; k < K; ++k) nu_acc += Dz[k] * rho[k];  // sum_e sum_k dz2_k rho_k (model.py:822-825)
+      // closed-form value the dense kernel uses for this tie: subtract it again from the statistics
+      float f[K], epsr;
+      bool dead;
+      vm_formula_rho<K>(a, may_dead, f, epsr, dead);
+      {
+        // closed-form k=0 as the statistics count it: the exact complement of the others (F_0 = n - dead - sum F_k)
+        double fk = 0.0;
 #pragma unroll
-      for (int k = 0; k < K; ++k) rho[k] = 0.0;
-      c.dev_flags[0] = 1;  // benign race: every writer stores the same value
-    } else {
-      double sum = 0.0;
+        for (int k = 1; k < K; ++k) fk += (double)f[k];
+        double* ru = c.rho_u + (size_t)u * K;
+        float* ru32 = c.rho_u32 + (size_t)u * K;
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        rho[k] = exp(lw[k] - mx);
-        sum += rho[k];
-      }
-      const double inv = vm_rcp64(sum);
-#pragma unroll
-      for (int k = 0; k < K; ++k) rho[k] *= inv;
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) nu_acc += Dz[k] * rho[k];  // sum_e sum_k dz2_k rho_k (model.py:822-825)
-    // closed-form value the dense kernel uses for this tie: subtract it again from the statistics
-    float f[K], epsr;
-    bool dead;
-    vm_formula_rho<K>(a, may_dead, f, epsr, dead);
-    {
-      // closed-form k=0 as the statistics count it: the exact complement of the others (F_0 = n - dead - sum F_k)
-      double fk = 0.0, dk[K];
-#pragma unroll
-      for (int k = 1; k < K; ++k) fk += (double)f[k];
-      const bool alive_u = mx >= VM_DEAD_LN;
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const double fv = (k == 0) ? (dead ? 0.0 : 1.0 - fk) : (double)f[k];
-        dk[k] = rho[k] - fv;
-        c.rho_u[u * K + k] = rho[k];
-        c.rho_u32[u * K + k] = (float)rho[k];
-        dsum[k] += dk[k];
-      }
-      o_lrow = lrow;
-      o_i = i;
-      o_j = j;
-      o_ti = ti;
-      o_tj = tj;
-      o_resid = (alive_u ? 1 : 0) - (dead ? 0 : 1);
-#pragma unroll
-      for (int k = 0; k < K; ++k) o_dk[k] = dk[k];
-    }
-    if (elbo) {
-      // log-Poisson-mean term: uses exp(rho) (Q1) and only the entries that are also in R (model.py:967-995)
-      double erho[K];
-#pragma unroll
-      for (int k = 0; k < K; ++k) erho[k] = exp(rho[k]);
-      const int64_t ef = c.u_ptr[u];
-      for (int64_t e = ef; e < ef + cnt; ++e) {
-        const int64_t lm = (int64_t)l * c.M + c.e_m[e];
-        const double Gth = c.GE_theta[2 * lm], x = (double)c.e_x[e], z2 = Gnu * (double)c.e_xT[e];
-        double val = 0.0;
-        if (c.e_flags[e] & 1) {
-#pragma unroll
-          for (int k = 0; k < K; ++k) val += erho[k] * (Gth * s_Gl[k] + z2);
+        for (int k = 0; k < K; ++k) {
+          const double fv = (k == 0) ? (dead ? 0.0 : 1.0 - fk) : (double)f[k];
+          o_dk[k] = rho[k] - fv;
+          ru[k] = rho[k];
+          ru32[k] = (float)rho[k];
+          dsum[k] += o_dk[k];
         }
-        t2_acc += x * log(val + c.eps);
+        o_lrow = lrow;
+        o_i = i;
+        o_j = j;
+        o_ti = ti;
+        o_tj = tj;
+        o_resid = (alive_u ? 1 : 0) - (dead ? 0 : 1);
       }
+      if (elbo) {
+        // log-Poisson-mean term: uses exp(rho) (Q1) and only the entries that are also in R (model.py:967-995)
+        double erho[K];
 #pragma unroll
-      for (int k = 0; k < K; ++k) cat_acc += rho[k] * (logpr[k] - log(rho[k] + c.eps));
-      cat_acc -= (double)vm_formula_cat<K>(f, epsr, dead, (float)lc[VM_LC_LP0(K)], (float)lc[VM_LC_LPK(K)],
-                                            (float)c.eps);
-    }
+        for (int k = 0; k < K; ++k) erho[k] = exp(rho[k]);
+        for (int64_t e = e0; e < e0 + cnt; ++e) {
+          const double Gth = ge_l[2 * c.e_m[e]], x = (double)c.e_x[e], z2 = Gnu * (double)c.e_xT[e];
+          double val = 0.0;
+          if (c.e_flags[e] & 1) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) val += erho[k] * (Gth * s_Gl[k] + z2);
+          }
+          t2_acc += x * log(val + eps);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) cat_acc += rho[k] * (logpr[k] - log(rho[k] + eps));
+        cat_acc -= (double)vm_formula_cat<K>(f, epsr, dead, cat_lp0, cat_lpk, epsf);
+      }
     }  // valid
-    if (RMODE == VM_R_EGO) vm_fix_accumulate<K>(c, valid, l, o_lrow, o_i, o_j, o_ti, o_tj, o_dk, o_resid);
+    if (RMODE == VM_R_EGO) vm_fix_accumulate<K>(fix_l, ego_diag, valid, o_lrow, o_i, o_j, o_ti, o_tj, o_dk, o_resid);
   }
   // per-WARP partials (no block barrier: a warp retires as soon as its own ties are done)
   const int64_t nup = c.L * c.n_ublk * 8, b = ((int64_t)l * c.n_ublk + blockIdx.x) * 8 + (threadIdx.x >> 5);
@@ -1183,7 +1196,9 @@ __global__ void k_init_delta(const __grid_constant__ vm_ctx c) {
       tj = (j < (int)c.M && c.rep[(int64_t)l * c.M + j]) ? 1.0 : 0.0;
     }
   }
-  if (c.r_mode == VM_R_EGO) vm_fix_accumulate<K>(c, valid, l, lrow, i, j, ti, tj, d, 0);
+  if (c.r_mode == VM_R_EGO)
+    vm_fix_accumulate<K>(reinterpret_cast<unsigned long long*>(c.fixA) + (int64_t)l * c.M * K, c.ego_diag != 0, valid,
+                         (int)lrow, i, j, ti, tj, d, 0);
 }
 // per-layer totals of delta_u, for the all-reporter initial statistics
 __global__ void __launch_bounds__(256) k_init_delta_all(const __grid_constant__ vm_ctx c, double* upart) {
