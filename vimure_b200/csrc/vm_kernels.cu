@@ -99,12 +99,15 @@ __global__ void __launch_bounds__(256) k_gamma_partial(const __grid_constant__ v
   if (lane == 0) part[chunk] = acc;
 }
 
-__global__ void k_gamma_reduce(const __grid_constant__ vm_ctx c, const double* part) {
-  const int64_t lm = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_gamma_reduce(const __grid_constant__ vm_ctx c, const double* part) {
+  // one warp per reporter: a reporter that reports every tie owns thousands of chunks
+  const int lane = threadIdx.x & 31;
+  const int64_t lm = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (lm >= c.L * c.M) return;
   double s = 0.0;
-  for (int64_t q = c.g_lm_cptr[lm]; q < c.g_lm_cptr[lm + 1]; ++q) s += part[q];
-  c.red1[lm] = s;
+  for (int64_t q = c.g_lm_cptr[lm] + lane; q < c.g_lm_cptr[lm + 1]; q += 32) s += part[q];
+  s = warp_sum(s);
+  if (lane == 0) c.red1[lm] = s;
 }
 
 // =====================================================================================================
@@ -337,6 +340,29 @@ __device__ __forceinline__ void vm_tie_logodds(const vm_ctx& c, int l, int64_t l
   }
 }
 
+#define VM_LONG_TIE 8  // ties with more X entries than this are swept cooperatively by the warp
+
+// contribution of one X entry to the log-weights of its tie and to the nu statistic:
+// lw_k += dz1_k (E[log theta_m] + E[log lambda_k]),  Dz_k += dz2_k   (model.py:693-696, 916-921)
+template <int K>
+__device__ __forceinline__ void vm_entry_accumulate(bool mut, double x, double xT, double2 ge, double Gnu,
+                                                    const double* s_Gl, const double* s_Ell, double* lw, double* Dz) {
+  if (mut) {
+    const double z2 = Gnu * xT;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double z1 = ge.x * s_Gl[k];
+      const double den = z1 + z2;
+      const double xi = (den == 0.0) ? 0.0 : x * vm_rcp64(den);  // model.py:692 (Q5)
+      lw[k] += (xi * z1) * (ge.y + s_Ell[k]);
+      Dz[k] += xi * z2;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) lw[k] += x * (ge.y + s_Ell[k]);
+  }
+}
+
 // Per-reporter accumulation of d[k] = (posterior of a special tie) - (closed form the dense kernel counts for it),
 // ego mask: the tie (i,j) is reported by i and by j (the diagonal tie once, and only if the mask contains it).
 // Fixed point + integer atomics: the sum is exact in any order, so the result is bit-reproducible.
@@ -438,14 +464,22 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
   for (int it = 0; it < TPT; ++it) {
     const int u = ub + it * 256;
     const bool valid = u < u1;
-    // outputs of the per-tie block that the warp-collective accumulation below needs
-    int o_lrow = 0, o_i = 0, o_j = 0, o_resid = 0;
-    double o_ti = 0.0, o_tj = 0.0, o_dk[K];
+    // ---- stage A (per thread): tie data, S, prior; entries of SHORT ties
+    int lrow = 0, i = 0, j = 0, cnt = 0;
+    int64_t e0 = 0;
+    double ti = 0.0, tj = 0.0;
+    double lw[K], Dz[K], logpr[K];
+    float a[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) o_dk[k] = 0.0;
+    for (int k = 0; k < K; ++k) {
+      lw[k] = Dz[k] = logpr[k] = 0.0;
+      a[k] = 0.f;
+    }
     if (valid) {
-      const int lrow = n_lrow;
-      const int j = n_col, cnt = n_cnt, m0 = n_m0;
+      lrow = n_lrow;
+      j = n_col;
+      cnt = n_cnt;
+      const int m0 = n_m0;
       const float x0 = n_x0, xT0 = n_xT0;
       const int un = u + 256;
       if (it + 1 < TPT && un < u1) {
@@ -456,15 +490,13 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
         n_x0 = c.u_x0[un];
         n_xT0 = c.u_xT0[un];
       }
-      const int i = lrow - l * nloc + row0;
+      i = lrow - l * nloc + row0;
       // the one dependent gather level: reporter cache of the first entry, prior, closed-form tables, S
       double2 ge0 = make_double2(0.0, 0.0);
-      if (cnt > 0) ge0 = *reinterpret_cast<const double2*>(ge_l + 2 * m0);
-      double logpr[K];
+      if (cnt > 0 && cnt <= VM_LONG_TIE) ge0 = *reinterpret_cast<const double2*>(ge_l + 2 * m0);
       const double* lp = c.u_logpr + (size_t)u * K;
 #pragma unroll
       for (int k = 0; k < K; ++k) logpr[k] = lp[k];
-      float a[K];
       if (RMODE == VM_R_CSR) {
         vm_tie_logodds<K>(c, l, lrow, j, a);
       } else {
@@ -474,7 +506,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
         for (int k = 0; k < K; ++k) a[k] = __fadd_rn(tp[k], tq[k]);
       }
       // S = sum over the tie's reporters of E[theta] * R.vals (model.py:766-792)
-      double S, ti = 0.0, tj = 0.0;
+      double S;
       if (RMODE == VM_R_EGO) {
         ti = er_l[i];
         tj = er_l[j];
@@ -486,38 +518,60 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
         const int64_t tie = (int64_t)lrow * N + j;
         for (int64_t e = c.r_ptr[tie]; e < c.r_ptr[tie + 1]; ++e) S += et_l[c.r_m[e]] * (double)c.r_val[e];
       }
-      double lw[K], Dz[K];
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        lw[k] = logpr[k] - S * s_El[k];
-        Dz[k] = 0.0;
-      }
-      int64_t e0 = 0;
+      for (int k = 0; k < K; ++k) lw[k] = logpr[k] - S * s_El[k];
       if (cnt > 1 || elbo) e0 = c.u_ptr[u];
-      for (int q = 0; q < cnt; ++q) {
-        double2 ge = ge0;  // (G_theta, Elog_theta)
-        double x = (double)x0, xT = (double)xT0;
-        if (q > 0) {
-          const int64_t e = e0 + q;
-          ge = *reinterpret_cast<const double2*>(ge_l + 2 * c.e_m[e]);
-          x = (double)c.e_x[e];
-          xT = (double)c.e_xT[e];
-        }
-        if (mut) {
-          const double z2 = Gnu * xT;
-#pragma unroll
-          for (int k = 0; k < K; ++k) {
-            const double z1 = ge.x * s_Gl[k];
-            const double den = z1 + z2;
-            const double xi = (den == 0.0) ? 0.0 : x * vm_rcp64(den);  // model.py:692 (Q5)
-            lw[k] += (xi * z1) * (ge.y + s_Ell[k]);
-            Dz[k] += xi * z2;
+      if (cnt <= VM_LONG_TIE) {
+        for (int q = 0; q < cnt; ++q) {
+          double2 ge = ge0;  // (G_theta, Elog_theta)
+          double x = (double)x0, xT = (double)xT0;
+          if (q > 0) {
+            const int64_t e = e0 + q;
+            ge = *reinterpret_cast<const double2*>(ge_l + 2 * c.e_m[e]);
+            x = (double)c.e_x[e];
+            xT = (double)c.e_xT[e];
           }
-        } else {
-#pragma unroll
-          for (int k = 0; k < K; ++k) lw[k] += x * (ge.y + s_Ell[k]);
+          vm_entry_accumulate<K>(mut, x, xT, ge, Gnu, s_Gl, s_Ell, lw, Dz);
         }
       }
+    }
+    // ---- stage B (warp-cooperative): ties with many entries (e.g. every reporter reports the tie) are swept by the
+    // whole warp, 32 entries at a time, instead of serialising one lane
+    {
+      unsigned longmask = __ballot_sync(0xffffffffu, valid && cnt > VM_LONG_TIE);
+      const int lane_b = threadIdx.x & 31;
+      while (longmask) {
+        const int b = __ffs(longmask) - 1;
+        longmask &= longmask - 1;
+        const int64_t be0 = __shfl_sync(0xffffffffu, e0, b);
+        const int bcnt = __shfl_sync(0xffffffffu, cnt, b);
+        double plw[K], pDz[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) plw[k] = pDz[k] = 0.0;
+        for (int q = lane_b; q < bcnt; q += 32) {
+          const int64_t e = be0 + q;
+          const double2 ge = *reinterpret_cast<const double2*>(ge_l + 2 * c.e_m[e]);
+          vm_entry_accumulate<K>(mut, (double)c.e_x[e], (double)c.e_xT[e], ge, Gnu, s_Gl, s_Ell, plw, pDz);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          plw[k] = warp_sum(plw[k]);  // fixed order; total in lane 0
+          pDz[k] = warp_sum(pDz[k]);
+          plw[k] = __shfl_sync(0xffffffffu, plw[k], 0);
+          pDz[k] = __shfl_sync(0xffffffffu, pDz[k], 0);
+          if (lane_b == b) {
+            lw[k] += plw[k];
+            Dz[k] += pDz[k];
+          }
+        }
+      }
+    }
+    // ---- stage C (per thread): softmax, statistics, stores
+    int o_resid = 0;
+    double o_dk[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) o_dk[k] = 0.0;
+    if (valid) {
       double mx = lw[0];
 #pragma unroll
       for (int k = 1; k < K; ++k) mx = fmax(mx, lw[k]);
@@ -559,11 +613,6 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
           ru32[k] = (float)rho[k];
           dsum[k] += o_dk[k];
         }
-        o_lrow = lrow;
-        o_i = i;
-        o_j = j;
-        o_ti = ti;
-        o_tj = tj;
         o_resid = (alive_u ? 1 : 0) - (dead ? 0 : 1);
       }
       if (elbo) {
@@ -585,7 +634,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
         cat_acc -= (double)vm_formula_cat<K>(f, epsr, dead, cat_lp0, cat_lpk, epsf);
       }
     }  // valid
-    if (RMODE == VM_R_EGO) vm_fix_accumulate<K>(fix_l, ego_diag, valid, o_lrow, o_i, o_j, o_ti, o_tj, o_dk, o_resid);
+    if (RMODE == VM_R_EGO) vm_fix_accumulate<K>(fix_l, ego_diag, valid, lrow, i, j, ti, tj, o_dk, o_resid);
   }
   // per-WARP partials (no block barrier: a warp retires as soon as its own ties are done)
   const int64_t nup = c.L * c.n_ublk * 8, b = ((int64_t)l * c.n_ublk + blockIdx.x) * 8 + (threadIdx.x >> 5);
@@ -1110,8 +1159,8 @@ __global__ void __launch_bounds__(256) k_stats_ego(const __grid_constant__ vm_ct
 
 // all-reporter mask: A[l,m,:] is the same for every m = per-layer totals.
 template <int K>
-__global__ void __launch_bounds__(256) k_stats_all(const __grid_constant__ vm_ctx c, int init, const double* upart) {
-  __shared__ double sm[8];
+__global__ void __launch_bounds__(1024) k_stats_all(const __grid_constant__ vm_ctx c, int init, const double* upart) {
+  __shared__ double sm[32];
   __shared__ double tot[K];
   const int l = blockIdx.x;
   const int64_t nrow = c.nloc * c.nct, nup = c.L * c.n_ublk * 8, nwl = c.n_ublk * 8;
@@ -1119,19 +1168,19 @@ __global__ void __launch_bounds__(256) k_stats_all(const __grid_constant__ vm_ct
 #pragma unroll
   for (int k = 0; k < K; ++k) f[k] = d[k] = 0.0;
   if (!init)
-    for (int64_t t = threadIdx.x; t < nrow; t += 256) {
+    for (int64_t t = threadIdx.x; t < nrow; t += 1024) {
 #pragma unroll
       for (int k = 0; k < K; ++k) f[k] += (double)c.rowpart[((int64_t)l * nrow + t) * K + k];
     }
-  for (int64_t b = threadIdx.x; b < nwl; b += 256) {
+  for (int64_t b = threadIdx.x; b < nwl; b += 1024) {
 #pragma unroll
     for (int k = 0; k < K; ++k) d[k] += upart[(UP_DELTA + k) * nup + (int64_t)l * nwl + b];
   }
   double fs[K], ds[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    fs[k] = block_sum<256>(f[k], sm);
-    ds[k] = block_sum<256>(d[k], sm);
+    fs[k] = block_sum<1024>(f[k], sm);
+    ds[k] = block_sum<1024>(d[k], sm);
   }
   if (threadIdx.x == 0) {
     double f0 = (double)c.nloc * (double)c.N - (init ? 0.0 : fs[0]);
@@ -1142,7 +1191,7 @@ __global__ void __launch_bounds__(256) k_stats_all(const __grid_constant__ vm_ct
     for (int k = 1; k < K; ++k) tot[k] = fs[k] + ds[k];
   }
   __syncthreads();
-  for (int64_t t = threadIdx.x; t < c.M * K; t += 256) c.red3[(int64_t)l * c.M * K + t] = tot[t % K];
+  for (int64_t t = threadIdx.x; t < c.M * K; t += 1024) c.red3[(int64_t)l * c.M * K + t] = tot[t % K];
 }
 
 // general mask: gather the (patched) dense slab through the per-reporter CSC.
@@ -1463,7 +1512,7 @@ static int launch_stats(const vm_ctx* c, int init, cudaStream_t st) {
     if (!init) k_col_reduce<K><<<(unsigned)cdiv(LM * K, 256), 256, 0, st>>>(*c);
     k_stats_ego<K><<<(unsigned)cdiv(LM, 8), 256, 0, st>>>(*c, init);
   } else if (c->r_mode == VM_R_ALL) {
-    k_stats_all<K><<<(unsigned)c->L, 256, 0, st>>>(*c, init, region_u(c));
+    k_stats_all<K><<<(unsigned)c->L, 1024, 0, st>>>(*c, init, region_u(c));
   } else {
     k_stats_csc<K><<<(unsigned)cdiv(LM, 8), 256, 0, st>>>(*c, init);
   }
@@ -1528,7 +1577,7 @@ static int tu_phase_gamma(const vm_ctx* c, void* stream) {
     DISPATCH_K(c->K, (k_gamma_partial<K><<<(unsigned)cdiv(c->n_gchunk, 8), 256, 0, st>>>(*c, c->blkpart)));
     VM_CHECK_LAUNCH();
   }
-  k_gamma_reduce<<<(unsigned)cdiv(c->L * c->M, 256), 256, 0, st>>>(*c, c->blkpart);
+  k_gamma_reduce<<<(unsigned)cdiv(c->L * c->M, 8), 256, 0, st>>>(*c, c->blkpart);
   VM_CHECK_LAUNCH();
   return 0;
 }
