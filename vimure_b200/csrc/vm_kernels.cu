@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
   const int nloc = (int)c.nloc, nct = (int)c.nct, N = (int)c.N, M = (int)c.M, row0 = (int)c.row0;
   const int u0 = c.utile_ptr[(int64_t)l * nloc * nct], u1 = c.utile_ptr[(int64_t)(l + 1) * nloc * nct];
   constexpr bool elbo = ELBO;
+  constexpr bool COOP = (RMODE != VM_R_EGO);
   const bool mut = c.mutuality != 0;
   const bool may_dead = vm_may_dead<K>(c, l);
   const bool ego_diag = c.ego_diag != 0;
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
       i = lrow - l * nloc + row0;
       // the one dependent gather level: reporter cache of the first entry, prior, closed-form tables, S
       double2 ge0 = make_double2(0.0, 0.0);
-      if (cnt > 0 && cnt <= VM_LONG_TIE) ge0 = *reinterpret_cast<const double2*>(ge_l + 2 * m0);
+      if (cnt > 0 && (!COOP || cnt <= VM_LONG_TIE)) ge0 = *reinterpret_cast<const double2*>(ge_l + 2 * m0);
       const double* lp = c.u_logpr + (size_t)u * K;
 #pragma unroll
       for (int k = 0; k < K; ++k) logpr[k] = lp[k];
@@ -521,7 +522,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
 #pragma unroll
       for (int k = 0; k < K; ++k) lw[k] = logpr[k] - S * s_El[k];
       if (cnt > 1 || elbo) e0 = c.u_ptr[u];
-      if (cnt <= VM_LONG_TIE) {
+      if (!COOP || cnt <= VM_LONG_TIE) {
         for (int q = 0; q < cnt; ++q) {
           double2 ge = ge0;  // (G_theta, Elog_theta)
           double x = (double)x0, xT = (double)xT0;
@@ -537,7 +538,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(
     }
     // ---- stage B (warp-cooperative): ties with many entries (e.g. every reporter reports the tie) are swept by the
     // whole warp, 32 entries at a time, instead of serialising one lane
-    {
+    if (COOP) {  // an ego mask has at most two reporters per tie: no long ties, stage compiled out
       unsigned longmask = __ballot_sync(0xffffffffu, valid && cnt > VM_LONG_TIE);
       const int lane_b = threadIdx.x & 31;
       while (longmask) {
