@@ -414,8 +414,11 @@ __device__ __forceinline__ void vm_fix_accumulate(unsigned long long* fix_l, boo
 // One thread per tie, VM_SPECIAL_TIES_PER_BLOCK ties per block (4 per thread, strided for coalescing).
 // All per-layer base pointers are hoisted and the per-tie indices are 32-bit: the kernel is issue-bound, and 64-bit
 // index arithmetic was ~1/4 of its instructions.
+#ifndef VM_SPECIAL_MINBLK
+#define VM_SPECIAL_MINBLK 4
+#endif
 template <int K, bool ELBO, int RMODE>
-__global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : 4) : 2)) k_special(const __grid_constant__ vm_ctx c, double* part) {
+__global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) : 2)) k_special(const __grid_constant__ vm_ctx c, double* part) {
   __shared__ double s_Gl[K], s_Ell[K], s_El[K];
   const int l = blockIdx.y;
   const int nloc = (int)c.nloc, nct = (int)c.nct, N = (int)c.N, M = (int)c.M, row0 = (int)c.row0;
