@@ -224,7 +224,31 @@ def run_ours(args):
         L, K, N = 2, 2, args.nodes or 8000
     elif args.config == "c5s":
         L, K, N = 4, 3, args.nodes or 16000
-    net = make_network(N, L, K, config=args.config)
+    if world > 1:
+        # rank 0 generates the network once and shares it through /dev/shm (every rank needs the full COO list to
+        # pair reciprocal reports; generating it 8 times concurrently would need 8x the host memory)
+        from vimure_b200 import masks
+        from vimure_b200.sptensor import sptensor
+
+        tag = "/dev/shm/vimure_bench_%s" % os.environ.get("MASTER_PORT", "0")
+        if rank == 0:
+            net0 = make_network(N, L, K, config=args.config)
+            np.save(tag + "_subs.npy", np.stack(net0.X.subs).astype(np.int32))
+            np.save(tag + "_vals.npy", np.asarray(net0.X.vals).astype(np.int32))
+            del net0
+        dist.barrier()
+
+        class _Net:
+            pass
+
+        net = _Net()
+        subs = np.load(tag + "_subs.npy", mmap_mode="r")
+        vals = np.load(tag + "_vals.npy", mmap_mode="r")
+        net.L, net.N, net.M = L, N, (64 if args.config == "c4" else N)
+        net.X = sptensor(tuple(subs[d] for d in range(4)), vals, shape=(L, N, N, net.M))
+        net.R = masks.AllMask(L, N, 64) if args.config == "c4" else masks.EgoMask(L, N, N, diag=True)
+    else:
+        net = make_network(N, L, K, config=args.config)
     T = float(L) * N * N
     nnzX = len(net.X.vals)
 
@@ -378,6 +402,13 @@ def run_ours(args):
         }
         print(json.dumps(line))
     if dist is not None:
+        dist.barrier()
+        if rank == 0:
+            for suffix in ("_subs.npy", "_vals.npy"):
+                try:
+                    os.remove("/dev/shm/vimure_bench_%s%s" % (os.environ.get("MASTER_PORT", "0"), suffix))
+                except OSError:
+                    pass
         dist.destroy_process_group()
 
 

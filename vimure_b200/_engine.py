@@ -118,10 +118,15 @@ class CaviEngine:
         if self.group is not None:
             torch.distributed.all_reduce(t, group=self.group if self.group is not True else None)
 
-    def kernels_per_iteration(self, elbo=False):
-        """Number of kernels of this library launched by one iteration (for bench.py's gpu_launches)."""
-        # gamma(2) phi(3) rho: phi_finish, [tables], special, dense, [col_reduce], stats, sums; finish(1)
-        n = 2 + 3 + 1 + (0 if self.P.r_mode == 2 else 1) + 2 + (1 if self.P.r_mode == 0 else 0) + 2 + 1
+    def kernels_per_iteration(self, elbo=False, store=True):
+        """Number of kernels of this library launched by one iteration (for bench.py's gpu_launches).
+        gamma: partial, reduce | phi: gamma_finish, phi_partial, phi_reduce | rho: phi_finish, [tables], special,
+        [dense_fast], dense, [col_reduce], stats, [elbo_b], sums_reduce | finish: [elbo_partial], finish."""
+        P = self.P
+        csr, ego = P.r_mode == 2, P.r_mode == 0
+        fast = (P.K <= 4 and not elbo and store and not csr and (P.N * P.K) % 4 == 0 and P.N >= P.tile_w
+                and P.tile_h <= 128)
+        n = 2 + 3 + 1 + (0 if csr else 1) + 1 + (1 if fast else 0) + 1 + (1 if ego else 0) + 1 + 1 + 1
         if elbo:
             n += 1 + (1 if self.mutuality else 0)
         return n
@@ -173,7 +178,8 @@ class CaviEngine:
                 _capi.check(self.lib.vm_phase_rho(self._cref, fl, st), "vm_phase_rho")
                 self._allreduce(self.red3)
                 _capi.check(self.lib.vm_phase_finish(self._cref, fl, st), "vm_phase_finish")
-        self.n_launch += (n - 1) * self.kernels_per_iteration(False) + self.kernels_per_iteration(elbo_last)
+        self.n_launch += (n - 1) * self.kernels_per_iteration(False, store) + \
+            self.kernels_per_iteration(elbo_last, store or store_last)
         self.rho_valid = bool(store or store_last)
         self.rho_is_prior = False
 

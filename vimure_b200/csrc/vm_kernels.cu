@@ -415,7 +415,7 @@ __device__ __forceinline__ void vm_fix_accumulate(unsigned long long* fix_l, boo
 // All per-layer base pointers are hoisted and the per-tie indices are 32-bit: the kernel is issue-bound, and 64-bit
 // index arithmetic was ~1/4 of its instructions.
 #ifndef VM_SPECIAL_MINBLK
-#define VM_SPECIAL_MINBLK 4
+#define VM_SPECIAL_MINBLK 3
 #endif
 template <int K, bool ELBO, int RMODE>
 __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) : 2)) k_special(const __grid_constant__ vm_ctx c, double* part) {
