@@ -997,6 +997,12 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2) ? VM_FAST_MINBLK2 :
       for (int t = 0; t < 4; ++t) colacc[ch][k][t] = 0.f;
   int off = 0;
   bool waited = false;
+  // the shuffle reduction of a row's partial sums is software-pipelined into the NEXT row's chunk loop (one step per
+  // chunk), so that its dependent SHFL->FADD chain never stalls the warp
+  float prev[K];
+  int64_t prev_idx = -1;
+#pragma unroll
+  for (int k = 1; k < K; ++k) prev[k] = 0.f;
   for (int r = warp; r < nrows; r += NW) {
     const int64_t lrow = (int64_t)l * nloc + i_lo + r;
     float p[K];
@@ -1033,14 +1039,25 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2) ? VM_FAST_MINBLK2 :
         }
       }
       vm_store_chunk<K>(dst + (int64_t)ch * 128 * K, lane, o, stage[warp]);
-    }
-    // ---- row partials
+      if (ch < 5) {  // step `ch` of the previous row's reduction (same order as warp_sum: 16, 8, 4, 2, 1)
 #pragma unroll
-    for (int k = 1; k < K; ++k) {
-      const float v = warp_sum(rowacc[k]);
-      if (lane == 0) c.rowpart[(lrow * nct + ct) * K + k] = v;
+        for (int k = 1; k < K; ++k) prev[k] += __shfl_down_sync(0xffffffffu, prev[k], 16 >> ch);
+      }
     }
-    if (lane == 0) c.rowpart[(lrow * nct + ct) * K] = 0.f;
+#pragma unroll
+    for (int st = NCH; st < 5; ++st) {
+#pragma unroll
+      for (int k = 1; k < K; ++k) prev[k] += __shfl_down_sync(0xffffffffu, prev[k], 16 >> st);
+    }
+    // ---- row partials of the previous row; this row's become `prev`
+    if (prev_idx >= 0 && lane == 0) {
+      c.rowpart[prev_idx] = 0.f;
+#pragma unroll
+      for (int k = 1; k < K; ++k) c.rowpart[prev_idx + k] = prev[k];
+    }
+    prev_idx = (lrow * nct + ct) * K;
+#pragma unroll
+    for (int k = 1; k < K; ++k) prev[k] = rowacc[k];
     // ---- patch the special ties of this row segment (after the row's own stores)
     if (!waited) {
       vm_cp_async_wait_all();
@@ -1060,6 +1077,15 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2) ? VM_FAST_MINBLK2 :
       for (int k = 0; k < K; ++k) rowdst[(int64_t)col * K + k] = c.rho_u32[(int64_t)(ua + e) * K + k];
     }
     off += take;
+  }
+  if (prev_idx >= 0) {  // the last row of this warp
+#pragma unroll
+    for (int k = 1; k < K; ++k) prev[k] = warp_sum(prev[k]);
+    if (lane == 0) {
+      c.rowpart[prev_idx] = 0.f;
+#pragma unroll
+      for (int k = 1; k < K; ++k) c.rowpart[prev_idx + k] = prev[k];
+    }
   }
   // ---- column partials: combine the 8 warps in a fixed order
   for (int w = 0; w < NW; ++w) {
