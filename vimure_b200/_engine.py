@@ -124,7 +124,7 @@ class CaviEngine:
         [dense_fast], dense, [col_reduce], stats, [elbo_b], sums_reduce | finish: [elbo_partial], finish."""
         P = self.P
         csr, ego = P.r_mode == 2, P.r_mode == 0
-        fast = (P.K <= 4 and not elbo and store and not csr and (P.N * P.K) % 4 == 0 and P.N >= P.tile_w
+        fast = (P.K <= 4 and store and not csr and (P.N * P.K) % 4 == 0 and P.N >= P.tile_w
                 and P.tile_h <= 128)
         n = 2 + 3 + 1 + (0 if csr else 1) + 1 + (1 if fast else 0) + 1 + (1 if ego else 0) + 1 + 1 + 1
         if elbo:

@@ -938,8 +938,8 @@ struct FastCfg {
 #ifndef VM_FAST_MINBLK2
 #define VM_FAST_MINBLK2 4
 #endif
-template <int K>
-__global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2) ? VM_FAST_MINBLK2 : 2) k_dense_fast(const __grid_constant__ vm_ctx c) {
+template <int K, bool ELBO>
+__global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_MINBLK2 : 2) k_dense_fast(const __grid_constant__ vm_ctx c, double* catpart) {
   constexpr int NCH = DenseCfg<K>::NCH, TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32, CAPW = FastCfg<K>::CAPW;
   __shared__ __align__(16) float qs[K - 1][TW];
   __shared__ __align__(16) float colbuf[K - 1][TW];
@@ -948,6 +948,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2) ? VM_FAST_MINBLK2 :
   __shared__ int tp0[VM_FAST_MAX_TILE_H], tp1[VM_FAST_MAX_TILE_H];
   __shared__ int pcol[NW][CAPW];
   __shared__ float pval[NW][CAPW][K];
+  __shared__ double sm_red[8];
   const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
   const int ct = blockIdx.x;
   const int l = blockIdx.y / nrt, rt = blockIdx.y - l * nrt;
@@ -956,6 +957,9 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2) ? VM_FAST_MINBLK2 :
   const int jt = ct * TW;
   const int i_lo = rt * (int)c.tile_h;
   const int nrows = min((int)c.tile_h, nloc - i_lo);
+  const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
+  const float lp0 = (float)lc[VM_LC_LP0(K)], lpk = (float)lc[VM_LC_LPK(K)], epsf = (float)c.eps;
+  double cat = 0.0;
   // ---- phase 0: everything the row loop reads from global memory, once per CTA
   for (int idx = tid; idx < TW; idx += VM_DENSE_THREADS) {
 #pragma unroll
@@ -1037,6 +1041,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2) ? VM_FAST_MINBLK2 :
           colacc[ch][k - 1][t] += v;
           rowacc[k] += v;
         }
+        if (ELBO) cat += (double)vm_formula_cat<K>(&o[t * K], s, false, lp0, lpk, epsf);
       }
       vm_store_chunk<K>(dst + (int64_t)ch * 128 * K, lane, o, stage[warp]);
       if (ch < 5) {  // step `ch` of the previous row's reduction (same order as warp_sum: 16, 8, 4, 2, 1)
@@ -1104,6 +1109,10 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2) ? VM_FAST_MINBLK2 :
     cp[0] = 0.f;
 #pragma unroll
     for (int k = 1; k < K; ++k) cp[k] = colbuf[k - 1][idx];
+  }
+  if (ELBO) {
+    const double v = block_sum<VM_DENSE_THREADS>(cat, sm_red);
+    if (tid == 0) catpart[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
   }
 }
 
@@ -1503,9 +1512,12 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st) {
   const dim3 grid((unsigned)c->nct, (unsigned)(c->L * c->nrt));
   const bool elbo = flags & VM_F_ELBO, store = !(flags & VM_F_NO_STORE), csr = c->r_mode == VM_R_CSR;
   double* cp = region_cat(c);
-  const bool fast = K <= 4 && !elbo && store && !csr && ((c->N * K) & 3) == 0 && c->N >= c->tile_w &&
+  const bool fast = K <= 4 && store && !csr && ((c->N * K) & 3) == 0 && c->N >= c->tile_w &&
                     c->tile_h <= VM_FAST_MAX_TILE_H;
-  if (fast) k_dense_fast<(K <= 4 ? K : 2)><<<grid, VM_DENSE_THREADS, 0, st>>>(*c);
+  if (fast) {
+    if (elbo) k_dense_fast<(K <= 4 ? K : 2), true><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp);
+    else k_dense_fast<(K <= 4 ? K : 2), false><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp);
+  }
 #define LD(E, S, C) k_dense<K, E, S, C><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, fast ? 1 : 0)
   if (csr) {
     if (!store) return VM_ENOTSUP;  // the general-mask statistics gather the slab
