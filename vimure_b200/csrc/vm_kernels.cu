@@ -585,6 +585,13 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
 #pragma unroll
         for (int k = 0; k < K; ++k) rho[k] = 0.0;
         c.dev_flags[0] = 1;  // benign race: every writer stores the same value
+      } else if (K == 2) {
+        // two categories: the larger weight is exp(0) = 1, only one exponential is needed
+        const double e = exp(-fabs(lw[1] - lw[0]));
+        const double inv = vm_rcp64(1.0 + e);
+        const bool one_max = lw[1] > lw[0];
+        rho[0] = one_max ? e * inv : inv;
+        rho[1] = one_max ? inv : e * inv;
       } else {
         double sum = 0.0;
 #pragma unroll
