@@ -109,6 +109,7 @@ class CaviEngine:
         c.A = self.red3.data_ptr()  # A aliases the (all-reduced) statistics vector
         self._cref = ctypes.byref(c)
         self.n_launch = 0
+        self._graphs = None  # flags -> captured CUDA graph of one iteration (small, launch-bound problems)
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -166,7 +167,10 @@ class CaviEngine:
         base = 0 if store else F["VM_F_NO_STORE"]
         last = (0 if (store or store_last) else F["VM_F_NO_STORE"]) | (F["VM_F_ELBO"] if elbo_last else 0)
         st = self._stream()
-        if self.group is None:
+        if self.group is None and self._graphs is not None:
+            for it in range(n):
+                self._graph(last if it == n - 1 else base).replay()
+        elif self.group is None:
             _capi.check(self.lib.vm_run(self._cref, int(n), base, last, st), "vm_run")
         else:
             for it in range(n):
@@ -182,6 +186,23 @@ class CaviEngine:
             self.kernels_per_iteration(elbo_last, store or store_last)
         self.rho_valid = bool(store or store_last)
         self.rho_is_prior = False
+
+    def enable_graphs(self):
+        """Replay one captured CUDA graph per iteration instead of ~17 launches (for launch-bound small problems;
+        single rank only -- the NCCL all-reduces of the sharded path sit between the phases)."""
+        if self.group is None and self._graphs is None:
+            self._graphs = {}
+        return self._graphs is not None
+
+    def _graph(self, flags):
+        g = self._graphs.get(flags)
+        if g is None:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.dev)
+            with torch.cuda.graph(g):  # capture only: nothing executes, the state does not advance
+                _capi.check(self.lib.vm_iteration(self._cref, int(flags), self._stream()), "vm_iteration (capture)")
+            self._graphs[flags] = g
+        return g
 
     # single phases, for tests that emulate several ranks on one GPU
     def phase(self, name, flags=0):

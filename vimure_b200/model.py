@@ -40,6 +40,7 @@ DEFAULT_BIAS0 = 0.0
 DEFAULT_MAX_ITER = 500
 DEFAULT_NUM_REALISATIONS = 1
 AUTO_REFERENCE_INIT_LIMIT = 5e7
+GRAPH_LIMIT = 2e7  # below this many rho entries an iteration is launch-bound: replay a captured CUDA graph
 
 
 class VimureModel(TransformerMixin, BaseEstimator):
@@ -71,7 +72,7 @@ class VimureModel(TransformerMixin, BaseEstimator):
         warnings and ValueErrors, but X/R end up as COO arrays + a structured mask instead of sktensor objects."""
         available = ["R", "EPS", "K", "bias0", "max_iter", "alpha_lambda", "beta_lambda", "alpha_theta", "beta_theta",
                      "alpha_teta", "beta_teta", "num_realisations", "init_state", "init", "device", "distributed",
-                     "store_rho", "tile_h"]
+                     "store_rho", "tile_h", "graphs"]
         for p in extra_params:
             if p not in available:
                 self.logger.warning("Ignoring unrecognised parameter %s." % p)
@@ -238,6 +239,8 @@ class VimureModel(TransformerMixin, BaseEstimator):
             priors = dict(alpha_theta=self.alpha_theta, beta_theta=self.beta_theta, alpha_lambda=self.alpha_lambda,
                           beta_lambda=self.beta_lambda, alpha_eta=self.alpha_mutuality, beta_eta=self.beta_mutuality)
             self._engine = eng = CaviEngine(P, priors, mutuality=self.mutuality, eps=self.EPS, group=group)
+            if group is None and float(self.L) * self.N * self.N * self.K <= GRAPH_LIMIT and extra_params.get("graphs", True):
+                eng.enable_graphs()  # launch-bound sizes: one graph replay per iteration
             torch.cuda.synchronize(dev)
             self.pack_time = self.timings["pack+engine"] = time.time() - t0
 
