@@ -21,7 +21,7 @@ def _packing_const():
 
 
 class CaviEngine:
-    def __init__(self, packed, priors, mutuality=True, eps=1e-12, group=None, may_dead=False):
+    def __init__(self, packed, priors, mutuality=True, eps=1e-12, group=None, may_dead=False, overlap=None):
         P = self.P = packed
         if not torch.cuda.is_available():
             raise RuntimeError("vimure_b200 needs a CUDA device: the CAVI kernels have no CPU fallback")
@@ -90,6 +90,20 @@ class CaviEngine:
         c.eps = float(eps)
         c.alpha_eta, c.beta_eta = self.alpha_eta, self.beta_eta
         c.b_all = float(P.b_all)
+        # special/dense overlap: worthwhile once the special-tie kernel is long enough to matter
+        self.aux_stream = None
+        if overlap is None:
+            overlap = P.U >= 200000
+        if overlap:
+            assert self.C["VM_NCHUNK"] == len(P.rt_end)
+            self.aux_stream = torch.cuda.Stream(device=dev)
+            c.n_chunks = len(P.rt_end)
+            c.rt_end0, c.rt_end1, c.rt_end2, c.rt_end3 = (int(v) for v in P.rt_end)
+            c.sp_grid0, c.sp_grid1, c.sp_grid2, c.sp_grid3 = (int(v) for v in P.sp_grid)
+            c.aux_stream = self.aux_stream.cuda_stream
+        else:
+            c.n_chunks = 0
+            c.aux_stream = None
         self._keep = []
 
         def ptr(t):
@@ -97,7 +111,7 @@ class CaviEngine:
             return t.data_ptr() if t.numel() else self._dummy.data_ptr()
 
         for name in ("u_lrow", "u_col", "u_ptr", "u_cnt", "u_m0", "u_x0", "u_xT0", "utile_ptr", "ucol_ptr", "ucol_perm", "e_u", "e_m", "e_x", "e_xT",
-                     "e_flags", "lay_eptr", "g_chunk_ptr", "g_chunk_lm", "g_u", "g_x", "g_xT", "g_lm_cptr", "t_u", "t_lrow",
+                     "e_flags", "lay_eptr", "sp_chunk_blk", "g_chunk_ptr", "g_chunk_lm", "g_u", "g_x", "g_xT", "g_lm_cptr", "t_u", "t_lrow",
                      "t_col", "t_x", "rep", "r_ptr", "r_m", "r_val", "c_ptr", "c_tie"):
             setattr(c, name, ptr(P.t[name]) if name in P.t else self._dummy.data_ptr())
         for name in ("u_logpr", "alpha_theta", "beta_theta", "alpha_lambda", "beta_lambda", "gamma_shp", "gamma_rte",
@@ -127,7 +141,9 @@ class CaviEngine:
         csr, ego = P.r_mode == 2, P.r_mode == 0
         fast = (P.K <= 4 and store and not csr and (P.N * P.K) % 4 == 0 and P.N >= P.tile_w
                 and P.tile_h <= 128)
-        n = 2 + 3 + 1 + (0 if csr else 1) + 1 + (1 if fast else 0) + 1 + (1 if ego else 0) + 1 + 1 + 1
+        nch = self.ctx.n_chunks if self.ctx.n_chunks else 1  # special / dense are launched once per row chunk
+        n_special = sum(1 for q in range(nch) if self.P.sp_grid[q] > 0) if self.ctx.n_chunks else 1
+        n = 2 + 3 + 1 + (0 if csr else 1) + n_special + nch * ((1 if fast else 0) + 1) + (1 if ego else 0) + 1 + 1 + 1
         if elbo:
             n += 1 + (1 if self.mutuality else 0)
         return n

@@ -418,11 +418,19 @@ __device__ __forceinline__ void vm_fix_accumulate(unsigned long long* fix_l, boo
 #define VM_SPECIAL_MINBLK 3
 #endif
 template <int K, bool ELBO, int RMODE>
-__global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) : 2)) k_special(const __grid_constant__ vm_ctx c, double* part) {
+__global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) : 2)) k_special(const __grid_constant__ vm_ctx c, double* part, int chunk) {
   __shared__ double s_Gl[K], s_Ell[K], s_El[K];
   const int l = blockIdx.y;
   const int nloc = (int)c.nloc, nct = (int)c.nct, N = (int)c.N, M = (int)c.M, row0 = (int)c.row0;
   const int u0 = c.utile_ptr[(int64_t)l * nloc * nct], u1 = c.utile_ptr[(int64_t)(l + 1) * nloc * nct];
+  // block index within the layer (chunked launches cover a sub-range of the layer's blocks)
+  int blk = blockIdx.x;
+  if (chunk >= 0) {
+    const int64_t b0 = c.sp_chunk_blk[(int64_t)l * (VM_NCHUNK + 1) + chunk];
+    const int64_t b1 = c.sp_chunk_blk[(int64_t)l * (VM_NCHUNK + 1) + chunk + 1];
+    blk += (int)b0;
+    if (blk >= b1) return;
+  }
   constexpr bool elbo = ELBO;
   constexpr bool COOP = (RMODE != VM_R_EGO);
   const bool mut = c.mutuality != 0;
@@ -451,7 +459,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
   for (int k = 0; k < K; ++k) dsum[k] = 0.0;
 
   constexpr int TPT = VM_SPECIAL_TIES_PER_BLOCK / 256;
-  const int ub = u0 + blockIdx.x * VM_SPECIAL_TIES_PER_BLOCK + threadIdx.x;
+  const int ub = u0 + blk * VM_SPECIAL_TIES_PER_BLOCK + threadIdx.x;
   // per-tie data of the first tie (incl. its first X entry, stored inline); the next tie's is fetched while the
   // current one is processed, so only ONE dependent gather level (tables indexed by node / reporter) is exposed
   int n_lrow = 0, n_col = 0, n_m0 = 0, n_cnt = 0;
@@ -648,7 +656,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
     if (RMODE == VM_R_EGO) vm_fix_accumulate<K>(fix_l, ego_diag, valid, lrow, i, j, ti, tj, o_dk, o_resid);
   }
   // per-WARP partials (no block barrier: a warp retires as soon as its own ties are done)
-  const int64_t nup = c.L * c.n_ublk * 8, b = ((int64_t)l * c.n_ublk + blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int64_t nup = c.L * c.n_ublk * 8, b = ((int64_t)l * c.n_ublk + blk) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   double v;
   v = warp_sum(nu_acc);
@@ -771,7 +779,7 @@ __device__ __forceinline__ void dense_quad(const float (*a)[K], const bool* vali
 
 // Generic dense kernel: any mask structure, ELBO partials, dead-row bookkeeping, partial tiles.
 template <int K, bool ELBO, bool STORE, bool CSR>
-__global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constant__ vm_ctx c, double* catpart, int skip_fast) {
+__global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constant__ vm_ctx c, double* catpart, int skip_fast, int rt0, int rtn) {
   constexpr int NCH = DenseCfg<K>::NCH, TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32;
   __shared__ __align__(16) float qs[K][TW];      // column terms of the tile (row 0: weight of k=0, dead check only)
   __shared__ __align__(16) float colbuf[K][TW];  // cross-warp column sums (row 0: dead counts)
@@ -779,7 +787,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constan
   __shared__ double sm_red[8];
   const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
   const int ct = blockIdx.x;
-  const int l = blockIdx.y / nrt, rt = blockIdx.y - l * nrt;
+  const int l = blockIdx.y / rtn, rt = rt0 + (blockIdx.y - l * rtn);  // row tiles [rt0, rt0+rtn) of every layer
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (skip_fast && vm_fast_tile<K>(c, l, ct)) return;  // k_dense_fast has written this tile
   const int jt = ct * TW;
@@ -923,7 +931,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constan
   }
   if (ELBO) {
     const double v = block_sum<VM_DENSE_THREADS>(cat, sm_red);
-    if (tid == 0) catpart[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
+    if (tid == 0) catpart[((int64_t)l * nrt + rt) * nct + ct] = v;
   }
 }
 
@@ -946,7 +954,7 @@ struct FastCfg {
 #define VM_FAST_MINBLK2 4
 #endif
 template <int K, bool ELBO>
-__global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_MINBLK2 : 2) k_dense_fast(const __grid_constant__ vm_ctx c, double* catpart) {
+__global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_MINBLK2 : 2) k_dense_fast(const __grid_constant__ vm_ctx c, double* catpart, int rt0, int rtn) {
   constexpr int NCH = DenseCfg<K>::NCH, TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32, CAPW = FastCfg<K>::CAPW;
   __shared__ __align__(16) float qs[K - 1][TW];
   __shared__ __align__(16) float colbuf[K - 1][TW];
@@ -958,7 +966,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
   __shared__ double sm_red[8];
   const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
   const int ct = blockIdx.x;
-  const int l = blockIdx.y / nrt, rt = blockIdx.y - l * nrt;
+  const int l = blockIdx.y / rtn, rt = rt0 + (blockIdx.y - l * rtn);  // row tiles [rt0, rt0+rtn) of every layer
   if (!vm_fast_tile<K>(c, l, ct)) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int jt = ct * TW;
@@ -1119,7 +1127,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
   }
   if (ELBO) {
     const double v = block_sum<VM_DENSE_THREADS>(cat, sm_red);
-    if (tid == 0) catpart[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
+    if (tid == 0) catpart[((int64_t)l * nrt + rt) * nct + ct] = v;
   }
 }
 
@@ -1515,17 +1523,18 @@ static int check_ctx(const vm_ctx* c) {
   }
 
 template <int K>
-static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st) {
-  const dim3 grid((unsigned)c->nct, (unsigned)(c->L * c->nrt));
+static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, int rtn) {
+  if (rtn <= 0) return 0;
+  const dim3 grid((unsigned)c->nct, (unsigned)(c->L * rtn));
   const bool elbo = flags & VM_F_ELBO, store = !(flags & VM_F_NO_STORE), csr = c->r_mode == VM_R_CSR;
   double* cp = region_cat(c);
   const bool fast = K <= 4 && store && !csr && ((c->N * K) & 3) == 0 && c->N >= c->tile_w &&
                     c->tile_h <= VM_FAST_MAX_TILE_H;
   if (fast) {
-    if (elbo) k_dense_fast<(K <= 4 ? K : 2), true><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp);
-    else k_dense_fast<(K <= 4 ? K : 2), false><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp);
+    if (elbo) k_dense_fast<(K <= 4 ? K : 2), true><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, rt0, rtn);
+    else k_dense_fast<(K <= 4 ? K : 2), false><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, rt0, rtn);
   }
-#define LD(E, S, C) k_dense<K, E, S, C><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, fast ? 1 : 0)
+#define LD(E, S, C) k_dense<K, E, S, C><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, fast ? 1 : 0, rt0, rtn)
   if (csr) {
     if (!store) return VM_ENOTSUP;  // the general-mask statistics gather the slab
     if (elbo) LD(true, true, true); else LD(false, true, true);
@@ -1539,10 +1548,11 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st) {
 }
 
 template <int K>
-static int launch_special(const vm_ctx* c, int flags, cudaStream_t st) {
-  const dim3 grid((unsigned)c->n_ublk, (unsigned)c->L);
+static int launch_special(const vm_ctx* c, int flags, cudaStream_t st, int chunk, int64_t gridx) {
+  if (gridx <= 0) return 0;
+  const dim3 grid((unsigned)gridx, (unsigned)c->L);
   const bool elbo = flags & VM_F_ELBO;
-#define LS(E, M) k_special<K, E, M><<<grid, 256, 0, st>>>(*c, region_u(c))
+#define LS(E, M) k_special<K, E, M><<<grid, 256, 0, st>>>(*c, region_u(c), chunk)
   if (c->r_mode == VM_R_EGO) {
     if (elbo) LS(true, VM_R_EGO); else LS(false, VM_R_EGO);
   } else if (c->r_mode == VM_R_ALL) {
@@ -1552,6 +1562,43 @@ static int launch_special(const vm_ctx* c, int flags, cudaStream_t st) {
   }
 #undef LS
   return 0;
+}
+
+// special-tie kernel + dense kernel of one rho update.  With an aux stream and row chunks, special-tie chunk c+1
+// (latency / issue bound) runs on the aux stream while the dense kernel (HBM-write bound) of chunk c runs on the main one.
+template <int K>
+static int launch_rho_kernels(const vm_ctx* c, int flags, cudaStream_t st) {
+  int rc;
+  cudaStream_t aux = (cudaStream_t)c->aux_stream;
+  if (c->n_chunks != VM_NCHUNK || aux == nullptr || aux == st) {
+    if ((rc = launch_special<K>(c, flags, st, -1, c->n_ublk))) return rc;
+    return launch_dense<K>(c, flags, st, 0, (int)c->nrt);
+  }
+  const int64_t rt_end[VM_NCHUNK] = {c->rt_end0, c->rt_end1, c->rt_end2, c->rt_end3};
+  const int64_t sp_grid[VM_NCHUNK] = {c->sp_grid0, c->sp_grid1, c->sp_grid2, c->sp_grid3};
+  cudaEvent_t ev_fork, ev[VM_NCHUNK];
+  cudaError_t e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+  if (e != cudaSuccess) return (int)e;
+  for (int q = 0; q < VM_NCHUNK; ++q) {
+    e = cudaEventCreateWithFlags(&ev[q], cudaEventDisableTiming);
+    if (e != cudaSuccess) return (int)e;
+  }
+  cudaEventRecord(ev_fork, st);
+  cudaStreamWaitEvent(aux, ev_fork, 0);
+  rc = 0;
+  for (int q = 0; q < VM_NCHUNK && !rc; ++q) {
+    rc = launch_special<K>(c, flags, aux, q, sp_grid[q]);
+    cudaEventRecord(ev[q], aux);
+  }
+  for (int q = 0; q < VM_NCHUNK; ++q) {
+    cudaStreamWaitEvent(st, ev[q], 0);  // after the last one the aux stream has joined
+    if (rc) continue;
+    const int rt0 = q == 0 ? 0 : (int)rt_end[q - 1];
+    rc = launch_dense<K>(c, flags, st, rt0, (int)rt_end[q] - rt0);
+  }
+  cudaEventDestroy(ev_fork);  // destruction is deferred by the runtime until the events have completed
+  for (int q = 0; q < VM_NCHUNK; ++q) cudaEventDestroy(ev[q]);
+  return rc;
 }
 
 template <int K>
@@ -1654,9 +1701,7 @@ static int tu_phase_rho(const vm_ctx* c, int flags, void* stream) {
     DISPATCH_K(c->K, (k_tables<K><<<(unsigned)cdiv(c->L * c->N, 256), 256, 0, st>>>(*c)));
     VM_CHECK_LAUNCH();
   }
-  DISPATCH_K(c->K, launch_special<K>(c, flags, st));
-  VM_CHECK_LAUNCH();
-  DISPATCH_K(c->K, rc = launch_dense<K>(c, flags, st));
+  DISPATCH_K(c->K, rc = launch_rho_kernels<K>(c, flags, st));
   if (rc) return rc;
   VM_CHECK_LAUNCH();
   DISPATCH_K(c->K, launch_stats<K>(c, 0, st));
@@ -1674,7 +1719,7 @@ static int tu_phase_rho(const vm_ctx* c, int flags, void* stream) {
 static int tu_dense_only(const vm_ctx* c, int flags, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
-  DISPATCH_K(c->K, rc = launch_dense<K>(c, flags, (cudaStream_t)stream));
+  DISPATCH_K(c->K, rc = launch_dense<K>(c, flags, (cudaStream_t)stream, 0, (int)c->nrt));
   if (rc) return rc;
   VM_CHECK_LAUNCH();
   return 0;
