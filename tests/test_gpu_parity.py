@@ -41,7 +41,7 @@ def build_inputs(g, structured=False):
     return X, R
 
 
-def make_engine(g, row0=0, nloc=None, structured=True, tile_h=64):
+def make_engine(g, row0=0, nloc=None, structured=True, tile_h=64, overlap=None):
     torch = _cuda()
     import vimure_b200 as vm
     from vimure_b200 import _packing
@@ -51,7 +51,7 @@ def make_engine(g, row0=0, nloc=None, structured=True, tile_h=64):
     mask = vm.masks.from_input(R, g.L, g.N, g.M)
     P = _packing.pack(g.X_subs, g.X_vals, g.L, g.N, g.M, g.K, mask, "cuda", row0=row0, nloc=nloc, tile_h=tile_h)
     eps = g.fit_kwargs.get("EPS", 1e-12)
-    eng = CaviEngine(P, g.priors(), mutuality=g.mutuality, eps=eps)
+    eng = CaviEngine(P, g.priors(), mutuality=g.mutuality, eps=eps, overlap=overlap)
     st = g.init_state()
     # prior of the special ties from the injected (l,i,j) -> values
     flat = P.t["u_gflat"].cpu().numpy()
@@ -209,3 +209,21 @@ def test_device_special_functions():
     torch.cuda.synchronize()
     np.testing.assert_allclose(dg.cpu().numpy(), sp.psi(x), rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(lg.cpu().numpy(), sp.gammaln(x), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["gm_l2_k3", "dense_reporting", "custom_mask"])
+def test_two_stream_overlap_option_is_equivalent(name):
+    """The optional special/dense overlap on two streams (row chunks) must give the same trajectory."""
+    g = Golden(name)
+    a, _ = make_engine(g, tile_h=8, overlap=False)
+    b, _ = make_engine(g, tile_h=8, overlap=True)
+    for it in range(4):
+        a.iterate(1, elbo_last=True)
+        b.iterate(1, elbo_last=True)
+        pa, pb = a.params(), b.params()
+        for k in ("gamma_shp", "gamma_rte", "phi_shp", "phi_rte", "nu_shp"):
+            np.testing.assert_array_equal(pa[k], pb[k])
+        assert a.elbo() == b.elbo()
+    import torch
+
+    assert torch.equal(a.rho_slab(), b.rho_slab())

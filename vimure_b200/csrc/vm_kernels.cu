@@ -1583,19 +1583,22 @@ static int launch_rho_kernels(const vm_ctx* c, int flags, cudaStream_t st) {
     e = cudaEventCreateWithFlags(&ev[q], cudaEventDisableTiming);
     if (e != cudaSuccess) return (int)e;
   }
-  cudaEventRecord(ev_fork, st);
-  cudaStreamWaitEvent(aux, ev_fork, 0);
+  // main stream: special-tie chunks back to back; aux stream (the caller gives it a HIGHER priority): dense chunk q as
+  // soon as special chunk q is done, so that dense CTAs take every slot that frees up and the special-tie kernel of the
+  // next chunk fills the rest
   rc = 0;
   for (int q = 0; q < VM_NCHUNK && !rc; ++q) {
-    rc = launch_special<K>(c, flags, aux, q, sp_grid[q]);
-    cudaEventRecord(ev[q], aux);
+    rc = launch_special<K>(c, flags, st, q, sp_grid[q]);
+    cudaEventRecord(ev[q], st);
   }
   for (int q = 0; q < VM_NCHUNK; ++q) {
-    cudaStreamWaitEvent(st, ev[q], 0);  // after the last one the aux stream has joined
+    cudaStreamWaitEvent(aux, ev[q], 0);
     if (rc) continue;
     const int rt0 = q == 0 ? 0 : (int)rt_end[q - 1];
-    rc = launch_dense<K>(c, flags, st, rt0, (int)rt_end[q] - rt0);
+    rc = launch_dense<K>(c, flags, aux, rt0, (int)rt_end[q] - rt0);
   }
+  cudaEventRecord(ev_fork, aux);
+  cudaStreamWaitEvent(st, ev_fork, 0);  // join
   cudaEventDestroy(ev_fork);  // destruction is deferred by the runtime until the events have completed
   for (int q = 0; q < VM_NCHUNK; ++q) cudaEventDestroy(ev[q]);
   return rc;
