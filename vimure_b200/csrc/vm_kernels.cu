@@ -347,7 +347,7 @@ __device__ __forceinline__ void vm_tie_logodds(const vm_ctx& c, int l, int64_t l
 template <int K>
 __device__ __forceinline__ void vm_entry_accumulate(bool mut, double x, double xT, double2 ge, double Gnu,
                                                     const double* s_Gl, const double* s_Ell, double* lw, double* Dz) {
-  if (mut) {
+  if (mut && xT != 0.0) {
     const double z2 = Gnu * xT;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -358,8 +358,13 @@ __device__ __forceinline__ void vm_entry_accumulate(bool mut, double x, double x
       Dz[k] += xi * z2;
     }
   } else {
+    // no reciprocal report (or no mutuality): z2 = 0, so dz1_k = x and dz2_k = 0 -- no division needed; with mutuality
+    // an underflowed z1_k = 0 makes the denominator 0 and the reference's rule (model.py:692) gives dz1_k = 0
 #pragma unroll
-    for (int k = 0; k < K; ++k) lw[k] += x * (ge.y + s_Ell[k]);
+    for (int k = 0; k < K; ++k) {
+      const bool zero = mut && (ge.x * s_Gl[k] == 0.0);
+      if (!zero) lw[k] += x * (ge.y + s_Ell[k]);
+    }
   }
 }
 
