@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VM_ABI_VERSION 9
+#define VM_ABI_VERSION 10
 
 /* reporter-mask structure (how R[l,i,j,m] is represented) */
 #define VM_R_EGO 0 /* reporter m == node m reports row m and column m (vimure synthetic.py:1184-1204, _io.py:229-242) */
@@ -115,12 +115,22 @@ typedef struct vm_ctx {
   const float* e_x;         /* [I] X[l,i,j,m] */
   const float* e_xT;        /* [I] X[l,j,i,m], pre-paired (replaces data_T_vals, model.py:152-161) */
   const uint8_t* e_flags;   /* [I] bit0: (l,i,j,m) is in R */
-  const int64_t* lay_eptr;  /* [L+1] entry range of each layer */
+  /* The gamma / phi passes only visit the entries WITH a reciprocal report (x^T > 0, "E1"): for the others the Poisson
+     allocation is dz1_k = x whatever the parameters, so their contribution is a pack-time constant (g0) for gamma and
+     sum_ties rho_k * u_x0sum for phi (accumulated by the special-tie kernel into phi0).  I1 = number of E1 entries. */
+  int64_t I1;
+  const int32_t* f_u;       /* [I1] E1 entries sorted by tie: special-tie index, reporter, x, x^T */
+  const int32_t* f_m;
+  const float* f_x;
+  const float* f_xT;
+  const int64_t* lay_eptr;  /* [L+1] E1 entry range of each layer (phi pass) */
+  const double* g0;         /* [L*M] sum of x over the E0 entries of reporter (l,m) */
+  const float* u_x0sum;     /* [U] sum of x over the E0 entries of the special tie */
   const int64_t* g_chunk_ptr; /* [n_gchunk+1] ranges in reporter-sorted order */
   const int32_t* g_chunk_lm;  /* [n_gchunk] reporter id l*M+m */
-  const int32_t* g_u;         /* [I] reporter-sorted copies of e_u / e_x / e_xT (coalesced gamma pass) */
-  const float* g_x;           /* [I] */
-  const float* g_xT;          /* [I] */
+  const int32_t* g_u;         /* [I1] reporter-sorted E1 entries (coalesced gamma pass) */
+  const float* g_x;           /* [I1] */
+  const float* g_xT;          /* [I1] */
   const int64_t* g_lm_cptr;   /* [L*M+1] chunk range of each reporter */
 
   /* ---- transposed-position list (ELBO eta term) ---- */
@@ -171,6 +181,8 @@ typedef struct vm_ctx {
   double* er_node;          /* [L*N] EGO: E[theta] of node n acting as reporter (0 if not an active reporter) */
   double* colsum;           /* [L*M*K] column partials reduced over the row tiles */
   int64_t* dev_flags;       /* [8] [0]: a special tie underflowed completely in the last rho update */
+  int64_t* fixG;            /* [L*M] fixed-point correction of g0: -x of the E0 entries of special ties that underflowed */
+  double* phi0;             /* [L*K] sum over special ties of rho_k * u_x0sum (E0 part of the next phi-shape sums) */
   int64_t* fixA;            /* [L*M*K] EGO: per-reporter sums of (special - closed form), fixed point 2^-44, accumulated
                                with integer atomics (order-independent => bit-reproducible); slot k=0 holds only the
                                residual count (live special) - (live closed form) */

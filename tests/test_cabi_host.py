@@ -67,7 +67,7 @@ def test_mask_detection(name):
     assert np.array_equal(tr, rep_any[tuple(q[:3])])
 
 
-@pytest.mark.parametrize("name,world", [("f1_over", 1), ("karnataka_vil1", 1), ("gm_l2_k3", 3), ("custom_mask", 2)])
+@pytest.mark.parametrize("name,world", [("f1_over", 1), ("karnataka_vil1", 1), ("gm_l2_k3", 3), ("custom_mask", 2), ("nomut", 2)])
 def test_packing_invariants(name, world):
     import vimure_b200 as vm
     from vimure_b200 import _packing
@@ -86,7 +86,8 @@ def test_packing_invariants(name, world):
     tot_I, tot_IT = 0, 0
     for r in range(world):
         row0, nloc = shard_rows(g.N, world, r)
-        P = _packing.pack(g.X_subs, g.X_vals, g.L, g.N, g.M, g.K, mask, "cpu", row0=row0, nloc=nloc, tile_h=16)
+        P = _packing.pack(g.X_subs, g.X_vals, g.L, g.N, g.M, g.K, mask, "cpu", row0=row0, nloc=nloc, tile_h=16,
+                          mutuality=g.mutuality)
         t = {k: v.numpy() for k, v in P.t.items()}
         tot_I += P.I
         tot_IT += P.IT
@@ -105,13 +106,32 @@ def test_packing_invariants(name, world):
         assert np.all(np.diff(key) > 0)
         tp = t["utile_ptr"]
         assert tp[0] == 0 and tp[-1] == P.U and np.all(np.diff(tp) >= 0)
-        # reporter chunks partition the entries by reporter
-        gp, cp, clm = t["g_perm"], t["g_chunk_ptr"], t["g_chunk_lm"]
-        assert sorted(gp.tolist()) == list(range(P.I))
+        # E1 = entries with a reciprocal report (the only ones the gamma / phi passes visit); E0 = the rest
+        e1 = t["e1_idx"]
+        is1 = np.zeros(P.I, dtype=bool)
+        is1[e1] = True
+        assert np.array_equal(is1, (t["e_xT"] != 0) if g.mutuality else np.zeros(P.I, dtype=bool))
+        assert P.I1 == int(is1.sum())
+        assert np.array_equal(t["f_u"], eu[e1]) and np.array_equal(t["f_x"], t["e_x"][e1])
         lm_of_entry = l * g.M + t["e_m"]
+        g0_ref = np.zeros(g.L * g.M)
+        np.add.at(g0_ref, lm_of_entry[~is1], t["e_x"][~is1].astype(np.float64))
+        np.testing.assert_allclose(t["g0"], g0_ref, rtol=0, atol=1e-9)
+        x0_ref = np.zeros(P.U)
+        np.add.at(x0_ref, eu[~is1], t["e_x"][~is1].astype(np.float64))
+        np.testing.assert_allclose(t["u_x0sum"], x0_ref, rtol=0, atol=1e-6)
+        # layer ranges of the E1 entries
+        lp = t["lay_eptr"]
+        assert lp[0] == 0 and lp[-1] == P.I1 and np.all(np.diff(lp) >= 0)
+        assert np.array_equal(np.repeat(np.arange(g.L), np.diff(lp)), l[e1])
+        # reporter chunks partition the E1 entries by reporter
+        gp, cp, clm = t["g_perm"], t["g_chunk_ptr"], t["g_chunk_lm"]
+        assert sorted(gp.tolist()) == list(range(P.I1))
+        lm1 = lm_of_entry[e1]
         for c in range(P.n_gchunk):
-            assert np.all(lm_of_entry[gp[cp[c]:cp[c + 1]]] == clm[c])
+            assert np.all(lm1[gp[cp[c]:cp[c + 1]]] == clm[c])
             assert 0 < cp[c + 1] - cp[c] <= _packing.GAMMA_CHUNK
+        assert np.array_equal(t["g_u"], t["f_u"][gp])
         # column grouping
         cperm, cptr = t["ucol_perm"], t["ucol_ptr"]
         ck = (t["u_lrow"] // nloc).astype(np.int64) * g.N + t["u_col"]

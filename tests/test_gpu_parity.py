@@ -49,7 +49,8 @@ def make_engine(g, row0=0, nloc=None, structured=True, tile_h=64, overlap=None):
 
     X, R = build_inputs(g, structured=structured)
     mask = vm.masks.from_input(R, g.L, g.N, g.M)
-    P = _packing.pack(g.X_subs, g.X_vals, g.L, g.N, g.M, g.K, mask, "cuda", row0=row0, nloc=nloc, tile_h=tile_h)
+    P = _packing.pack(g.X_subs, g.X_vals, g.L, g.N, g.M, g.K, mask, "cuda", row0=row0, nloc=nloc, tile_h=tile_h,
+                      mutuality=g.mutuality)
     eps = g.fit_kwargs.get("EPS", 1e-12)
     eng = CaviEngine(P, g.priors(), mutuality=g.mutuality, eps=eps, overlap=overlap)
     st = g.init_state()

@@ -24,7 +24,8 @@ def _engine_and_oracle(net, mask, spec, K, mutuality=True, seed=3, tile_h=64, ro
 
     L, N, M = net.X.shape[0], net.X.shape[1], net.X.shape[3]
     subs = np.stack(net.X.subs)
-    P = _packing.pack(subs, net.X.vals, L, N, M, K, mask, "cuda", row0=row0, nloc=nloc, tile_h=tile_h)
+    P = _packing.pack(subs, net.X.vals, L, N, M, K, mask, "cuda", row0=row0, nloc=nloc, tile_h=tile_h,
+                      mutuality=mutuality)
     eng = CaviEngine(P, PRIORS, mutuality=mutuality, eps=1e-12)
     prng = np.random.RandomState(seed)
     rs = prng.random_sample

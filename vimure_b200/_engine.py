@@ -35,6 +35,8 @@ class CaviEngine:
         if dev.type != "cuda":
             raise RuntimeError("packed data must live on a CUDA device")
         self.mutuality = bool(mutuality)
+        if self.mutuality and not getattr(P, "mutuality", True):
+            raise ValueError("the data were packed for mutuality=False (no entry visits the gamma/phi passes)")
         f64 = dict(dtype=torch.float64, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
 
@@ -71,9 +73,11 @@ class CaviEngine:
         self.colsum = z(L * M * K)
         self.dev_flags = torch.zeros(8, dtype=torch.int64, device=dev)
         self.fixA = torch.zeros(L * M * K, dtype=torch.int64, device=dev)
+        self.fixG = torch.zeros(L * M, dtype=torch.int64, device=dev)
+        self.phi0 = z(L * K)
         assert _packing_const() == self.C["VM_SPECIAL_TIES_PER_BLOCK"]
         n_blk = max(P.n_gchunk, L * P.n_phichunk * K,
-                    L * P.n_ublk * 8 * (3 + self.C["VM_MAX_K"]) + P.nct * L * P.nrt + 128 + 2 * 64) + 64
+                    L * P.n_ublk * 8 * (3 + 2 * K) + P.nct * L * P.nrt + 128 + 2 * 64) + 64
         self.blkpart = z(n_blk)
         self.red1, self.red2 = z(L * M), z(L * K)
         self.red3 = z(L * M * K + self.C["VM_R3_EXTRA"])
@@ -82,7 +86,7 @@ class CaviEngine:
 
         Ctx = _capi.ctx_class()
         c = self.ctx = Ctx()
-        for name in ("L", "N", "M", "K", "row0", "nloc", "U", "I", "IT", "tile_w", "tile_h", "nct", "nrt", "n_gchunk",
+        for name in ("L", "N", "M", "K", "row0", "nloc", "U", "I", "I1", "IT", "tile_w", "tile_h", "nct", "nrt", "n_gchunk",
                      "phi_chunk", "n_phichunk", "n_ublk", "r_mode", "ego_diag"):
             setattr(c, name, int(getattr(P, name)))
         c.mutuality = int(self.mutuality)
@@ -113,13 +117,13 @@ class CaviEngine:
             return t.data_ptr() if t.numel() else self._dummy.data_ptr()
 
         for name in ("u_lrow", "u_col", "u_ptr", "u_cnt", "u_m0", "u_x0", "u_xT0", "utile_ptr", "ucol_ptr", "ucol_perm", "e_u", "e_m", "e_x", "e_xT",
-                     "e_flags", "lay_eptr", "sp_chunk_blk", "g_chunk_ptr", "g_chunk_lm", "g_u", "g_x", "g_xT", "g_lm_cptr", "t_u", "t_lrow",
+                     "e_flags", "f_u", "f_m", "f_x", "f_xT", "lay_eptr", "g0", "u_x0sum", "sp_chunk_blk", "g_chunk_ptr", "g_chunk_lm", "g_u", "g_x", "g_xT", "g_lm_cptr", "t_u", "t_lrow",
                      "t_col", "t_x", "rep", "r_ptr", "r_m", "r_val", "c_ptr", "c_tie"):
             setattr(c, name, ptr(P.t[name]) if name in P.t else self._dummy.data_ptr())
         for name in ("u_logpr", "alpha_theta", "beta_theta", "alpha_lambda", "beta_lambda", "gamma_shp", "gamma_rte",
                      "phi_shp", "phi_rte", "nu", "G_theta", "E_theta", "Elog_theta", "G_lambda", "E_lambda",
                      "Elog_lambda", "GE_theta", "rho_u", "rho_u32", "delta_u", "rho", "layer_consts", "tab_p", "tab_q",
-                     "rowpart", "colpart", "er_node", "colsum", "dev_flags", "fixA", "blkpart", "red1", "red2", "red3",
+                     "rowpart", "colpart", "er_node", "colsum", "dev_flags", "fixA", "fixG", "phi0", "blkpart", "red1", "red2", "red3",
                      "elbo_out"):
             setattr(c, name, ptr(getattr(self, name)))
         c.A = self.red3.data_ptr()  # A aliases the (all-reduced) statistics vector

@@ -47,10 +47,13 @@ class Packed:
         raise AttributeError(k)
 
 
-def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64):
+def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64, mutuality=True, split_e0=True):
     """Build the packed layout.
 
     X_subs : (4, I) integer array-like (l, i, j, m);  X_vals : (I,) counts;  mask : masks.ReporterMask.
+    mutuality / split_e0 : the gamma and phi passes only visit the entries with a reciprocal report (x^T > 0); for the
+        others dz1_k = x, a constant (reference model.py:679-681, 693 with z2 = 0).  `split_e0=False` makes every entry
+        visited (needed when a prior is so small that exp(E[log theta]) can underflow to 0, where model.py:692 gives 0).
     """
     dev = torch.device(device)
     nloc = N - row0 if nloc is None else int(nloc)
@@ -61,6 +64,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64)
     P.nct = (N + TILE_W - 1) // TILE_W
     P.nrt = (nloc + P.tile_h - 1) // P.tile_h
     P.mask = mask
+    P.mutuality = bool(mutuality)
 
     def _up(a, small):
         """host array -> device int64/float64 tensor, moving as few bytes as possible over PCIe"""
@@ -182,19 +186,52 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64)
     P.sp_grid = [int(v) for v in (blk[:, 1:] - blk[:, :-1]).max(dim=0)[0].cpu()]
 
     # ---- layer ranges and reporter chunks of the entries
-    lay_eptr = torch.searchsorted(tk_sorted, torch.arange(L + 1, device=dev, dtype=torch.int64) * (nloc * N))
+    P.phi_chunk = PHI_CHUNK
+    e_l = tk_sorted // (nloc * N)
+    lm_all = e_l * M + xm[sel]
+    # E1 = entries the gamma / phi passes visit; E0 = the rest (constant Poisson allocation dz1 = x)
+    if not split_e0:
+        is1 = torch.ones(I, dtype=torch.bool, device=dev)
+    elif mutuality:
+        is1 = P.t["e_xT"] != 0
+    else:
+        is1 = torch.zeros(I, dtype=torch.bool, device=dev)
+    e1 = torch.nonzero(is1).flatten()
+    P.I1 = int(e1.numel())
+    P.t["e1_idx"] = e1
+    P.t["f_u"] = P.t["e_u"][e1].contiguous()
+    P.t["f_m"] = P.t["e_m"][e1].contiguous()
+    P.t["f_x"] = P.t["e_x"][e1].contiguous()
+    P.t["f_xT"] = P.t["e_xT"][e1].contiguous()
+    x64 = P.t["e_x"].to(torch.float64)
+    x0 = torch.where(is1, torch.zeros_like(x64), x64)
+    # per-reporter / per-tie sums of x over E0 (deterministic: sorted segments, no atomics)
+    g0 = torch.zeros(L * M, dtype=torch.float64, device=dev)
+    if I:
+        o_lm = torch.sort(lm_all, stable=True)[1]
+        cs = torch.cat([x0.new_zeros(1), torch.cumsum(x0[o_lm], 0)])
+        bnd = torch.searchsorted(lm_all[o_lm], torch.arange(L * M + 1, device=dev, dtype=torch.int64))
+        g0 = cs[bnd[1:]] - cs[bnd[:-1]]
+        cs_t = torch.cat([x0.new_zeros(1), torch.cumsum(x0, 0)])
+        x0sum = (cs_t[u_ptr[1:]] - cs_t[u_ptr[:-1]])
+    else:
+        x0sum = torch.zeros(U, dtype=torch.float64, device=dev)
+    P.t["g0"] = g0.contiguous()
+    P.t["u_x0sum"] = x0sum.to(torch.float32).contiguous()
+    # layer ranges of the E1 entries (phi pass)
+    lay_eptr = torch.searchsorted(e_l[e1].contiguous(), torch.arange(L + 1, device=dev, dtype=torch.int64))
     P.t["lay_eptr"] = lay_eptr.contiguous()
     n_lay = lay_eptr[1:] - lay_eptr[:-1]
-    P.phi_chunk = PHI_CHUNK
     P.n_phichunk = max(1, int((int(n_lay.max()) + PHI_CHUNK - 1) // PHI_CHUNK)) if L else 1
-    e_l = tk_sorted // (nloc * N)
-    lm = e_l * M + xm[sel]
+    # reporter-sorted E1 entries (gamma pass)
+    lm = lm_all[e1]
+    I1 = P.I1
     lm_sorted, gperm = torch.sort(lm, stable=True)
     P.t["g_perm"] = _i32(gperm)
-    P.t["g_u"] = P.t["e_u"][gperm].contiguous()
-    P.t["g_x"] = P.t["e_x"][gperm].contiguous()
-    P.t["g_xT"] = P.t["e_xT"][gperm].contiguous()
-    cnt = torch.bincount(lm, minlength=L * M) if I else torch.zeros(L * M, dtype=torch.int64, device=dev)
+    P.t["g_u"] = P.t["f_u"][gperm].contiguous()
+    P.t["g_x"] = P.t["f_x"][gperm].contiguous()
+    P.t["g_xT"] = P.t["f_xT"][gperm].contiguous()
+    cnt = torch.bincount(lm, minlength=L * M) if I1 else torch.zeros(L * M, dtype=torch.int64, device=dev)
     nch = (cnt + GAMMA_CHUNK - 1) // GAMMA_CHUNK
     cptr = torch.cat([nch.new_zeros(1), torch.cumsum(nch, 0)])
     P.t["g_lm_cptr"] = cptr.contiguous()
@@ -205,7 +242,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64)
     within = torch.arange(n_gchunk, device=dev, dtype=torch.int64) - cptr[chunk_lm]
     cstart = estart[chunk_lm] + within * GAMMA_CHUNK
     P.t["g_chunk_lm"] = _i32(chunk_lm)
-    P.t["g_chunk_ptr"] = torch.cat([cstart, cstart.new_tensor([I])]).contiguous()
+    P.t["g_chunk_ptr"] = torch.cat([cstart, cstart.new_tensor([I1])]).contiguous()
 
     # ---- transposed-position list for the eta part of the ELBO (model.py:1269-1290): the X entry (l,i,j,m)
     # is the "X_T" value of the mask entry (l,j,i,m); it belongs to the rank that owns row j

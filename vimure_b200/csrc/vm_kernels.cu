@@ -46,8 +46,9 @@ static bool vm_debug_sync() {
 #define UP_NU 0
 #define UP_CAT 1
 #define UP_T2 2
-#define UP_DELTA 3  // + k
-#define UP_SLOTS (3 + VM_MAX_K)
+#define UP_DELTA 3        // + k
+#define UP_P0(K) (3 + (K))  // + k: rho_k * u_x0sum (E0 part of the next phi-shape sums)
+#define UP_SLOTS(K) (3 + 2 * (K))
 
 // =====================================================================================================
 // phase gamma
@@ -107,7 +108,8 @@ __global__ void __launch_bounds__(256) k_gamma_reduce(const __grid_constant__ vm
   double s = 0.0;
   for (int64_t q = c.g_lm_cptr[lm] + lane; q < c.g_lm_cptr[lm + 1]; q += 32) s += part[q];
   s = warp_sum(s);
-  if (lane == 0) c.red1[lm] = s;
+  // + the entries without a reciprocal report: dz1 = x, so their share is sum x (minus the ties that underflowed)
+  if (lane == 0) c.red1[lm] = s + c.g0[lm] + (double)c.fixG[lm] * VM_FIX_INV;
 }
 
 // =====================================================================================================
@@ -163,10 +165,10 @@ __global__ void __launch_bounds__(256) k_phi_partial(const __grid_constant__ vm_
     for (int q = 0; q < 4; ++q) {
       const int64_t e = eb + 256 * q;
       const bool ok = e < s1;
-      u[q] = ok ? (int64_t)c.e_u[e] : 0;
-      m[q] = ok ? c.e_m[e] : 0;
-      x[q] = ok ? c.e_x[e] : 0.f;
-      xT[q] = ok ? c.e_xT[e] : 0.f;
+      u[q] = ok ? (int64_t)c.f_u[e] : 0;
+      m[q] = ok ? c.f_m[e] : 0;
+      x[q] = ok ? c.f_x[e] : 0.f;
+      xT[q] = ok ? c.f_xT[e] : 0.f;
     }
     double r[4][K], Gth[4];
 #pragma unroll
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(256) k_phi_reduce(const __grid_constant__ vm_c
     double v = 0.0;
     for (int64_t q = threadIdx.x; q < c.n_phichunk; q += 256) v += part[((int64_t)l * c.n_phichunk + q) * K + k];
     v = block_sum<256>(v, sm);
-    if (threadIdx.x == 0) c.red2[l * K + k] = v;
+    if (threadIdx.x == 0) c.red2[l * K + k] = v + c.phi0[l * K + k];  // + the E0 entries (from the last rho update)
   }
 }
 
@@ -233,6 +235,7 @@ __global__ void __launch_bounds__(256) k_phi_finish(const __grid_constant__ vm_c
   emax = block_max<256>(emax, sm);
   if (c.r_mode == VM_R_EGO)
     for (int64_t t = threadIdx.x; t < M * K; t += 256) c.fixA[(int64_t)l * M * K + t] = 0;
+  for (int64_t t = threadIdx.x; t < M; t += 256) c.fixG[(int64_t)l * M + t] = 0;  // consumed by k_gamma_reduce already
   if (threadIdx.x == 0) {
     if (l == 0) c.dev_flags[0] = 0;
     double El[K];
@@ -459,9 +462,9 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
   }
   __syncthreads();
   double nu_acc = 0.0, cat_acc = 0.0, t2_acc = 0.0;
-  double dsum[K];
+  double dsum[K], p0[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) dsum[k] = 0.0;
+  for (int k = 0; k < K; ++k) dsum[k] = p0[k] = 0.0;
 
   constexpr int TPT = VM_SPECIAL_TIES_PER_BLOCK / 256;
   const int ub = u0 + blk * VM_SPECIAL_TIES_PER_BLOCK + threadIdx.x;
@@ -598,6 +601,14 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
 #pragma unroll
         for (int k = 0; k < K; ++k) rho[k] = 0.0;
         c.dev_flags[0] = 1;  // benign race: every writer stores the same value
+        // its E0 entries no longer contribute x to the gamma-shape sums: take them out of the constant g0
+        if (cnt > 0) {
+          const int64_t ef = c.u_ptr[u];
+          for (int64_t e = ef; e < ef + cnt; ++e)
+            if (!mut || c.e_xT[e] == 0.f)
+              atomicAdd(reinterpret_cast<unsigned long long*>(c.fixG) + (int64_t)l * M + c.e_m[e],
+                        (unsigned long long)(-__double2ll_rn((double)c.e_x[e] * VM_FIX_SCALE)));
+        }
       } else if (K == 2) {
         // two categories: the larger weight is exp(0) = 1, only one exponential is needed
         const double e = exp(-fabs(lw[1] - lw[0]));
@@ -616,8 +627,14 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
 #pragma unroll
         for (int k = 0; k < K; ++k) rho[k] *= inv;
       }
+      {
+        const double x0s = (double)c.u_x0sum[u];
 #pragma unroll
-      for (int k = 0; k < K; ++k) nu_acc += Dz[k] * rho[k];  // sum_e sum_k dz2_k rho_k (model.py:822-825)
+        for (int k = 0; k < K; ++k) {
+          nu_acc += Dz[k] * rho[k];  // sum_e sum_k dz2_k rho_k (model.py:822-825)
+          p0[k] += rho[k] * x0s;     // E0 part of the next phi-shape sums (model.py:880-887 with dz1 = x)
+        }
+      }
       // closed-form value the dense kernel uses for this tie: subtract it again from the statistics
       float f[K], epsr;
       bool dead;
@@ -671,6 +688,11 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
     if (lane == 0) part[UP_CAT * nup + b] = v;
     v = warp_sum(t2_acc);
     if (lane == 0) part[UP_T2 * nup + b] = v;
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    v = warp_sum(p0[k]);
+    if (lane == 0) part[(UP_P0(K) + k) * nup + b] = v;
   }
   if (RMODE == VM_R_ALL) {  // the all-reporter statistics only need per-layer totals of delta
 #pragma unroll
@@ -1277,36 +1299,51 @@ __global__ void __launch_bounds__(256) k_stats_csc(const __grid_constant__ vm_ct
 
 // initial statistics (rho = pr_rho, model.py:602): delta = rho_u - onehot per special tie
 template <int K>
-__global__ void k_init_delta(const __grid_constant__ vm_ctx c) {
-  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = u < c.U;
-  double d[K];
+__global__ void __launch_bounds__(256) k_init_delta(const __grid_constant__ vm_ctx c, double* part) {
+  // same (layer, block, warp) decomposition as k_special, so that the partials land in the same slots
+  const int l = blockIdx.y;
+  const int nloc = (int)c.nloc, nct = (int)c.nct;
+  const int u0 = c.utile_ptr[(int64_t)l * nloc * nct], u1 = c.utile_ptr[(int64_t)(l + 1) * nloc * nct];
+  double p0[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) d[k] = 0.0;
-  int l = 0, i = 0, j = 0;
-  int64_t lrow = 0;
-  double ti = 0.0, tj = 0.0;
-  if (valid) {
+  for (int k = 0; k < K; ++k) p0[k] = 0.0;
+  for (int it = 0; it < VM_SPECIAL_TIES_PER_BLOCK / 256; ++it) {
+    const int u = u0 + blockIdx.x * VM_SPECIAL_TIES_PER_BLOCK + it * 256 + threadIdx.x;
+    const bool valid = u < u1;
+    double d[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const double r = c.rho_u[u * K + k];
-      d[k] = r - (k == 0 ? 1.0 : 0.0);
-      c.delta_u[u * K + k] = d[k];
-      c.rho_u32[u * K + k] = (float)r;
+    for (int k = 0; k < K; ++k) d[k] = 0.0;
+    int i = 0, j = 0, lrow = 0;
+    double ti = 0.0, tj = 0.0;
+    if (valid) {
+      const double x0s = (double)c.u_x0sum[u];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const double r = c.rho_u[(size_t)u * K + k];
+        d[k] = r - (k == 0 ? 1.0 : 0.0);
+        c.delta_u[(size_t)u * K + k] = d[k];
+        c.rho_u32[(size_t)u * K + k] = (float)r;
+        p0[k] += r * x0s;
+      }
+      if (c.r_mode == VM_R_EGO) {
+        lrow = c.u_lrow[u];
+        i = lrow - l * nloc + (int)c.row0;
+        j = c.u_col[u];
+        // activity flags from the mask itself (the caches may not be final yet)
+        ti = (i < (int)c.M && c.rep[(int64_t)l * c.M + i]) ? 1.0 : 0.0;
+        tj = (j < (int)c.M && c.rep[(int64_t)l * c.M + j]) ? 1.0 : 0.0;
+      }
     }
-    if (c.r_mode == VM_R_EGO) {
-      lrow = c.u_lrow[u];
-      l = (int)(lrow / c.nloc);
-      i = (int)(lrow - (int64_t)l * c.nloc) + (int)c.row0;
-      j = c.u_col[u];
-      // activity flags from the mask itself (the caches may not be final yet)
-      ti = (i < (int)c.M && c.rep[(int64_t)l * c.M + i]) ? 1.0 : 0.0;
-      tj = (j < (int)c.M && c.rep[(int64_t)l * c.M + j]) ? 1.0 : 0.0;
-    }
+    if (c.r_mode == VM_R_EGO)
+      vm_fix_accumulate<K>(reinterpret_cast<unsigned long long*>(c.fixA) + (int64_t)l * c.M * K, c.ego_diag != 0, valid,
+                           lrow, i, j, ti, tj, d, 0);
   }
-  if (c.r_mode == VM_R_EGO)
-    vm_fix_accumulate<K>(reinterpret_cast<unsigned long long*>(c.fixA) + (int64_t)l * c.M * K, c.ego_diag != 0, valid,
-                         (int)lrow, i, j, ti, tj, d, 0);
+  const int64_t nup = c.L * c.n_ublk * 8, b = ((int64_t)l * c.n_ublk + blockIdx.x) * 8 + (threadIdx.x >> 5);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double v = warp_sum(p0[k]);
+    if ((threadIdx.x & 31) == 0) part[(UP_P0(K) + k) * nup + b] = v;
+  }
 }
 // per-layer totals of delta_u, for the all-reporter initial statistics
 __global__ void __launch_bounds__(256) k_init_delta_all(const __grid_constant__ vm_ctx c, double* upart) {
@@ -1370,14 +1407,16 @@ __global__ void __launch_bounds__(1024) k_sums_reduce(const __grid_constant__ vm
                                                       const double* bpart, int64_t n_b) {
   __shared__ double sm[32];
   double nu = 0.0, cat = 0.0, t2 = 0.0, b = 0.0;
-  const bool elbo = flags & VM_F_ELBO;
-  for (int64_t q = threadIdx.x; q < n_upart; q += 1024) {
-    nu += upart[UP_NU * n_upart + q];
-    if (elbo) {
-      cat += upart[UP_CAT * n_upart + q];
-      t2 += upart[UP_T2 * n_upart + q];
+  const bool elbo = flags & VM_F_ELBO, init = flags & VM_F_INIT;
+  const int K = (int)c.K;
+  if (!init)
+    for (int64_t q = threadIdx.x; q < n_upart; q += 1024) {
+      nu += upart[UP_NU * n_upart + q];
+      if (elbo) {
+        cat += upart[UP_CAT * n_upart + q];
+        t2 += upart[UP_T2 * n_upart + q];
+      }
     }
-  }
   if (elbo) {
     for (int64_t q = threadIdx.x; q < n_cat; q += 1024) cat += catpart[q];
     for (int64_t q = threadIdx.x; q < n_b; q += 1024) b += bpart[q];
@@ -1393,6 +1432,15 @@ __global__ void __launch_bounds__(1024) k_sums_reduce(const __grid_constant__ vm
     ex[VM_R3_T2] = t2;
     ex[VM_R3_B] = elbo ? c.b_all - b : 0.0;
   }
+  // phi0[l,k] = sum over this rank's special ties of layer l of rho_k * u_x0sum (per-warp partials of k_special / k_init_delta)
+  const int64_t nwl = c.n_ublk * 8;
+  for (int l = 0; l < (int)c.L; ++l)
+    for (int k = 0; k < K; ++k) {
+      double v = 0.0;
+      for (int64_t q = threadIdx.x; q < nwl; q += 1024) v += upart[(UP_P0(K) + k) * n_upart + (int64_t)l * nwl + q];
+      v = block_sum<1024>(v, sm);
+      if (threadIdx.x == 0) c.phi0[l * K + k] = v;
+    }
 }
 
 // =====================================================================================================
@@ -1499,7 +1547,7 @@ static inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 // blkpart regions (doubles)
 static inline double* region_u(const vm_ctx* c) { return c->blkpart; }  // special-tie block partials
 static inline int64_t n_upart(const vm_ctx* c) { return c->L * c->n_ublk * 8; }  // one partial per warp
-static inline double* region_cat(const vm_ctx* c) { return c->blkpart + n_upart(c) * UP_SLOTS; }
+static inline double* region_cat(const vm_ctx* c) { return c->blkpart + n_upart(c) * UP_SLOTS(c->K); }
 static inline int64_t n_catpart(const vm_ctx* c) { return c->nct * c->L * c->nrt; }
 static inline double* region_b(const vm_ctx* c) { return region_cat(c) + n_catpart(c); }
 #define VM_B_BLOCKS 128
@@ -1653,10 +1701,10 @@ static int tu_init_stats(const vm_ctx* c, void* stream) {
     cudaMemsetAsync(c->fixA, 0, (size_t)(c->L * c->M * c->K) * sizeof(int64_t), st);
     VM_CHECK_LAUNCH();
   }
-  if (c->U > 0) {
-    DISPATCH_K(c->K, (k_init_delta<K><<<(unsigned)cdiv(c->U, 256), 256, 0, st>>>(*c)));
-    VM_CHECK_LAUNCH();
-  }
+  cudaMemsetAsync(c->fixG, 0, (size_t)(c->L * c->M) * sizeof(int64_t), st);
+  VM_CHECK_LAUNCH();
+  DISPATCH_K(c->K, (k_init_delta<K><<<dim3((unsigned)c->n_ublk, (unsigned)c->L), 256, 0, st>>>(*c, region_u(c))));
+  VM_CHECK_LAUNCH();
   if (c->r_mode == VM_R_ALL) {
     k_init_delta_all<<<dim3((unsigned)c->n_ublk, (unsigned)c->L), 256, 0, st>>>(*c, region_u(c));
     VM_CHECK_LAUNCH();
@@ -1667,8 +1715,8 @@ static int tu_init_stats(const vm_ctx* c, void* stream) {
   }
   DISPATCH_K(c->K, launch_stats<K>(c, 1, st));
   VM_CHECK_LAUNCH();
-  // zero the scalar sums
-  cudaMemsetAsync(c->red3 + c->L * c->M * c->K, 0, VM_R3_EXTRA * sizeof(double), st);
+  // scalar sums = 0, phi0 from the prior
+  k_sums_reduce<<<1, 1024, 0, st>>>(*c, VM_F_INIT, region_u(c), n_upart(c), nullptr, 0, nullptr, 0);
   VM_CHECK_LAUNCH();
   return 0;
 }

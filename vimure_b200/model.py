@@ -229,8 +229,13 @@ class VimureModel(TransformerMixin, BaseEstimator):
         self.timings = {"check_params": t_check}
         with torch.cuda.device(dev):
             t0 = time.time()
+            # entries without a reciprocal report have a parameter-free Poisson allocation (dz1 = x) unless a prior is so
+            # small that exp(E[log theta/lambda]) can underflow to exactly 0 (then model.py:692 applies): psi(0.01) ~ -100
+            split_e0 = (not self.mutuality) or (float(np.min(self.alpha_theta)) >= 0.01 and
+                                                float(np.min(self.alpha_lambda)) >= 0.01)
             self._packed = P = _packing.pack(self.X.subs, self.X.vals, self.L, self.N, self.M, self.K, self.R, dev,
-                                             row0=row0, nloc=nloc, tile_h=int(extra_params.get("tile_h", 128)))
+                                             row0=row0, nloc=nloc, tile_h=int(extra_params.get("tile_h", 128)),
+                                             mutuality=self.mutuality, split_e0=split_e0)
             if self.undirected:  # model.py:127-132: X must be symmetric in (i, j)
                 if not bool(torch.all(P.t["e_xT"] == P.t["e_x"])):
                     msg = "If undirected is True, the given network has to be symmetric wrt l and m!"
