@@ -77,7 +77,7 @@ class CaviEngine:
         self.phi0 = z(L * K)
         assert _packing_const() == self.C["VM_SPECIAL_TIES_PER_BLOCK"]
         n_blk = max(P.n_gchunk, L * P.n_phichunk * K,
-                    L * P.n_ublk * 8 * (3 + 2 * K) + P.nct * L * P.nrt + 128 + 2 * 64) + 64
+                    L * P.n_ublk * 8 * (3 + 2 * K) + P.nct * L * P.nrt + 128 + 2 * 64 + L * 64 * (3 + K)) + 64
         self.blkpart = z(n_blk)
         self.red1, self.red2 = z(L * M), z(L * K)
         self.red3 = z(L * M * K + self.C["VM_R3_EXTRA"])
@@ -149,7 +149,7 @@ class CaviEngine:
                 and P.tile_h <= 128)
         nch = self.ctx.n_chunks if self.ctx.n_chunks else 1  # special / dense are launched once per row chunk
         n_special = sum(1 for q in range(nch) if self.P.sp_grid[q] > 0) if self.ctx.n_chunks else 1
-        n = 2 + 3 + 1 + (0 if csr else 1) + n_special + nch * ((1 if fast else 0) + 1) + (1 if ego else 0) + 1 + 1 + 1
+        n = 2 + 3 + 1 + (0 if csr else 1) + n_special + nch * ((1 if fast else 0) + 1) + (1 if ego else 0) + 1 + 2 + 1
         if elbo:
             n += 1 + (1 if self.mutuality else 0)
         return n

@@ -1401,30 +1401,51 @@ __global__ void __launch_bounds__(256) k_elbo_b(const __grid_constant__ vm_ctx c
   if (threadIdx.x == 0) part[blockIdx.x] = v;
 }
 
-// second pass over the scalar partials: nu, cat, t2 (special-tie blocks), cat (dense blocks), B
-__global__ void __launch_bounds__(1024) k_sums_reduce(const __grid_constant__ vm_ctx c, int flags, const double* upart,
-                                                      int64_t n_upart, const double* catpart, int64_t n_cat,
-                                                      const double* bpart, int64_t n_b) {
-  __shared__ double sm[32];
-  double nu = 0.0, cat = 0.0, t2 = 0.0, b = 0.0;
+// second pass over the scalar partials, in two stages (one block cannot stream the ~1e5 per-warp partials fast enough):
+// stage 1: grid (VM_S1_BLOCKS, L), block (bx, l) reduces its slice of layer l's per-warp partials of k_special /
+// k_init_delta: nu, cat, t2 and p0[k] -> s1[((l*VM_S1_BLOCKS + bx)*(3+K)) + slot]
+#define VM_S1_BLOCKS 64
+__global__ void __launch_bounds__(256) k_sums_stage1(const __grid_constant__ vm_ctx c, int flags, const double* upart,
+                                                     double* s1) {
+  __shared__ double sm[8];
+  const int l = blockIdx.y, K = (int)c.K;
   const bool elbo = flags & VM_F_ELBO, init = flags & VM_F_INIT;
-  const int K = (int)c.K;
-  if (!init)
-    for (int64_t q = threadIdx.x; q < n_upart; q += 1024) {
-      nu += upart[UP_NU * n_upart + q];
-      if (elbo) {
-        cat += upart[UP_CAT * n_upart + q];
-        t2 += upart[UP_T2 * n_upart + q];
-      }
-    }
-  if (elbo) {
-    for (int64_t q = threadIdx.x; q < n_cat; q += 1024) cat += catpart[q];
-    for (int64_t q = threadIdx.x; q < n_b; q += 1024) b += bpart[q];
+  const int64_t nwl = c.n_ublk * 8, nup = c.L * nwl;
+  const int64_t per = (nwl + VM_S1_BLOCKS - 1) / VM_S1_BLOCKS;
+  const int64_t q0 = (int64_t)l * nwl + (int64_t)blockIdx.x * per, q1 = min(q0 + per, (int64_t)(l + 1) * nwl);
+  double* out = s1 + ((int64_t)l * VM_S1_BLOCKS + blockIdx.x) * (3 + K);
+  for (int slot = 0; slot < 3 + K; ++slot) {
+    const bool used = slot >= 3 ? true : (init ? false : (slot == UP_NU ? true : elbo));
+    const int64_t src = slot >= 3 ? (UP_P0(K) + (slot - 3)) : slot;
+    double v = 0.0;
+    if (used)
+      for (int64_t q = q0 + threadIdx.x; q < q1; q += 256) v += upart[src * nup + q];
+    v = block_sum<256>(v, sm);
+    if (threadIdx.x == 0) out[slot] = v;
   }
-  nu = block_sum<1024>(nu, sm);
-  cat = block_sum<1024>(cat, sm);
-  t2 = block_sum<1024>(t2, sm);
-  b = block_sum<1024>(b, sm);
+}
+
+// stage 2: nu, cat, t2 (special-tie partials), cat (dense blocks), B, and phi0[l,k]
+__global__ void __launch_bounds__(256) k_sums_reduce(const __grid_constant__ vm_ctx c, int flags, const double* s1,
+                                                     const double* catpart, int64_t n_cat, const double* bpart,
+                                                     int64_t n_b) {
+  __shared__ double sm[8];
+  const int K = (int)c.K, L = (int)c.L;
+  const bool elbo = flags & VM_F_ELBO;
+  double acc[3] = {0.0, 0.0, 0.0}, b = 0.0;
+  for (int t = threadIdx.x; t < L * VM_S1_BLOCKS; t += 256) {
+    acc[0] += s1[(int64_t)t * (3 + K) + UP_NU];
+    acc[1] += s1[(int64_t)t * (3 + K) + UP_CAT];
+    acc[2] += s1[(int64_t)t * (3 + K) + UP_T2];
+  }
+  if (elbo) {
+    for (int64_t q = threadIdx.x; q < n_cat; q += 256) acc[1] += catpart[q];
+    for (int64_t q = threadIdx.x; q < n_b; q += 256) b += bpart[q];
+  }
+  const double nu = block_sum<256>(acc[0], sm);
+  const double cat = block_sum<256>(acc[1], sm);
+  const double t2 = block_sum<256>(acc[2], sm);
+  b = block_sum<256>(b, sm);
   if (threadIdx.x == 0) {
     double* ex = c.red3 + c.L * c.M * c.K;
     ex[VM_R3_NU] = nu;
@@ -1432,13 +1453,11 @@ __global__ void __launch_bounds__(1024) k_sums_reduce(const __grid_constant__ vm
     ex[VM_R3_T2] = t2;
     ex[VM_R3_B] = elbo ? c.b_all - b : 0.0;
   }
-  // phi0[l,k] = sum over this rank's special ties of layer l of rho_k * u_x0sum (per-warp partials of k_special / k_init_delta)
-  const int64_t nwl = c.n_ublk * 8;
-  for (int l = 0; l < (int)c.L; ++l)
+  // phi0[l,k] = sum over this rank's special ties of layer l of rho_k * u_x0sum
+  for (int l = 0; l < L; ++l)
     for (int k = 0; k < K; ++k) {
-      double v = 0.0;
-      for (int64_t q = threadIdx.x; q < nwl; q += 1024) v += upart[(UP_P0(K) + k) * n_upart + (int64_t)l * nwl + q];
-      v = block_sum<1024>(v, sm);
+      double v = (threadIdx.x < VM_S1_BLOCKS) ? s1[((int64_t)l * VM_S1_BLOCKS + threadIdx.x) * (3 + K) + 3 + k] : 0.0;
+      v = block_sum<256>(v, sm);
       if (threadIdx.x == 0) c.phi0[l * K + k] = v;
     }
 }
@@ -1552,6 +1571,7 @@ static inline int64_t n_catpart(const vm_ctx* c) { return c->nct * c->L * c->nrt
 static inline double* region_b(const vm_ctx* c) { return region_cat(c) + n_catpart(c); }
 #define VM_B_BLOCKS 128
 static inline double* region_ep(const vm_ctx* c) { return region_b(c) + VM_B_BLOCKS; }
+static inline double* region_s1(const vm_ctx* c) { return region_ep(c) + 2 * VM_EP_BLOCKS; }  // L*VM_S1_BLOCKS*(3+K)
 
 static int check_ctx(const vm_ctx* c) {
   if (!c) return VM_EINVAL;
@@ -1716,7 +1736,9 @@ static int tu_init_stats(const vm_ctx* c, void* stream) {
   DISPATCH_K(c->K, launch_stats<K>(c, 1, st));
   VM_CHECK_LAUNCH();
   // scalar sums = 0, phi0 from the prior
-  k_sums_reduce<<<1, 1024, 0, st>>>(*c, VM_F_INIT, region_u(c), n_upart(c), nullptr, 0, nullptr, 0);
+  k_sums_stage1<<<dim3(VM_S1_BLOCKS, (unsigned)c->L), 256, 0, st>>>(*c, VM_F_INIT, region_u(c), region_s1(c));
+  VM_CHECK_LAUNCH();
+  k_sums_reduce<<<1, 256, 0, st>>>(*c, VM_F_INIT, region_s1(c), nullptr, 0, nullptr, 0);
   VM_CHECK_LAUNCH();
   return 0;
 }
@@ -1766,7 +1788,9 @@ static int tu_phase_rho(const vm_ctx* c, int flags, void* stream) {
     DISPATCH_K(c->K, (k_elbo_b<K><<<VM_B_BLOCKS, 256, 0, st>>>(*c, region_b(c))));
     VM_CHECK_LAUNCH();
   }
-  k_sums_reduce<<<1, 1024, 0, st>>>(*c, flags, region_u(c), n_upart(c), region_cat(c), n_catpart(c), region_b(c),
+  k_sums_stage1<<<dim3(VM_S1_BLOCKS, (unsigned)c->L), 256, 0, st>>>(*c, flags, region_u(c), region_s1(c));
+  VM_CHECK_LAUNCH();
+  k_sums_reduce<<<1, 256, 0, st>>>(*c, flags, region_s1(c), region_cat(c), n_catpart(c), region_b(c),
                                    c->mutuality ? VM_B_BLOCKS : 0);
   VM_CHECK_LAUNCH();
   return 0;
