@@ -211,8 +211,8 @@ __global__ void __launch_bounds__(256) k_phi_reduce(const __grid_constant__ vm_c
 // `_update_phi` (model.py:729-749): phi_rte[l,k] = beta + sum_m E[theta_lm](new) A[l,m,k]; lambda part of the cache;
 // then the per-layer constants of the closed-form tie posterior.
 template <int K>
-__global__ void __launch_bounds__(256) k_phi_finish(const __grid_constant__ vm_ctx c) {
-  __shared__ double sm[8];
+__global__ void __launch_bounds__(1024) k_phi_finish(const __grid_constant__ vm_ctx c) {
+  __shared__ double sm[32];
   __shared__ double rte_s[K + 1];
   const int l = blockIdx.x;
   const int64_t M = c.M;
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) k_phi_finish(const __grid_constant__ vm_c
   double emax = 0.0;
 #pragma unroll
   for (int k = 0; k <= K; ++k) acc[k] = 0.0;
-  for (int64_t m = threadIdx.x; m < M; m += 256) {
+  for (int64_t m = threadIdx.x; m < M; m += 1024) {
     const double et = c.E_theta[l * M + m];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] += et * c.A[(l * M + m) * K + k];
@@ -229,13 +229,13 @@ __global__ void __launch_bounds__(256) k_phi_finish(const __grid_constant__ vm_c
   }
 #pragma unroll
   for (int k = 0; k <= K; ++k) {
-    const double v = block_sum<256>(acc[k], sm);
+    const double v = block_sum<1024>(acc[k], sm);
     if (threadIdx.x == 0) rte_s[k] = v;
   }
-  emax = block_max<256>(emax, sm);
+  emax = block_max<1024>(emax, sm);
   if (c.r_mode == VM_R_EGO)
-    for (int64_t t = threadIdx.x; t < M * K; t += 256) c.fixA[(int64_t)l * M * K + t] = 0;
-  for (int64_t t = threadIdx.x; t < M; t += 256) c.fixG[(int64_t)l * M + t] = 0;  // consumed by k_gamma_reduce already
+    for (int64_t t = threadIdx.x; t < M * K; t += 1024) c.fixA[(int64_t)l * M * K + t] = 0;
+  for (int64_t t = threadIdx.x; t < M; t += 1024) c.fixG[(int64_t)l * M + t] = 0;  // consumed by k_gamma_reduce already
   if (threadIdx.x == 0) {
     if (l == 0) c.dev_flags[0] = 0;
     double El[K];
@@ -1773,7 +1773,7 @@ static int tu_phase_rho(const vm_ctx* c, int flags, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH_K(c->K, (k_phi_finish<K><<<(unsigned)c->L, 256, 0, st>>>(*c)));
+  DISPATCH_K(c->K, (k_phi_finish<K><<<(unsigned)c->L, 1024, 0, st>>>(*c)));
   VM_CHECK_LAUNCH();
   if (c->r_mode != VM_R_CSR) {
     DISPATCH_K(c->K, (k_tables<K><<<(unsigned)cdiv(c->L * c->N, 256), 256, 0, st>>>(*c)));
