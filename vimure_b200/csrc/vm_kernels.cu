@@ -471,7 +471,10 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
   // per-tie data of the first tie (incl. its first X entry, stored inline); the next tie's is fetched while the
   // current one is processed, so only ONE dependent gather level (tables indexed by node / reporter) is exposed
   int n_lrow = 0, n_col = 0, n_m0 = 0, n_cnt = 0;
-  float n_x0 = 0.f, n_xT0 = 0.f;
+  float n_x0 = 0.f, n_xT0 = 0.f, n_x0s = 0.f;
+  double n_logpr[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) n_logpr[k] = 0.0;
   if (ub < u1) {
     n_lrow = c.u_lrow[ub];
     n_col = c.u_col[ub];
@@ -479,6 +482,9 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
     n_m0 = c.u_m0[ub];
     n_x0 = c.u_x0[ub];
     n_xT0 = c.u_xT0[ub];
+    n_x0s = c.u_x0sum[ub];
+#pragma unroll
+    for (int k = 0; k < K; ++k) n_logpr[k] = c.u_logpr[(size_t)ub * K + k];
   }
 #pragma unroll 1
   for (int it = 0; it < TPT; ++it) {
@@ -487,7 +493,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
     // ---- stage A (per thread): tie data, S, prior; entries of SHORT ties
     int lrow = 0, i = 0, j = 0, cnt = 0;
     int64_t e0 = 0;
-    double ti = 0.0, tj = 0.0;
+    double ti = 0.0, tj = 0.0, x0s = 0.0;
     double lw[K], Dz[K], logpr[K];
     float a[K];
 #pragma unroll
@@ -501,6 +507,9 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
       cnt = n_cnt;
       const int m0 = n_m0;
       const float x0 = n_x0, xT0 = n_xT0;
+      x0s = (double)n_x0s;
+#pragma unroll
+      for (int k = 0; k < K; ++k) logpr[k] = n_logpr[k];
       const int un = u + 256;
       if (it + 1 < TPT && un < u1) {
         n_lrow = c.u_lrow[un];
@@ -509,14 +518,14 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
         n_m0 = c.u_m0[un];
         n_x0 = c.u_x0[un];
         n_xT0 = c.u_xT0[un];
+        n_x0s = c.u_x0sum[un];
+#pragma unroll
+        for (int k = 0; k < K; ++k) n_logpr[k] = c.u_logpr[(size_t)un * K + k];
       }
       i = lrow - l * nloc + row0;
       // the one dependent gather level: reporter cache of the first entry, prior, closed-form tables, S
       double2 ge0 = make_double2(0.0, 0.0);
       if (cnt > 0 && (!COOP || cnt <= VM_LONG_TIE)) ge0 = *reinterpret_cast<const double2*>(ge_l + 2 * m0);
-      const double* lp = c.u_logpr + (size_t)u * K;
-#pragma unroll
-      for (int k = 0; k < K; ++k) logpr[k] = lp[k];
       if (RMODE == VM_R_CSR) {
         vm_tie_logodds<K>(c, l, lrow, j, a);
       } else {
@@ -628,7 +637,6 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
         for (int k = 0; k < K; ++k) rho[k] *= inv;
       }
       {
-        const double x0s = (double)c.u_x0sum[u];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           nu_acc += Dz[k] * rho[k];  // sum_e sum_k dz2_k rho_k (model.py:822-825)
