@@ -247,6 +247,19 @@ def scenario_rho_prior(vm):
     save_fixture("rho_prior", gt.X, gt.R, 1, 30, 30, 3, model_kwargs, fit_kwargs, rec)
 
 
+def scenario_undirected(vm):
+    """undirected=True (model.py:58-65, 127-132, 477-478): symmetric dense X, mutuality forced off, symmetrised prior."""
+    gt = vm.synthetic.StandardSBM(N=30, M=30, L=1, K=2, C=2, avg_degree=4, sparsify=True, seed=17)
+    gt._build_X(mutuality=0.0, flag_self_reporter=True, seed=17)
+    Xd = gt.X.toarray()
+    Xs = np.maximum(Xd, np.transpose(Xd, axes=(0, 2, 1, 3)))
+    fit_kwargs = dict(K=2, seed=31, max_iter=12, R=gt.R)
+    model_kwargs = dict(undirected=True, convergence_tol=0.0)
+    rec = run_reference_trace(Xs, fit_kwargs, model_kwargs)
+    X = rec["model"].X
+    save_fixture("undirected", X, gt.R, 1, 30, 30, 2, model_kwargs, fit_kwargs, rec)
+
+
 SCENARIOS = {
     "f1_over": lambda vm: scenario_f1(vm, "over"),
     "f1_under": lambda vm: scenario_f1(vm, "under"),
@@ -257,6 +270,7 @@ SCENARIOS = {
     "custom_mask": scenario_custom_mask,
     "karnataka_vil1": scenario_karnataka,
     "rho_prior": scenario_rho_prior,
+    "undirected": scenario_undirected,
 }
 
 if __name__ == "__main__":

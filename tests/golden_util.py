@@ -6,7 +6,7 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ALL_FIXTURES = ["f1_over", "f1_under", "sbm_k3", "gm_l2_k3", "nomut", "dense_reporting", "custom_mask",
-                "karnataka_vil1", "rho_prior"]
+                "karnataka_vil1", "rho_prior", "undirected"]
 
 
 class Golden:
@@ -34,7 +34,7 @@ class Golden:
         elif kind == "coo":
             self.R_spec["subs"] = z["R_subs"].astype(np.int64)
             self.R_spec["vals"] = z["R_vals"]
-        self.mutuality = bool(self.model_kwargs.get("mutuality", True))
+        self.mutuality = bool(self.model_kwargs.get("mutuality", True)) and not self.model_kwargs.get("undirected", False)
         self.n_iter = len(z["it_elbo"])
 
     # priors as the reference resolves them (model.py:238-317)

@@ -228,3 +228,26 @@ def test_two_stream_overlap_option_is_equivalent(name):
     import torch
 
     assert torch.equal(a.rho_slab(), b.rho_slab())
+
+
+@pytest.mark.parametrize("name", ["undirected", "rho_prior", "nomut", "gm_l2_k3"])
+def test_fit_with_reference_seeded_init_reproduces_reference_trace(name):
+    """`init="reference"` consumes the reference's RNG stream (model.py:470-500, 570-592): a seeded fit reproduces the
+    reference's ELBO trace without any injected state -- incl. the symmetrised prior of undirected=True and a user rho_prior."""
+    _cuda()
+    import vimure_b200 as vm
+
+    g = Golden(name)
+    X, R = build_inputs(g)
+    model = vm.VimureModel(**g.model_kwargs)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model.fit(X, R=R, init="reference", **g.fit_kwargs)
+    ref = g.z["trace"]  # realisation, iter, elbo, reached
+    assert list(model.trace["iter"]) == [int(v) for v in ref[:, 1]]
+    np.testing.assert_allclose(model.trace["elbo"].to_numpy(), ref[:, 2], rtol=RTOL_ELBO)
+    np.testing.assert_allclose(model.maxL, float(g.z["maxL"]), rtol=RTOL_ELBO)
+    np.testing.assert_allclose(model.gamma_shp, g.z["it_gamma_shp"][-1], rtol=RTOL_PARAM)
+    np.testing.assert_allclose(model.pr_rho.reshape(-1, g.K)[
+        (g.z["init_pr_ties"][:, 0] * g.N + g.z["init_pr_ties"][:, 1]) * g.N + g.z["init_pr_ties"][:, 2]],
+        g.z["init_pr_vals"], rtol=1e-12)
