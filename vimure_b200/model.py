@@ -31,7 +31,7 @@ from sklearn.base import BaseEstimator, TransformerMixin
 from . import _packing, masks
 from ._engine import CaviEngine
 from ._log import setup_logging
-from .sptensor import dtensor, is_sparse_like, sptensor
+from .sptensor import is_sparse_like, sptensor
 from .utils import apply_rho_threshold, match_arg
 
 INF = 1e10
