@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tile-h", type=int, default=128)
+    ap.add_argument("--trace", action="store_true", help="print per-batch device times (rank 0, stderr)")
     ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5s"],
                     help="c3: StandardSBM ego N=20k L=1 K=2 (headline); c4: dense reporting N=8k M=64 L=2 K=2; "
                          "c5s: GMReciprocity ego L=4 K=3 at N=16k (config 5 scaled to one GPU)")
@@ -273,11 +274,20 @@ def run_ours(args):
             while not (nxt == 1 or nxt % 10 == 0 or nxt == total) and nxt < end:
                 nxt += 1
             is_elbo = (nxt == 1 or nxt % 10 == 0 or nxt == total)
+            if args.trace:
+                torch.cuda.synchronize(dev)
+                t_b = time.time()
             eng.iterate(nxt - it + 1, elbo_last=is_elbo)
+            if args.trace:
+                torch.cuda.synchronize(dev)
+                t_i = time.time()
             if is_elbo:
                 e = eng.elbo()  # the one D2H scalar of `_check_for_convergence`
                 if not np.isfinite(e):
                     raise RuntimeError("ELBO is not finite")
+            if args.trace and rank == 0:
+                print("trace: iters %d..%d elbo=%s  %.3f ms (+%.3f ms elbo readback)" %
+                      (it, nxt, is_elbo, (t_i - t_b) * 1e3, (time.time() - t_i) * 1e3), file=sys.stderr)
             it = nxt + 1
 
     def barrier():
