@@ -158,11 +158,13 @@ class ClockSampler:
 
     def __enter__(self):
         # ONE long-lived nvidia-smi sampling every 20 ms (spawning one per sample is too slow for a ~0.1 s region)
+        if self.index is None:
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            time.sleep(0.15)  # let it start emitting before the timed region opens
+            time.sleep(0.3)  # let it finish its NVML initialisation
         except Exception:
             self.proc = None
         return self
@@ -296,11 +298,14 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     total = args.warmup + args.steps
-    run_iters(1, args.warmup, total)
-    barrier()
-    n0 = eng.n_launch
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    # the clock sampler (one nvidia-smi process, rank 0 only) is started BEFORE the warm-up: its NVML initialisation
+    # takes driver locks for a few hundred ms and must not fall into the timed region
+    clk = ClockSampler(local if rank == 0 else None)
+    with clk:
+        run_iters(1, args.warmup, total)
+        barrier()
+        n0 = eng.n_launch
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         run_iters(args.warmup + 1, args.steps, total)
         ev1.record()
