@@ -242,6 +242,12 @@ int vm_materialize_prior(const vm_ctx* c, void* stream);
  * out[t] = argmax_k rho[t,k] (mode 0) or rho[t,1] >= threshold (mode 1), uint8, [L*nloc*N]. */
 int vm_infer(const vm_ctx* c, int mode, double threshold, uint8_t* out, void* stream);
 
+/* `sample_inferred_model` on the dense slab (model.py:1062-1096): out[t] = argmax_k of the counts of n_trials draws from
+ * Categorical(rho[t,:]) (numpy: multinomial(n_trials, rho).argmax(-1)), uint8, [L*nloc*N].  Counter-based RNG (Philox4x32-10)
+ * keyed by `seed` and the GLOBAL tie id: reproducible, independent of launch geometry and of the sharding.  The stream is
+ * not numpy's (the reference draws with numpy.random.default_rng(seed)). */
+int vm_sample(const vm_ctx* c, int64_t n_trials, uint64_t seed, uint8_t* out, void* stream);
+
 /* Special functions exposed for testing the device implementations against scipy. */
 int vm_test_special(const double* x, double* out_digamma, double* out_lgamma, int64_t n, void* stream);
 

@@ -150,3 +150,80 @@ def test_dataframe_input_equals_tensor_input():
     np.testing.assert_array_equal(a.gamma_shp, b.gamma_shp)
     np.testing.assert_array_equal(a.trace["elbo"].to_numpy(), b.trace["elbo"].to_numpy())
     check_final_parameters(a, net.L, net.N, net.N, 2)
+
+
+@pytest.mark.parametrize("name,kw", [("f1_over", {}), ("karnataka_vil1", {"convergence_tol": 0.1})])
+def test_concurrent_realisations_match_sequential(name, kw):
+    """The restarts of model.py:386-437 run side by side (one stream + one state per restart) must give exactly what
+    they give one after the other: same seeds, same trace, same best restart, same posteriors."""
+    _cuda()
+    import vimure_b200 as vm
+
+    g = Golden(name)
+    X, R = build_inputs(g)
+    fk = dict(g.fit_kwargs)
+    fk["num_realisations"] = 4
+    fk["max_iter"] = 35  # ELBO at 1, 10, 20, 30, 35: restarts may stop at different iterations
+    fits = {}
+    for conc in (False, True):
+        m = vm.VimureModel(mutuality=True, **kw)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m.fit(X, R=R, init="reference", concurrent_realisations=conc, **fk)
+        fits[conc] = m
+    a, b = fits[False], fits[True]
+    for col in ("realisation", "seed", "iter", "reached_convergence"):
+        assert list(a.trace[col]) == list(b.trace[col])
+    np.testing.assert_array_equal(a.trace["elbo"].to_numpy(), b.trace["elbo"].to_numpy())
+    assert a.maxL == b.maxL and a.seed == b.seed and a.n_iter_ == b.n_iter_
+    for nm in ("gamma_shp", "gamma_rte", "phi_shp", "phi_rte", "nu_shp", "gamma_shp_f", "gamma_rte_f", "phi_shp_f",
+               "phi_rte_f", "nu_shp_f", "G_exp_theta_f", "G_exp_lambda_f", "G_exp_nu_f"):
+        np.testing.assert_array_equal(np.asarray(getattr(a, nm)), np.asarray(getattr(b, nm)), err_msg=nm)
+    np.testing.assert_array_equal(a.rho, b.rho)
+    np.testing.assert_array_equal(a.rho_f, b.rho_f)
+    np.testing.assert_array_equal(a.pr_rho, b.pr_rho)
+    np.testing.assert_array_equal(a.get_inferred_model(), b.get_inferred_model())
+    np.testing.assert_array_equal(a.get_inferred_model(method="fixed_threshold", threshold=0.3),
+                                  b.get_inferred_model(method="fixed_threshold", threshold=0.3))
+    # and the default ("auto") takes the side-by-side path for a launch-bound problem like this one
+    m = vm.VimureModel(mutuality=True, **kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m.fit(X, R=R, init="reference", **fk)
+    assert m._engine_f is not None
+    np.testing.assert_array_equal(m.trace["elbo"].to_numpy(), a.trace["elbo"].to_numpy())
+
+
+def test_device_sampling_follows_rho(fitted):
+    """`sample_inferred_model(rng="device")` (vm_sample): reproducible, keyed by seed, and distributed like
+    multinomial(n, rho).argmax(-1) of reference model.py:1086-1088."""
+    net, models = fitted
+    m = models[True]
+    rho1 = m.rho_f[..., 1]
+    a = m.sample_inferred_model(N=3, seed=7, rng="device")
+    b = m.sample_inferred_model(N=3, seed=7, rng="device")
+    assert len(a) == 3 and all(x.shape == (1, 100, 100) and x.dtype.kind == "i" for x in a)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
+    assert (a[0] != a[1]).any()  # seed + i: different streams
+    np.testing.assert_array_equal(m.sample_inferred_model(N=2, seed=8, rng="device")[0],
+                                  m._engine_of_rho_f().sample(2, 8).cpu().numpy())
+    # one trial per tie: P(Y = 1) = rho_1; frequencies over 400 seeds within 6 sigma (+ slack)
+    eng = m._engine_of_rho_f()
+    n = 400
+    freq = np.zeros(rho1.shape)
+    for s in range(n):
+        freq += eng.sample(1, 1000 + s).cpu().numpy()
+    freq /= n
+    sigma = np.sqrt(np.maximum(rho1 * (1 - rho1), 1e-12) / n)
+    assert np.all(np.abs(freq - rho1) <= 6 * sigma + 5e-3), float(np.max(np.abs(freq - rho1) / (sigma + 1e-3)))
+    mid = (rho1 > 0.2) & (rho1 < 0.8)
+    if mid.any():  # and it does fluctuate where the posterior is undecided
+        assert np.abs(freq - rho1)[mid].max() > 0
+    # many trials: the most frequent category is the most probable one wherever the posterior is decided
+    big = eng.sample(2001, 5).cpu().numpy()
+    decided = np.abs(rho1 - 0.5) > 0.1
+    np.testing.assert_array_equal(big[decided], (rho1 > 0.5)[decided].astype(big.dtype))
+    # the numpy path still exists and agrees in law on the decided ties
+    host = m.sample_inferred_model(N=1, seed=7, rng="numpy")[0]
+    assert host.shape == (1, 100, 100)

@@ -72,13 +72,19 @@ def consts():
 def load():
     """Load the CUDA library (building is `__graft_entry__.build()` / `python -m vimure_b200.build`)."""
     global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+    if _lib is None:
+        _lib = open_library(LIB_PATH)
+    return _lib
+
+
+def open_library(path):
+    """dlopen `path`, declare the prototypes of the header's entry points and verify the ABI (not cached: the A/B timing
+    tool opens several builds of the library in one process)."""
+    if not os.path.exists(path):
         raise RuntimeError(
             "vimure_b200: CUDA library %s is missing -- run `python -m vimure_b200.build` (needs nvcc). "
-            "There is no CPU fallback." % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
+            "There is no CPU fallback." % path)
+    lib = ctypes.CDLL(path)
     Ctx = ctx_class()
     P = ctypes.POINTER(Ctx)
     vp, i, i64, d = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
@@ -97,6 +103,7 @@ def load():
         "vm_run": (i, [P, i, i, i, vp]),
         "vm_materialize_prior": (i, [P, vp]),
         "vm_infer": (i, [P, i, d, vp, vp]),
+        "vm_sample": (i, [P, i64, ctypes.c_uint64, vp, vp]),
         "vm_test_special": (i, [vp, vp, vp, i64, vp]),
     }
     for name, (res, args) in protos.items():
@@ -108,7 +115,6 @@ def load():
                            % (lib.vm_ctx_size(), ctypes.sizeof(Ctx)))
     if lib.vm_abi_version() != consts()["VM_ABI_VERSION"]:
         raise RuntimeError("vimure_b200: ABI version mismatch between header and library (stale build?)")
-    _lib = lib
     return lib
 
 

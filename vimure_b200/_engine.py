@@ -216,6 +216,14 @@ class CaviEngine:
             self._graphs = {}
         return self._graphs is not None
 
+    def prepare_graphs(self, store=True):
+        """Capture the graphs `iterate(..., elbo_last=True, store=store, store_last=True)` replays, up front (a capture
+        synchronises the device: do it before several engines start to run side by side on their own streams)."""
+        if self._graphs is not None:
+            F = self.C
+            for flags in (0 if store else F["VM_F_NO_STORE"], F["VM_F_ELBO"]):
+                self._graph(flags)
+
     def _graph(self, flags):
         g = self._graphs.get(flags)
         if g is None:
@@ -280,5 +288,16 @@ class CaviEngine:
         out = torch.empty(P.L, P.nloc, P.N, dtype=torch.uint8, device=self.dev)
         _capi.check(self.lib.vm_infer(self._cref, int(mode), float(threshold), ctypes.c_void_p(out.data_ptr()),
                                       self._stream()), "vm_infer")
+        self.n_launch += 1
+        return out
+
+    def sample(self, n_trials=1, seed=0):
+        """argmax of the counts of `n_trials` categorical draws per tie (reference `sample_inferred_model`,
+        model.py:1086-1088) on the device: uint8 (L, nloc, N).  Philox stream keyed by (seed, global tie id)."""
+        self.rho_slab()
+        P = self.P
+        out = torch.empty(P.L, P.nloc, P.N, dtype=torch.uint8, device=self.dev)
+        _capi.check(self.lib.vm_sample(self._cref, int(n_trials), ctypes.c_uint64(int(seed) & (2**64 - 1)),
+                                       ctypes.c_void_p(out.data_ptr()), self._stream()), "vm_sample")
         self.n_launch += 1
         return out

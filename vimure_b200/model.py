@@ -17,7 +17,11 @@ Extra, optional `fit` keywords (a superset of the reference's):
     init       : "reference" (bit-compatible RNG stream: consumes L*N*N*K draws like model.py:470),
                  "fast" (draws only for the ties that need them), or "auto" (reference when L*N*N*K <= 5e7);
     device     : CUDA device (default: current);
-    distributed: "auto" | True | False -- shard the ties by node-row blocks over torch.distributed ranks.
+    distributed: "auto" | True | False -- shard the ties by node-row blocks over torch.distributed ranks;
+    concurrent_realisations: "auto" | True | False -- run the `num_realisations` restarts (model.py:386-437) side by
+                 side, one CUDA stream + one state per restart over the shared packed data, instead of one after the
+                 other.  Same seeds, same trace, same best restart; "auto" = when an iteration is launch-bound
+                 (L*N*N*K <= 2e7) and the restarts' posterior slabs fit together.
 """
 import time
 import warnings
@@ -41,6 +45,7 @@ DEFAULT_MAX_ITER = 500
 DEFAULT_NUM_REALISATIONS = 1
 AUTO_REFERENCE_INIT_LIMIT = 5e7
 GRAPH_LIMIT = 2e7  # below this many rho entries an iteration is launch-bound: replay a captured CUDA graph
+CONCURRENT_SLAB_BYTES = 8e9  # restarts run side by side only while their posterior slabs fit together in this many bytes
 
 
 class VimureModel(TransformerMixin, BaseEstimator):
@@ -72,7 +77,7 @@ class VimureModel(TransformerMixin, BaseEstimator):
         warnings and ValueErrors, but X/R end up as COO arrays + a structured mask instead of sktensor objects."""
         available = ["R", "EPS", "K", "bias0", "max_iter", "alpha_lambda", "beta_lambda", "alpha_theta", "beta_theta",
                      "alpha_teta", "beta_teta", "num_realisations", "init_state", "init", "device", "distributed",
-                     "store_rho", "tile_h", "graphs"]
+                     "store_rho", "tile_h", "graphs", "concurrent_realisations"]
         for p in extra_params:
             if p not in available:
                 self.logger.warning("Ignoring unrecognised parameter %s." % p)
@@ -252,8 +257,20 @@ class VimureModel(TransformerMixin, BaseEstimator):
             maxL = -INF
             trace = []
             self._rho_f_dev = None
+            self._engine_f = None
             injected = extra_params.get("init_state", None)
             init_mode = extra_params.get("init", "auto")
+            conc = extra_params.get("concurrent_realisations", "auto")
+            small = float(self.L) * self.N * self.N * self.K <= GRAPH_LIMIT
+            if conc == "auto":
+                conc = small and float(self.L) * nloc * self.N * self.K * 4 * self.num_realisations <= CONCURRENT_SLAB_BYTES
+            if conc and self.num_realisations > 1 and group is None:
+                maxL, trace = self._fit_concurrent(P, priors, dev, injected, init_mode,
+                                                   use_graphs=small and extra_params.get("graphs", True))
+                cols = ["realisation", "seed", "iter", "elbo", "runtime", "reached_convergence"]
+                self.trace = pd.DataFrame(trace, columns=cols)
+                self.maxL = maxL
+                return self
             for r in range(self.num_realisations):
                 bias0 = DEFAULT_BIAS0 if r < 5 else (r - 4) * self.bias0  # model.py:390-394
                 t1 = time.time()
@@ -308,6 +325,96 @@ class VimureModel(TransformerMixin, BaseEstimator):
         self.trace = pd.DataFrame(trace, columns=cols)
         self.maxL = maxL
         return self
+
+    def _fit_concurrent(self, P, priors, dev, injected, init_mode, use_graphs):
+        """The `num_realisations` restarts of reference model.py:386-437, run side by side.
+
+        The reference's restarts are independent given their initial states, and its RNG is only consumed while a state
+        is drawn (model.py:458-605) and when the next seed is derived (model.py:431-435) -- never inside the CAVI loop.
+        So the states are drawn first, in the reference's order, and the loops then advance together: restart r owns a
+        CUDA stream and an engine (state, special-tie posterior, dense slab) over the SHARED packed data; all restarts
+        that are still running are launched up to their next ELBO evaluation before any ELBO is read back."""
+        R = self.num_realisations
+        states, seeds = [], []
+        t1 = time.time()
+        for r in range(R):
+            bias0 = DEFAULT_BIAS0 if r < 5 else (r - 4) * self.bias0  # model.py:390-394
+            st = self._state_from_injection(injected) if (injected is not None and r == 0) else \
+                self._draw_initial_state(bias0, init_mode)
+            states.append(st)
+            seeds.append(self.seed)
+            new_seed = self.prng.randint(1, 500) if self.seed is None else self.seed + self.prng.randint(1, 500)
+            self._change_seed(new_seed)
+        self.timings["draw_init"] = time.time() - t1
+
+        t1 = time.time()
+        engines = [self._engine] + [CaviEngine(P, priors, mutuality=self.mutuality, eps=self.EPS) for _ in range(R - 1)]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(R)]
+        torch.cuda.synchronize(dev)  # the engines' buffers were zero-filled on the current stream
+        for eng, st, s in zip(engines, states, streams):
+            with torch.cuda.stream(s):
+                eng.set_state(st["gamma_shp"], st["gamma_rte"], st["phi_shp"], st["phi_rte"], st["nu_shp"],
+                              st["nu_rte"], st["pr_u"], self.EPS)
+        torch.cuda.synchronize(dev)
+        if use_graphs:
+            for eng in engines:  # capture before anything runs asynchronously
+                if eng.enable_graphs():
+                    eng.prepare_graphs(store=self._store_rho)
+        self.timings["init_state"] = time.time() - t1
+
+        t_loop = time.time()
+        run = [dict(coincide=0, it=1, reached=False, elbo=-INF, rows=[]) for _ in range(R)]
+        active = list(range(R))
+        while active:
+            torch.cuda.synchronize(dev)
+            t_start = time.time()
+            batch = {}
+            for r in active:
+                it = nxt = run[r]["it"]
+                while not (nxt == 1 or nxt % 10 == 0 or nxt == self.max_iter):
+                    nxt += 1
+                batch[r] = (nxt, nxt - it + 1)
+                with torch.cuda.stream(streams[r]):
+                    engines[r].iterate(nxt - it + 1, elbo_last=True, store=self._store_rho, store_last=True)
+            for r in active:
+                with torch.cuda.stream(streams[r]):
+                    new_elbo = engines[r].elbo()
+                nxt, n = batch[r]
+                runtime = (time.time() - t_start) / n
+                q = run[r]
+                if np.isnan(new_elbo):
+                    raise ValueError("ELBO is NaN!!!!")
+                old_L, q["elbo"] = q["elbo"], new_elbo  # `_check_for_convergence`, model.py:1036-1056
+                q["coincide"] = q["coincide"] + 1 if abs(q["elbo"] - old_L) < self.convergence_tol else 0
+                if q["coincide"] > self.decision:
+                    q["reached"] = True
+                if self.verbose:
+                    self.logger.debug(f"Realisation {r:2} | Iter {nxt:4} | ELBO value: {new_elbo:6.12f} | "
+                                      f"Reached convergence: {q['reached']}")
+                q["it"] = nxt + 1
+                if nxt % 10 == 0:  # model.py:423-426
+                    q["rows"].append((r, seeds[r], nxt, new_elbo, runtime, q["reached"]))
+            active = [r for r in active if not run[r]["reached"] and run[r]["it"] <= self.max_iter]
+        torch.cuda.synchronize(dev)
+        self.timings["cavi_loop"] = time.time() - t_loop
+
+        maxL, trace, best = -INF, [], None
+        for r in range(R):  # the reference's bookkeeping, in the reference's order
+            trace.extend(run[r]["rows"])
+            if maxL < run[r]["elbo"]:
+                maxL, best = run[r]["elbo"], r
+        self.n_iter_ = run[R - 1]["it"] - 1
+        self._pr_u = states[R - 1]["pr_u"]
+        if best is not None:
+            self._engine = engines[best]
+            self._fetch_params()
+            self._update_optimal_parameters(clone_rho=False)  # every restart keeps its own slab: nothing to copy
+        self._engine = engines[R - 1]  # `rho`, `gamma_shp`, ... without _f are the LAST restart's (model.py:925-942)
+        self._fetch_params()
+        self._engine_f = engines[best] if best is not None else None
+        self._rho_f_dev = engines[best].rho_slab() if (best is not None and best != R - 1) else None
+        self._rho_f_cache = None
+        return maxL, trace
 
     # ------------------------------------------------------------------ initial state
     def _special_tie_info(self):
@@ -456,7 +563,7 @@ class VimureModel(TransformerMixin, BaseEstimator):
         self._rho_cache = None
         self._pr_rho_cache = None
 
-    def _update_optimal_parameters(self):
+    def _update_optimal_parameters(self, clone_rho=True):
         """reference model.py:925-942"""
         import scipy.special as sp
 
@@ -470,7 +577,7 @@ class VimureModel(TransformerMixin, BaseEstimator):
         self.G_exp_lambda_f = np.exp(sp.psi(self.phi_shp_f) - np.log(self.phi_rte_f))
         self.G_exp_nu_f = np.exp(sp.psi(self.nu_shp_f) - np.log(self.nu_rte_f))
         # rho_f stays on the device; a copy is needed only when further realisations will overwrite the slab
-        if self.num_realisations > 1:
+        if self.num_realisations > 1 and clone_rho:
             self._rho_f_dev = self._engine.rho_slab().clone()
         else:
             self._rho_f_dev = None
@@ -544,10 +651,34 @@ class VimureModel(TransformerMixin, BaseEstimator):
         return sptensor((l, j, i, m), self.X.vals, shape=self.X.shape)
 
     # ------------------------------------------------------------------ inferred model (model.py:1062-1214)
-    def sample_inferred_model(self, N=1, seed=None):
-        """Sample Y trials from the rho distribution (reference model.py:1062-1096)."""
+    def _engine_of_rho_f(self):
+        """The engine whose device slab IS rho_f (the best restart's own when the restarts ran side by side, else the only /
+        last one unless an earlier restart won and rho_f is a copy), or None."""
+        if self._world != 1:
+            return None
+        return getattr(self, "_engine_f", None) or (self._engine if self._rho_f_dev is None else None)
+
+    def sample_inferred_model(self, N=1, seed=None, rng="auto"):
+        """Sample Y trials from the rho distribution (reference model.py:1062-1096): a list of N arrays (L, N, N), each the
+        argmax of the counts of N categorical draws per tie.
+
+        rng = "numpy": the reference's generator (`default_rng(seed + i).multinomial`) on the host, which materialises
+        rho_f as float64 -- 8 bytes * L*N*N*K; rng = "device": the `vm_sample` kernel on the fp32 slab (Philox stream
+        keyed by seed and tie: same law, different stream, 1 byte per tie comes back); "auto": numpy while
+        L*N*N*K <= 5e7, else device."""
         if seed is None:
             seed = self.seed
+        if rng not in ("auto", "numpy", "device"):
+            raise ValueError("rng must be 'auto', 'numpy' or 'device'")
+        eng_f = self._engine_of_rho_f()
+        if rng == "auto":
+            big = float(self.L) * self.N * self.N * self.K > AUTO_REFERENCE_INIT_LIMIT
+            rng = "device" if (big and eng_f is not None) else "numpy"
+        if rng == "device":
+            if eng_f is None:
+                raise RuntimeError("rng='device' needs rho_f on this rank's device (single-rank fit whose best restart's "
+                                   "slab is still resident)")
+            return [eng_f.sample(N, int(seed) + i).cpu().numpy().astype("int") for i in range(0, N)]
 
         def sampleY(seed):
             pnrg = np.random.default_rng(seed)
@@ -571,10 +702,11 @@ class VimureModel(TransformerMixin, BaseEstimator):
             warnings.warn(msg, UserWarning)
             method = "rho_max"
 
-        single = self._world == 1 and self._rho_f_dev is None
+        eng_f = self._engine_of_rho_f()
+        single = eng_f is not None
         if method == "rho_max":
             if single:  # argmax on the device, 1 byte per tie back
-                return self._engine.infer(0).cpu().numpy().astype("int")
+                return eng_f.infer(0).cpu().numpy().astype("int")
             return np.argmax(self.rho_f, axis=-1).astype("int")
         if method == "rho_mean":
             return np.dot(self.rho_f, range(0, self.K))
@@ -582,7 +714,7 @@ class VimureModel(TransformerMixin, BaseEstimator):
             if (threshold is None) or (threshold > 1) or (threshold < 0):
                 raise ValueError('For method="fixed_threshold", you must set the threshold to a value in [0,1].')
             if single:
-                return self._engine.infer(1, threshold).cpu().numpy().astype(np.float64)
+                return eng_f.infer(1, threshold).cpu().numpy().astype(np.float64)
             Y = np.copy(self.rho_f[:, :, :, 1])
             Y[Y < threshold] = 0
             Y[Y >= threshold] = 1
