@@ -63,7 +63,9 @@ extern "C" {
 /* maximum K compiled in */
 #define VM_MAX_K 32
 /* special ties handled by one block of the special-tie kernel (n_ublk = ceil(max per layer / this)) */
+#ifndef VM_SPECIAL_TIES_PER_BLOCK /* (a timing variant may be built with a multiple of it: tools/ab_libs.py) */
 #define VM_SPECIAL_TIES_PER_BLOCK 1024
+#endif
 /* row chunks of the special/dense overlap */
 #define VM_NCHUNK 4
 

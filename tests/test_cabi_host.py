@@ -67,6 +67,41 @@ def test_mask_detection(name):
     assert np.array_equal(tr, rep_any[tuple(q[:3])])
 
 
+def test_ego_detection_rejects_duplicates_and_near_misses():
+    """An explicit mask is only recognised as an ego mask if it is EXACTLY one (same entries, each once)."""
+    import vimure_b200 as vm
+
+    L, N, M = 2, 30, 20
+    ego = vm.masks.EgoMask(L, N, M, rep=np.arange(0, M, 2), diag=True)
+    R = ego.to_sptensor()
+    subs, vals = [np.asarray(s) for s in R.subs], np.asarray(R.vals)
+    m = vm.masks.from_input(R, L, N, M)
+    assert m.kind == "ego" and m.diag and np.array_equal(m.rep, ego.rep)
+    # one entry replaced by a copy of another entry of the same reporter and side: same counts, not distinct
+    l, i, j, r = (a.copy() for a in subs)
+    idx = np.nonzero((l == l[0]) & (r == r[0]) & (i == r) & (j != r))[0][:2]
+    for a in (l, i, j, r):
+        a[idx[1]] = a[idx[0]]
+    assert vm.masks._detect_ego((l, i, j, r), vals, L, N, M) is None
+    assert vm.masks.from_input(vm.sptensor.sptensor((l, i, j, r), vals, shape=R.shape), L, N, M).kind == "coo"
+    # a reporter that reports a tie it is not part of / a non-unit value / a missing entry
+    l, i, j, r = (a.copy() for a in subs)
+    i[5], j[5] = (r[5] + 1) % N, (r[5] + 2) % N
+    assert vm.masks._detect_ego((l, i, j, r), vals, L, N, M) is None
+    v2 = vals.copy()
+    v2[3] = 2
+    assert vm.masks._detect_ego(subs, v2, L, N, M) is None
+    assert vm.masks._detect_ego([a[1:] for a in subs], vals[1:], L, N, M) is None
+    # without the diagonal entries it is the diag=False ego mask
+    keep = ~((subs[1] == subs[3]) & (subs[2] == subs[3]))
+    m2 = vm.masks._detect_ego([a[keep] for a in subs], vals[keep], L, N, M)
+    assert m2 is not None and not m2.diag
+    # the sort-based path (far fewer entries than slots) gives the same verdicts
+    assert vm.masks._ego_entries_distinct(*[a[:7] for a in subs], L=L, N=10**6, M=M)
+    dup = [np.concatenate([a[:7], a[:1]]) for a in subs]
+    assert not vm.masks._ego_entries_distinct(*dup, L=L, N=10**6, M=M)
+
+
 @pytest.mark.parametrize("name,world", [("f1_over", 1), ("karnataka_vil1", 1), ("gm_l2_k3", 3), ("custom_mask", 2), ("nomut", 2)])
 def test_packing_invariants(name, world):
     import vimure_b200 as vm

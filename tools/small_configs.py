@@ -50,4 +50,5 @@ for name in ("f1_over", "karnataka_vil1"):
             torch.cuda.synchronize()
             dt = time.time() - t0
         print(f"{name}: 5 restarts x 200 iterations, side by side={conc}: fit {dt*1e3:.1f} ms, CAVI loop "
-              f"{m.timings['cavi_loop']*1e3:.1f} ms = {5*200/m.timings['cavi_loop']:.0f} iter/s, maxL={m.maxL:.6f}")
+              f"{m.timings['cavi_loop']*1e3:.1f} ms = {5*200/m.timings['cavi_loop']:.0f} iter/s, maxL={m.maxL:.6f}  "
+              + " ".join(f"{k}={v*1e3:.1f}" for k, v in m.timings.items()))

@@ -130,6 +130,7 @@ class CaviEngine:
         self._cref = ctypes.byref(c)
         self.n_launch = 0
         self._graphs = None  # flags -> captured CUDA graph of one iteration (small, launch-bound problems)
+        self._capture_stream = None
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -227,10 +228,24 @@ class CaviEngine:
     def _graph(self, flags):
         g = self._graphs.get(flags)
         if g is None:
+            # Explicit capture_begin/capture_end on a side stream instead of the `torch.cuda.graph` context manager: that
+            # one runs gc.collect() and torch.cuda.empty_cache() on entry (hundreds of ms once the caching allocator holds
+            # many blocks), which a capture that allocates nothing does not need.  Capture only: nothing executes, the
+            # state does not advance.
             g = torch.cuda.CUDAGraph()
-            torch.cuda.synchronize(self.dev)
-            with torch.cuda.graph(g):  # capture only: nothing executes, the state does not advance
-                _capi.check(self.lib.vm_iteration(self._cref, int(flags), self._stream()), "vm_iteration (capture)")
+            cur = torch.cuda.current_stream(self.dev)
+            if self._capture_stream is None:
+                self._capture_stream = torch.cuda.Stream(device=self.dev)
+            side = self._capture_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                g.capture_begin(capture_error_mode="thread_local")
+                try:
+                    rc = self.lib.vm_iteration(self._cref, int(flags), self._stream())
+                finally:
+                    g.capture_end()
+                _capi.check(rc, "vm_iteration (capture)")
+            cur.wait_stream(side)
             self._graphs[flags] = g
         return g
 

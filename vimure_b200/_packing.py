@@ -34,6 +34,31 @@ def _i32(t):
     return t.to(torch.int32).contiguous()
 
 
+class _Trace:
+    """VM_PACK_TRACE=1: print the wall time of the packer's stages (each closed by a device synchronisation)."""
+
+    def __init__(self, dev):
+        import os
+        import time
+
+        self.on = os.environ.get("VM_PACK_TRACE") == "1"
+        self.dev, self.time = dev, time
+        if self.on:
+            self._sync()
+            self.t = time.time()
+
+    def _sync(self):
+        if self.dev.type == "cuda":
+            torch.cuda.synchronize(self.dev)
+
+    def __call__(self, label):
+        if self.on:
+            self._sync()
+            now = self.time.time()
+            print("pack: %-24s %7.2f ms" % (label, (now - self.t) * 1e3), flush=True)
+            self.t = now
+
+
 class Packed:
     """Plain container of the packed tensors + dimensions."""
 
@@ -57,6 +82,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
     """
     dev = torch.device(device)
     nloc = N - row0 if nloc is None else int(nloc)
+    _mark = _Trace(dev)
     P = Packed()
     P.L, P.N, P.M, P.K, P.row0, P.nloc = int(L), int(N), int(M), int(K), int(row0), nloc
     TILE_W = dense_tile_w(K)
@@ -85,6 +111,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
         if mx[0] >= L or mx[1] >= N or mx[2] >= N or mx[3] >= M or mx[4] > 0:
             raise ValueError("X has subscripts outside its shape")
 
+    _mark("h2d+check")
     # ---- reciprocal pairing: xT[I] = X[l, j, i, m]   (model.py:152-161)
     key = ((xl * N + xi) * N + xj) * M + xm
     skey, order = torch.sort(key)
@@ -99,6 +126,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
         xT = xv.clone()
     P.sumX = float(xv.sum()) if I_all else 0.0
 
+    _mark("pairing")
     in_R = mask.entry_multiplicity(xl, xi, xj, xm) if I_all else xv.clone()
     in_RT = mask.entry_multiplicity(xl, xj, xi, xm) if I_all else xv.clone()
 
@@ -112,6 +140,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
     P.I = int(I)
     P.entry_src = sel  # position of each packed entry in the caller's COO order
 
+    _mark("mask+tie sort")
     # ---- special ties
     ukeys = torch.unique_consecutive(tk_sorted)
     if mask.kind == "ego":
@@ -156,6 +185,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
     P.t["u_reported"] = mask.tie_reported(u_l, u_i, u_col) if U else torch.zeros(0, dtype=torch.bool, device=dev)
     P.t["u_gflat"] = (u_l * N + u_i) * N + u_col  # global flat tie id (l,i,j) -> position in the reference's arrays
 
+    _mark("special ties")
     # dense-tile pointers: first special tie of every (local row, column tile)
     rows = torch.arange(L * nloc, device=dev, dtype=torch.int64)
     bounds = (rows[:, None] * N + torch.arange(P.nct, device=dev, dtype=torch.int64)[None, :] * TILE_W).flatten()
@@ -185,6 +215,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
     P.t["sp_chunk_blk"] = blk.contiguous().flatten()
     P.sp_grid = [int(v) for v in (blk[:, 1:] - blk[:, :-1]).max(dim=0)[0].cpu()]
 
+    _mark("tile/col pointers")
     # ---- layer ranges and reporter chunks of the entries
     P.phi_chunk = PHI_CHUNK
     e_l = tk_sorted // (nloc * N)
@@ -244,6 +275,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
     P.t["g_chunk_lm"] = _i32(chunk_lm)
     P.t["g_chunk_ptr"] = torch.cat([cstart, cstart.new_tensor([I1])]).contiguous()
 
+    _mark("E0/E1 + reporter order")
     # ---- transposed-position list for the eta part of the ELBO (model.py:1269-1290): the X entry (l,i,j,m)
     # is the "X_T" value of the mask entry (l,j,i,m); it belongs to the rank that owns row j
     ownT = (xj >= row0) & (xj < row0 + nloc) & (in_RT > 0)
@@ -263,6 +295,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
     P.t["t_x"] = (xv[st] * in_RT[st]).to(torch.float32).contiguous()
     P.b_all = float(P.t["t_x"].to(torch.float64).sum()) if P.IT else 0.0
 
+    _mark("transposed list")
     # ---- reporter mask
     P.r_mode = {"ego": 0, "all": 1, "coo": 2}[mask.kind]
     P.ego_diag = int(getattr(mask, "diag", False))
@@ -284,6 +317,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
         rlm_s, co = torch.sort(rlm, stable=True)
         P.t["c_ptr"] = torch.searchsorted(rlm_s, torch.arange(L * M + 1, device=dev, dtype=torch.int64)).contiguous()
         P.t["c_tie"] = rtie_s[co].contiguous()
+    _mark("mask arrays")
     return P
 
 

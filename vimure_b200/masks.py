@@ -142,6 +142,22 @@ class CooMask(ReporterMask):
         return tk[pos] == k
 
 
+def _ego_entries_distinct(l, i, j, m, L, N, M):
+    """No (l, i, j, m) occurs twice, given that every entry has i == m or j == m: an entry is then identified by its
+    reporter, the side the reporter is on and the other node -- one flag per such slot (O(n)) instead of a sort / hash
+    of the 4-subscript keys (np.unique took 0.34 s of a 0.4 s fit set-up on the 6.8e5-entry Karnataka mask)."""
+    n = l.size
+    slots = 2 * L * M * N
+    if slots > 8 * n + (1 << 20):  # far sparser than an ego mask can be: the sort is cheaper than the flag array
+        key = np.sort(((l * N + i) * N + j) * M + m)
+        return not bool(np.any(key[1:] == key[:-1]))
+    row_side = i == m  # reporter is the source (this includes the diagonal entry)
+    slot = ((l * M + m) * 2 + np.where(row_side, 0, 1)) * N + np.where(row_side, j, i)
+    seen = np.zeros(slots, dtype=bool)
+    seen[slot] = True
+    return int(np.count_nonzero(seen)) == n
+
+
 def _detect_ego(subs, vals, L, N, M):
     """Return an EgoMask if the COO mask is exactly an ego mask, else None."""
     if M > N or len(vals) == 0:
@@ -157,8 +173,7 @@ def _detect_ego(subs, vals, L, N, M):
     for diag in (True, False):
         full = 2 * N - 1 if diag else 2 * N - 2
         if np.all(cnt[rep] == full) and ndiag == (int(rep.sum()) if diag else 0):
-            key = ((l * N + i) * N + j) * M + m
-            if np.unique(key).size == key.size:
+            if _ego_entries_distinct(l, i, j, m, L, N, M):
                 return EgoMask(L, N, M, rep=rep.astype(np.uint8), diag=diag)
     return None
 

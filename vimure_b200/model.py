@@ -23,6 +23,7 @@ Extra, optional `fit` keywords (a superset of the reference's):
                  other.  Same seeds, same trace, same best restart; "auto" = when an iteration is launch-bound
                  (L*N*N*K <= 2e7) and the restarts' posterior slabs fit together.
 """
+import os
 import time
 import warnings
 
@@ -246,6 +247,9 @@ class VimureModel(TransformerMixin, BaseEstimator):
                     msg = "If undirected is True, the given network has to be symmetric wrt l and m!"
                     self.logger.error(msg)
                     raise ValueError(msg)
+            if os.environ.get("VM_PACK_TRACE") == "1":
+                torch.cuda.synchronize(dev)
+                self.timings["pack"] = time.time() - t0
             priors = dict(alpha_theta=self.alpha_theta, beta_theta=self.beta_theta, alpha_lambda=self.alpha_lambda,
                           beta_lambda=self.beta_lambda, alpha_eta=self.alpha_mutuality, beta_eta=self.beta_mutuality)
             self._engine = eng = CaviEngine(P, priors, mutuality=self.mutuality, eps=self.EPS, group=group)
