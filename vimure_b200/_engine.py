@@ -108,8 +108,11 @@ class CaviEngine:
             c.sp_grid0, c.sp_grid1, c.sp_grid2, c.sp_grid3 = (int(v) for v in P.sp_grid)
             c.aux_stream = self.aux_stream.cuda_stream
         else:
+            # serial special -> dense; the aux stream only carries the general dense kernel (partial column tiles) under
+            # the fast one (see launch_dense)
+            self.aux_stream = torch.cuda.Stream(device=dev)
             c.n_chunks = 0
-            c.aux_stream = None
+            c.aux_stream = self.aux_stream.cuda_stream
         self._keep = []
 
         def ptr(t):
@@ -171,7 +174,8 @@ class CaviEngine:
         if P.U:
             pr = (pr_u.to(**f64) if torch.is_tensor(pr_u) else torch.as_tensor(pr_u, **f64)).reshape(P.U, P.K)
             self.rho_u.copy_(pr)
-            self.u_logpr.copy_(torch.log(pr + float(eps)))
+            torch.add(pr, float(eps), out=self.u_logpr)  # log(pr_rho + EPS), model.py:559, without temporaries
+            self.u_logpr.log_()
         st = self._stream()
         _capi.check(self.lib.vm_refresh_cache(self._cref, st), "vm_refresh_cache")
         _capi.check(self.lib.vm_init_stats(self._cref, st), "vm_init_stats")

@@ -1611,21 +1611,44 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, in
   double* cp = region_cat(c);
   const bool fast = K <= 4 && store && !csr && ((c->N * K) & 3) == 0 && c->N >= c->tile_w &&
                     c->tile_h <= VM_FAST_MAX_TILE_H;
-  if (fast) {
+  // The general kernel only has the tiles the fast one leaves (the partial last column tile: 157 of 6280 CTAs at config 3,
+  // each a serial sweep of its rows, 32 us): it goes to the caller's aux stream, forked from and joined back into `st`,
+  // so that it runs under the fast kernel instead of after it.  The two write disjoint tiles and disjoint partial slots.
+  cudaStream_t aux = (cudaStream_t)c->aux_stream;
+  const bool side = fast && aux != nullptr && aux != st;
+  cudaStream_t sg = side ? aux : st;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (side) {
+    if (cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)
+      return (int)cudaGetLastError();
+    cudaEventRecord(ev_fork, st);
+    cudaStreamWaitEvent(aux, ev_fork, 0);
+  }
+  if (fast && !side) {
     if (elbo) k_dense_fast<(K <= 4 ? K : 2), true><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, rt0, rtn);
     else k_dense_fast<(K <= 4 ? K : 2), false><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, rt0, rtn);
   }
-#define LD(E, S, C) k_dense<K, E, S, C><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, fast ? 1 : 0, rt0, rtn)
+  int rc = 0;
+#define LD(E, S, C) k_dense<K, E, S, C><<<grid, VM_DENSE_THREADS, 0, sg>>>(*c, cp, fast ? 1 : 0, rt0, rtn)
   if (csr) {
-    if (!store) return VM_ENOTSUP;  // the general-mask statistics gather the slab
-    if (elbo) LD(true, true, true); else LD(false, true, true);
+    if (!store) rc = VM_ENOTSUP;  // the general-mask statistics gather the slab
+    else if (elbo) LD(true, true, true); else LD(false, true, true);
   } else if (elbo) {
     if (store) LD(true, true, false); else LD(true, false, false);
   } else {
     if (store) LD(false, true, false); else LD(false, false, false);
   }
 #undef LD
-  return 0;
+  if (side) {
+    if (elbo) k_dense_fast<(K <= 4 ? K : 2), true><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, rt0, rtn);
+    else k_dense_fast<(K <= 4 ? K : 2), false><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, rt0, rtn);
+    cudaEventRecord(ev_join, aux);
+    cudaStreamWaitEvent(st, ev_join, 0);
+    cudaEventDestroy(ev_fork);  // destruction is deferred by the runtime until the events have completed
+    cudaEventDestroy(ev_join);
+  }
+  return rc;
 }
 
 template <int K>

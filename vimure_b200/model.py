@@ -45,7 +45,7 @@ DEFAULT_BIAS0 = 0.0
 DEFAULT_MAX_ITER = 500
 DEFAULT_NUM_REALISATIONS = 1
 AUTO_REFERENCE_INIT_LIMIT = 5e7
-GRAPH_LIMIT = 2e7  # below this many rho entries an iteration is launch-bound: replay a captured CUDA graph
+GRAPH_LIMIT = 2e7  # below this many rho entries an iteration is launch-bound (restarts are then run side by side)
 CONCURRENT_SLAB_BYTES = 8e9  # restarts run side by side only while their posterior slabs fit together in this many bytes
 
 
@@ -253,8 +253,10 @@ class VimureModel(TransformerMixin, BaseEstimator):
             priors = dict(alpha_theta=self.alpha_theta, beta_theta=self.beta_theta, alpha_lambda=self.alpha_lambda,
                           beta_lambda=self.beta_lambda, alpha_eta=self.alpha_mutuality, beta_eta=self.beta_mutuality)
             self._engine = eng = CaviEngine(P, priors, mutuality=self.mutuality, eps=self.EPS, group=group)
-            if group is None and float(self.L) * self.N * self.N * self.K <= GRAPH_LIMIT and extra_params.get("graphs", True):
-                eng.enable_graphs()  # launch-bound sizes: one graph replay per iteration
+            if group is None and extra_params.get("graphs", True):
+                # one graph replay per iteration instead of ~17 launches: decisive for launch-bound sizes, and still 1.6 %
+                # at config 3 (1.377 -> 1.355 ms per iteration, B200)
+                eng.enable_graphs()
             torch.cuda.synchronize(dev)
             self.pack_time = self.timings["pack+engine"] = time.time() - t0
 
@@ -270,10 +272,11 @@ class VimureModel(TransformerMixin, BaseEstimator):
                 conc = small and float(self.L) * nloc * self.N * self.K * 4 * self.num_realisations <= CONCURRENT_SLAB_BYTES
             if conc and self.num_realisations > 1 and group is None:
                 maxL, trace = self._fit_concurrent(P, priors, dev, injected, init_mode,
-                                                   use_graphs=small and extra_params.get("graphs", True))
+                                                   use_graphs=extra_params.get("graphs", True))
                 cols = ["realisation", "seed", "iter", "elbo", "runtime", "reached_convergence"]
                 self.trace = pd.DataFrame(trace, columns=cols)
                 self.maxL = maxL
+                self.timings["fit_total"] = time.time() - t_fit
                 return self
             for r in range(self.num_realisations):
                 bias0 = DEFAULT_BIAS0 if r < 5 else (r - 4) * self.bias0  # model.py:390-394
@@ -318,16 +321,19 @@ class VimureModel(TransformerMixin, BaseEstimator):
                         trace.append((r, self.seed, it - 1, elbo, runtime, reached))
                 self.n_iter_ = it - 1
                 self.timings["cavi_loop"] = self.timings.get("cavi_loop", 0.0) + time.time() - t_loop
+                t1 = time.time()
                 self._fetch_params()
                 if maxL < elbo:
                     self._update_optimal_parameters()
                     maxL = elbo
+                self.timings["fetch_results"] = self.timings.get("fetch_results", 0.0) + time.time() - t1
                 new_seed = self.prng.randint(1, 500) if self.seed is None else self.seed + self.prng.randint(1, 500)
                 self._change_seed(new_seed)
 
         cols = ["realisation", "seed", "iter", "elbo", "runtime", "reached_convergence"]
         self.trace = pd.DataFrame(trace, columns=cols)
         self.maxL = maxL
+        self.timings["fit_total"] = time.time() - t_fit
         return self
 
     def _fit_concurrent(self, P, priors, dev, injected, init_mode, use_graphs):
@@ -442,13 +448,15 @@ class VimureModel(TransformerMixin, BaseEstimator):
             dev = P.t["u_lrow"].device
             gen = torch.Generator(device=dev)
             gen.manual_seed(int(self.prng.randint(0, 2**31 - 1)))
-            keep_d = P.t["u_has_x"] & P.t["u_reported"]
-            pr = 1 + 0.01 * torch.rand((int(keep_d.sum()), K), generator=gen, dtype=torch.float64, device=dev)
-            pr[:, 0] += bias0
-            pr /= pr.sum(dim=-1, keepdim=True)
-            pr_u = torch.zeros((U, K), dtype=torch.float64, device=dev)
-            pr_u[:, 0] = 1.0
-            pr_u[keep_d] = pr
+            # in place, no host synchronisation: one draw per special tie, then the ties that keep the one-hot prior
+            # (no X entry / not reported, model.py:536-556) are overwritten
+            drop = ~(P.t["u_has_x"] & P.t["u_reported"])
+            pr_u = torch.rand((U, K), generator=gen, dtype=torch.float64, device=dev)
+            pr_u.mul_(0.01).add_(1.0)
+            pr_u[:, 0] += bias0
+            pr_u /= pr_u.sum(dim=-1, keepdim=True)
+            pr_u.masked_fill_(drop[:, None], 0.0)
+            pr_u[:, 0].masked_fill_(drop, 1.0)
             st = dict(pr_u=pr_u)
             self._draw_small_params(st)
             return st
