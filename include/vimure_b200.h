@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VM_ABI_VERSION 10
+#define VM_ABI_VERSION 11
 
 /* reporter-mask structure (how R[l,i,j,m] is represented) */
 #define VM_R_EGO 0 /* reporter m == node m reports row m and column m (vimure synthetic.py:1184-1204, _io.py:229-242) */
@@ -111,6 +111,26 @@ typedef struct vm_ctx {
   const int64_t* ucol_ptr;  /* [L*N+1] EGO: special ties grouped by (l, col) */
   const int32_t* ucol_perm; /* [U] */
 
+  /* ---- simple special ties ----
+     A special tie is SIMPLE when none of its X entries has a reciprocal report (x^T = 0, or mutuality off), it is off the
+     diagonal and lies in a full column tile.  Its Poisson allocation is dz1_k = x whatever the parameters, and the
+     E[log theta] of its reporters is common to every k, so its posterior odds are
+        log2 rho_k/rho_0 = lo_k - S (E[lambda_k]-E[lambda_0]) log2e + X (E[log lambda_k]-E[log lambda_0]) log2e,
+     lo_k = log2((pr_k+EPS)/(pr_0+EPS)), X = sum of its x: the same separable form as a tie without data, plus a per-tie
+     constant and a per-layer multiple of X.  On iterations that store the slab and do not evaluate the ELBO the fast
+     dense kernel evaluates these ties itself (fp32, terms of magnitude O(1): no cancellation) and the special-tie kernel
+     only visits the others (`cx_idx`); every other iteration runs the special-tie kernel over all special ties, as
+     does any layer for which k_phi_finish cannot rule out a completely underflowed tie (layer constant VM_LC_SIMPLE). */
+  int64_t simple_mode;      /* 1 = enabled (EGO mask, K <= 4, fast dense kernel eligible, serial special/dense launch) */
+  int64_t n_cx;             /* special ties that are NOT simple */
+  const int32_t* cx_idx;    /* [n_cx + U] their indices, ascending; then the identity 0..U-1 (what a layer that cannot
+                               use the shortcut walks instead, through the same code) */
+  const int64_t* cx_ptr;    /* [L+1] range of cx_idx[0..n_cx) of every layer */
+  float* u_patch;           /* [U*K] patch source of the fast dense kernel on such iterations: (-X, lo_1..lo_{K-1}) for a
+                               simple tie (constant over a fit), the fp32 posterior (written by the special-tie kernel) else */
+  const double* simple_consts; /* [2] min over the simple ties of log(pr_0+EPS); max X */
+  int64_t* fixP;            /* [L*K] fixed point 2^-30: sum over the simple ties of rho_k X (their part of phi0) */
+
   /* ---- X entries, sorted by tie ---- */
   const int32_t* e_u;       /* [I] special-tie index */
   const int32_t* e_m;       /* [I] reporter */
@@ -175,7 +195,8 @@ typedef struct vm_ctx {
   float* rho;               /* [L*nloc*N*K] dense posterior slab */
 
   /* ---- workspaces ---- */
-  double* layer_consts;     /* [L*(2*K+4)] per layer: c_k, d_k (log2 domain), S_all, log-prior consts, dead flag */
+  double* layer_consts;     /* [L*(3*K+5)] per layer: c_k, d_k (log2 domain), S_all, log-prior consts, dead flag,
+                               simple-tie flag, g_k */
   float* tab_p;             /* [L*nloc*K] row part of the log2-odds */
   float* tab_q;             /* [L*N*K] column part */
   float* rowpart;           /* [L*nloc*nct*K] */

@@ -146,3 +146,122 @@ def test_full_size_properties_config3():
     for k in ("gamma_shp", "gamma_rte", "phi_shp", "phi_rte", "nu_shp"):
         assert np.array_equal(runs[0][0][k], runs[1][0][k]), k
     assert runs[0][1] == runs[1][1]
+
+
+@pytest.mark.parametrize("case", ["sbm_k2", "gm_l2_k3", "nomut_k2", "subset_k4"])
+def test_simple_special_ties_in_the_dense_kernel(case, monkeypatch):
+    """On iterations without ELBO the fast dense kernel evaluates the special ties that have no reciprocal report itself
+    (fp32, include/vimure_b200.h: vm_ctx.simple_mode) and the special-tie kernel only walks the others.  Against the
+    oracle (the usual tolerances, after runs of such iterations) and against the same engine with the shortcut off."""
+    torch = _cuda()
+    import vimure_b200 as vm
+    import vimure_b200.synthetic as syn
+
+    mutuality = True
+    if case == "sbm_k2":  # two full column tiles + a partial one
+        L, N, K = 1, 1100, 2
+        net = syn.StandardSBM(N=N, L=L, K=K, C=2, avg_degree=10, seed=10).build_X(mutuality=0.5, seed=20)
+        mask, rep, diag = net.R, np.ones((L, N), dtype=np.uint8), True
+    elif case == "gm_l2_k3":
+        L, N, K = 2, 640, 3
+        net = syn.Multitensor(N=N, L=L, K=K, C=2, avg_degree=8, eta=0.5, seed=3).build_X(mutuality=0.5, seed=4)
+        mask, rep, diag = net.R, np.ones((L, N), dtype=np.uint8), True
+    elif case == "nomut_k2":  # mutuality off: every tie with a report is simple
+        L, N, K, mutuality = 1, 600, 2, False
+        net = syn.StandardSBM(N=N, L=L, K=K, C=2, avg_degree=6, seed=5).build_X(mutuality=0.3, seed=6)
+        mask, rep, diag = net.R, np.ones((L, N), dtype=np.uint8), True
+    else:  # reporters are a subset of the nodes, no diagonal entries in the mask
+        L, N, K, M = 2, 520, 4, 60
+        net = syn.StandardSBM(N=N, M=M, L=L, K=K, C=2, avg_degree=6, seed=7).build_X(mutuality=0.4, seed=8)
+        rep = np.zeros((L, M), dtype=np.uint8)
+        rep[:, ::2] = 1
+        s = np.stack(net.X.subs)
+        keep = (s[3] < M) & (rep[s[0], np.minimum(s[3], M - 1)] == 1)
+        net.X = vm.sptensor.sptensor(tuple(s[:, keep]), np.asarray(net.X.vals)[keep], shape=(L, N, N, M))
+        mask, diag = vm.masks.EgoMask(L, N, M, rep=rep, diag=False), False
+    spec = {"kind": "ego", "rep": rep, "diag": diag}
+    eng, o, P = _engine_and_oracle(net, mask, spec, K, mutuality=mutuality, tile_h=32)
+    assert eng.simple_mode and int(P.t["u_simple"].sum()) > 0 and P.n_cx < P.U
+    monkeypatch.setenv("VM_NO_SIMPLE", "1")
+    ref, _, P2 = _engine_and_oracle(net, mask, None, K, mutuality=mutuality, tile_h=32)
+    assert not ref.simple_mode and P2.n_cx == P2.U
+
+    def check(tag, slab):
+        p, q = eng.params(), ref.params()
+        for k in ("gamma_shp", "gamma_rte", "phi_shp", "phi_rte"):
+            np.testing.assert_allclose(p[k], getattr(o, k), rtol=1e-5, err_msg=f"{k} vs oracle {tag}")
+            np.testing.assert_allclose(p[k], q[k], rtol=2e-6, err_msg=f"{k} vs fp64 path {tag}")
+        if mutuality:
+            np.testing.assert_allclose(p["nu_shp"], o.nu_shp, rtol=1e-5, err_msg=tag)
+        if slab:
+            a = eng.rho_slab().cpu().numpy().astype(np.float64)
+            np.testing.assert_allclose(a, o.rho, rtol=2e-5, atol=1e-30, err_msg=tag)
+            np.testing.assert_allclose(a, ref.rho_slab().cpu().numpy(), rtol=1e-5, atol=1e-30, err_msg=tag)
+
+    # the layers do take the shortcut (flag written by k_phi_finish), and the special-tie kernel skips the simple ties
+    for e in (eng, ref):
+        e.iterate(2)  # two iterations without ELBO
+    o.iterate()
+    o.iterate()
+    lc = eng.layer_consts.cpu().numpy().reshape(L, 3 * K + 5)
+    assert (lc[:, 2 * K + 4] == 1.0).all()
+    check("after 2 fast iterations", slab=True)
+    for e in (eng, ref):
+        e.iterate(4, elbo_last=True)  # three more without, then one with the ELBO (every special tie in fp64)
+    for _ in range(4):
+        o.iterate()
+    np.testing.assert_allclose(eng.elbo(), o.elbo(), rtol=1e-6)
+    np.testing.assert_allclose(eng.elbo(), ref.elbo(), rtol=1e-7)
+    check("after an ELBO iteration", slab=True)
+    for e in (eng, ref):
+        e.iterate(3)
+    for _ in range(3):
+        o.iterate()
+    check("fast iterations after an ELBO iteration", slab=True)
+    torch.cuda.synchronize()
+
+
+def test_simple_special_ties_sharded_rows():
+    """The shortcut with row-block sharding (row0 > 0): three shards of the N=1100 problem, statistics vectors summed by
+    hand between the phases (what the NCCL all-reduce does), iterations without ELBO -- against the single-rank engine."""
+    torch = _cuda()
+    import vimure_b200.synthetic as syn
+    from vimure_b200.model import shard_rows
+
+    L, N, K, W = 1, 1100, 2, 3
+    net = syn.StandardSBM(N=N, L=L, K=K, C=2, avg_degree=10, seed=10).build_X(mutuality=0.5, seed=20)
+    one, _, _ = _engine_and_oracle(net, net.R, None, K, tile_h=32)
+    engs = [_engine_and_oracle(net, net.R, None, K, tile_h=32, row0=r0, nloc=nl)[0]
+            for r0, nl in (shard_rows(N, W, r) for r in range(W))]
+    assert all(e.simple_mode for e in engs) and sum(e.P.U - e.P.n_cx for e in engs) == one.P.U - one.P.n_cx
+    F = one.C
+
+    def allreduce(attr):
+        tot = sum(getattr(e, attr) for e in engs)
+        for e in engs:
+            getattr(e, attr).copy_(tot)
+
+    allreduce("red3")  # the initial statistics were computed per shard
+    for it in range(5):
+        fl = F["VM_F_ELBO"] if it == 3 else 0
+        for e in engs:
+            e.phase("gamma")
+        allreduce("red1")
+        for e in engs:
+            e.phase("phi")
+        allreduce("red2")
+        for e in engs:
+            e.phase("rho", fl)
+        allreduce("red3")
+        for e in engs:
+            e.phase("finish", fl)
+        one.iterate(1, elbo_last=bool(fl))
+        p = one.params()
+        for e in engs:
+            q = e.params()
+            for k in ("gamma_shp", "gamma_rte", "phi_shp", "phi_rte", "nu_shp"):
+                np.testing.assert_allclose(q[k], p[k], rtol=1e-6, err_msg=f"{k} it{it}")
+            if fl:
+                np.testing.assert_allclose(e.elbo(), one.elbo(), rtol=1e-8)
+    slab = torch.cat([e.rho_slab() for e in engs], dim=1)
+    np.testing.assert_allclose(slab.cpu().numpy(), one.rho_slab().cpu().numpy(), rtol=1e-6, atol=1e-30)

@@ -64,7 +64,7 @@ class CaviEngine:
         self.rho = torch.empty(L, nloc, N, K, **f32)
         self.rho_valid = False
         # workspaces
-        self.layer_consts = z(L * (2 * K + 4))
+        self.layer_consts = z(L * (3 * K + 5))
         self.tab_p = torch.zeros(L * nloc * K, **f32)
         self.tab_q = torch.zeros(L * N * K, **f32)
         self.rowpart = torch.zeros(L * nloc * P.nct * K, **f32)
@@ -75,6 +75,11 @@ class CaviEngine:
         self.fixA = torch.zeros(L * M * K, dtype=torch.int64, device=dev)
         self.fixG = torch.zeros(L * M, dtype=torch.int64, device=dev)
         self.phi0 = z(L * K)
+        # simple special ties (see include/vimure_b200.h): patch source of the fast dense kernel, their phi0 part
+        self.simple_mode = bool(getattr(P, "simple_ok", False)) and not overlap
+        self.u_patch = torch.zeros(max(U, 1), K, **f32)
+        self.fixP = torch.zeros(L * K, dtype=torch.int64, device=dev)
+        self.simple_consts = z(2)
         assert _packing_const() == self.C["VM_SPECIAL_TIES_PER_BLOCK"]
         n_blk = max(P.n_gchunk, L * P.n_phichunk * K,
                     L * P.n_ublk * 8 * (3 + 2 * K) + P.nct * L * P.nrt + 128 + 2 * 64 + L * 64 * (3 + K)) + 64
@@ -94,6 +99,8 @@ class CaviEngine:
         c.eps = float(eps)
         c.alpha_eta, c.beta_eta = self.alpha_eta, self.beta_eta
         c.b_all = float(P.b_all)
+        c.simple_mode = int(self.simple_mode)
+        c.n_cx = int(getattr(P, "n_cx", U))
         # special/dense overlap: worthwhile once the special-tie kernel is long enough to matter
         self.aux_stream = None
         if overlap is None:
@@ -121,13 +128,13 @@ class CaviEngine:
 
         for name in ("u_lrow", "u_col", "u_ptr", "u_cnt", "u_m0", "u_x0", "u_xT0", "utile_ptr", "ucol_ptr", "ucol_perm", "e_u", "e_m", "e_x", "e_xT",
                      "e_flags", "f_u", "f_m", "f_x", "f_xT", "lay_eptr", "g0", "u_x0sum", "sp_chunk_blk", "g_chunk_ptr", "g_chunk_lm", "g_u", "g_x", "g_xT", "g_lm_cptr", "t_u", "t_lrow",
-                     "t_col", "t_x", "rep", "r_ptr", "r_m", "r_val", "c_ptr", "c_tie"):
+                     "t_col", "t_x", "rep", "r_ptr", "r_m", "r_val", "c_ptr", "c_tie", "cx_idx", "cx_ptr"):
             setattr(c, name, ptr(P.t[name]) if name in P.t else self._dummy.data_ptr())
         for name in ("u_logpr", "alpha_theta", "beta_theta", "alpha_lambda", "beta_lambda", "gamma_shp", "gamma_rte",
                      "phi_shp", "phi_rte", "nu", "G_theta", "E_theta", "Elog_theta", "G_lambda", "E_lambda",
                      "Elog_lambda", "GE_theta", "rho_u", "rho_u32", "delta_u", "rho", "layer_consts", "tab_p", "tab_q",
                      "rowpart", "colpart", "er_node", "colsum", "dev_flags", "fixA", "fixG", "phi0", "blkpart", "red1", "red2", "red3",
-                     "elbo_out"):
+                     "elbo_out", "u_patch", "fixP", "simple_consts"):
             setattr(c, name, ptr(getattr(self, name)))
         c.A = self.red3.data_ptr()  # A aliases the (all-reduced) statistics vector
         self._cref = ctypes.byref(c)
@@ -176,6 +183,18 @@ class CaviEngine:
             self.rho_u.copy_(pr)
             torch.add(pr, float(eps), out=self.u_logpr)  # log(pr_rho + EPS), model.py:559, without temporaries
             self.u_logpr.log_()
+            if self.simple_mode:
+                # patch entries of the simple ties: (-X, lo_1..lo_{K-1}), lo_k = log2((pr_k+EPS)/(pr_0+EPS)); the others
+                # are rewritten by the special-tie kernel before the dense kernel reads them
+                sm = P.t["u_simple"]
+                lp = self.u_logpr
+                self.u_patch.zero_()
+                self.u_patch[:, 0] = torch.where(sm, -P.t["u_x0sum"], torch.zeros_like(P.t["u_x0sum"]))
+                lo = ((lp[:, 1:] - lp[:, :1]) * 1.4426950408889634).to(torch.float32)
+                self.u_patch[:, 1:] = torch.where(sm[:, None], lo, torch.zeros_like(lo))
+                big = torch.full_like(lp[:, 0], 1e300)
+                self.simple_consts[0] = torch.where(sm, lp[:, 0], big).min().clamp(max=0.0)
+                self.simple_consts[1] = torch.where(sm, P.t["u_x0sum"], torch.zeros_like(P.t["u_x0sum"])).max().to(torch.float64)
         st = self._stream()
         _capi.check(self.lib.vm_refresh_cache(self._cref, st), "vm_refresh_cache")
         _capi.check(self.lib.vm_init_stats(self._cref, st), "vm_init_stats")
@@ -269,6 +288,9 @@ class CaviEngine:
         """Launch only the per-tie dense kernel (measurement hook, see vm_dense_only)."""
         _capi.check(self.lib.vm_dense_only(self._cref, int(flags), self._stream()), "vm_dense_only")
         self.n_launch += 1
+        if self.simple_mode:
+            # after an ELBO iteration u_patch still holds the posteriors of the iteration before: timing only
+            self.rho_valid = False
 
     def elbo(self):
         return float(self.elbo_out[0].item())

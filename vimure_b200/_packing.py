@@ -72,14 +72,21 @@ class Packed:
         raise AttributeError(k)
 
 
-def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64, mutuality=True, split_e0=True):
+def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64, mutuality=True, split_e0=True,
+         simple=None):
     """Build the packed layout.
 
     X_subs : (4, I) integer array-like (l, i, j, m);  X_vals : (I,) counts;  mask : masks.ReporterMask.
     mutuality / split_e0 : the gamma and phi passes only visit the entries with a reciprocal report (x^T > 0); for the
         others dz1_k = x, a constant (reference model.py:679-681, 693 with z2 = 0).  `split_e0=False` makes every entry
         visited (needed when a prior is so small that exp(E[log theta]) can underflow to 0, where model.py:692 gives 0).
+    simple : classify the special ties whose posterior the fast dense kernel can evaluate itself (default: yes, unless the
+        environment says VM_NO_SIMPLE=1 -- the A/B switch of the tests and tools).
     """
+    if simple is None:
+        import os
+
+        simple = os.environ.get("VM_NO_SIMPLE") != "1"
     dev = torch.device(device)
     nloc = N - row0 if nloc is None else int(nloc)
     _mark = _Trace(dev)
@@ -249,6 +256,22 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
         x0sum = torch.zeros(U, dtype=torch.float64, device=dev)
     P.t["g0"] = g0.contiguous()
     P.t["u_x0sum"] = x0sum.to(torch.float32).contiguous()
+    # ---- simple special ties (include/vimure_b200.h, vm_ctx.simple_mode): no entry with a reciprocal report, off the
+    # diagonal, in a full column tile.  On iterations without ELBO the fast dense kernel evaluates them and the special-tie
+    # kernel walks `cx_idx`, the others; `cx_idx` ends with the identity, for layers that cannot use the shortcut.
+    P.simple_ok = bool(simple and mask.kind == "ego" and K <= 4 and (N * K) % 4 == 0 and N >= TILE_W and P.tile_h <= 128
+                       and (split_e0 or not mutuality) and U > 0)
+    u_simple = torch.zeros(U, dtype=torch.bool, device=dev)
+    if P.simple_ok:
+        has_e1 = torch.zeros(U, dtype=torch.bool, device=dev)
+        if P.I1:
+            has_e1[P.t["e_u"][e1].to(torch.int64)] = True
+        u_simple = P.t["u_has_x"] & ~has_e1 & (u_i != u_col) & (u_col < (N // TILE_W) * TILE_W)
+    P.t["u_simple"] = u_simple
+    cx = torch.nonzero(~u_simple).flatten()
+    P.n_cx = int(cx.numel())
+    P.t["cx_idx"] = _i32(torch.cat([cx, torch.arange(U, device=dev, dtype=torch.int64)]))
+    P.t["cx_ptr"] = torch.searchsorted(u_l[cx].contiguous(), torch.arange(L + 1, device=dev, dtype=torch.int64)).contiguous()
     # layer ranges of the E1 entries (phi pass)
     lay_eptr = torch.searchsorted(e_l[e1].contiguous(), torch.arange(L + 1, device=dev, dtype=torch.int64))
     P.t["lay_eptr"] = lay_eptr.contiguous()

@@ -214,10 +214,14 @@ __device__ __forceinline__ void vm_alloc(bool mut, double x, double xT, double G
 }
 
 // layout of the per-layer constants block
-#define VM_LC_STRIDE(K) (2 * (K) + 4)
+#define VM_LC_STRIDE(K) (3 * (K) + 5)
 #define VM_LC_C(k) (k)                 // c_k: log2-odds intercept (k>=1), log2 weight of k=0 (k=0)
 #define VM_LC_D(K, k) ((K) + (k))      // d_k: slope in S
 #define VM_LC_SALL(K) (2 * (K))        // sum_m E[theta_lm]
 #define VM_LC_LP0(K) (2 * (K) + 1)     // log(1+EPS)
 #define VM_LC_LPK(K) (2 * (K) + 2)     // log(EPS)
 #define VM_LC_DEAD(K) (2 * (K) + 3)    // != 0: some closed-form row of this layer may underflow completely
+#define VM_LC_SIMPLE(K) (2 * (K) + 4)  // != 0: the fast dense kernel evaluates the simple special ties of this layer
+#define VM_LC_G(K, k) (2 * (K) + 5 + (k))  // (E[log lambda_k] - E[log lambda_0]) log2e
+// fixed-point scale of fixP (sums of rho_k X over the simple ties of a layer: up to ~1e7)
+#define VM_FIXP_SCALE 1073741824.0

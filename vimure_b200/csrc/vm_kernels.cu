@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(1024) k_phi_finish(const __grid_constant__ vm_
   const int l = blockIdx.x;
   const int64_t M = c.M;
   double acc[K + 1];
-  double emax = 0.0;
+  double emax = 0.0, nelmin = -1e300;  // max E[theta]; max of -E[log theta]
 #pragma unroll
   for (int k = 0; k <= K; ++k) acc[k] = 0.0;
   for (int64_t m = threadIdx.x; m < M; m += 1024) {
@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(1024) k_phi_finish(const __grid_constant__ vm_
     for (int k = 0; k < K; ++k) acc[k] += et * c.A[(l * M + m) * K + k];
     acc[K] += et;
     emax = fmax(emax, et);
+    if (c.simple_mode) nelmin = fmax(nelmin, -c.Elog_theta[l * M + m]);
   }
 #pragma unroll
   for (int k = 0; k <= K; ++k) {
@@ -233,12 +234,16 @@ __global__ void __launch_bounds__(1024) k_phi_finish(const __grid_constant__ vm_
     if (threadIdx.x == 0) rte_s[k] = v;
   }
   emax = block_max<1024>(emax, sm);
+  if (c.simple_mode) {
+    nelmin = block_max<1024>(nelmin, sm);
+    if (threadIdx.x < K) c.fixP[l * K + threadIdx.x] = 0;
+  }
   if (c.r_mode == VM_R_EGO)
     for (int64_t t = threadIdx.x; t < M * K; t += 1024) c.fixA[(int64_t)l * M * K + t] = 0;
   for (int64_t t = threadIdx.x; t < M; t += 1024) c.fixG[(int64_t)l * M + t] = 0;  // consumed by k_gamma_reduce already
   if (threadIdx.x == 0) {
     if (l == 0) c.dev_flags[0] = 0;
-    double El[K];
+    double El[K], Ell[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const double shp = c.alpha_lambda[l * K + k] + c.red2[l * K + k];
@@ -246,6 +251,7 @@ __global__ void __launch_bounds__(1024) k_phi_finish(const __grid_constant__ vm_
       c.phi_shp[l * K + k] = shp;
       c.phi_rte[l * K + k] = rte;
       const double el = vm_digamma(shp) - log(rte);
+      Ell[k] = el;
       c.Elog_lambda[l * K + k] = el;
       c.G_lambda[l * K + k] = exp(el);
       El[k] = shp / rte;
@@ -266,6 +272,16 @@ __global__ void __launch_bounds__(1024) k_phi_finish(const __grid_constant__ vm_
     // no closed-form row can underflow completely if even the largest possible S keeps k=0 alive
     const double s_max = (c.r_mode == VM_R_EGO) ? 2.0 * emax : rte_s[K];
     lc[VM_LC_DEAD(K)] = (c.r_mode == VM_R_CSR || lp0 - s_max * El[0] < VM_DEAD_LN + 8.0) ? 1.0 : 0.0;
+    // simple special ties (see vm_ctx.simple_mode): evaluated by the fast dense kernel only if none of them can underflow
+    // completely: log-weight of k=0 >= min log(pr_0+EPS) - S_max E[lambda_0] + X_max min(0, min E[log theta] + E[log lambda_0])
+#pragma unroll
+    for (int k = 0; k < K; ++k) lc[VM_LC_G(K, k)] = (Ell[k] - Ell[0]) * VM_LOG2E;
+    bool simple_ok = false;
+    if (c.simple_mode && c.r_mode == VM_R_EGO && c.may_dead == 0 && lc[VM_LC_DEAD(K)] == 0.0) {
+      const double lw0 = c.simple_consts[0] - s_max * El[0] + c.simple_consts[1] * fmin(0.0, -nelmin + Ell[0]);
+      simple_ok = lw0 >= VM_DEAD_LN + 8.0;
+    }
+    lc[VM_LC_SIMPLE(K)] = simple_ok ? 1.0 : 0.0;
   }
 }
 
@@ -425,7 +441,10 @@ __device__ __forceinline__ void vm_fix_accumulate(unsigned long long* fix_l, boo
 #ifndef VM_SPECIAL_MINBLK
 #define VM_SPECIAL_MINBLK 3
 #endif
-template <int K, bool ELBO, int RMODE>
+// LIST (ego mask, no ELBO): in the layers whose simple ties the fast dense kernel evaluates (layer constant VM_LC_SIMPLE)
+// the kernel walks `cx_idx`, the special ties that are not simple, instead of every special tie, and also writes the fp32
+// posterior into `u_patch`, the dense kernel's patch source on such iterations.
+template <int K, bool ELBO, int RMODE, bool LIST = false>
 __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) : 2)) k_special(const __grid_constant__ vm_ctx c, double* part, int chunk) {
   __shared__ double s_Gl[K], s_Ell[K], s_El[K];
   const int l = blockIdx.y;
@@ -467,7 +486,15 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
   for (int k = 0; k < K; ++k) dsum[k] = p0[k] = 0.0;
 
   constexpr int TPT = VM_SPECIAL_TIES_PER_BLOCK / 256;
-  const int ub = u0 + blk * VM_SPECIAL_TIES_PER_BLOCK + threadIdx.x;
+  // positions [base, end): tie indices themselves, or (LIST) positions in cx_idx
+  // (a layer whose simple ties cannot be left to the dense kernel walks the identity appended to cx_idx, same code)
+  int base = u0, end = u1;
+  if (LIST) {
+    const bool safe = lc[VM_LC_SIMPLE(K)] != 0.0;
+    base = safe ? (int)c.cx_ptr[l] : (int)c.n_cx + u0;
+    end = safe ? (int)c.cx_ptr[l + 1] : (int)c.n_cx + u1;
+  }
+  const int ub = base + blk * VM_SPECIAL_TIES_PER_BLOCK + threadIdx.x;
   // per-tie data of the first tie (incl. its first X entry, stored inline); the next tie's is fetched while the
   // current one is processed, so only ONE dependent gather level (tables indexed by node / reporter) is exposed
   int n_lrow = 0, n_col = 0, n_m0 = 0, n_cnt = 0;
@@ -475,21 +502,27 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
   double n_logpr[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) n_logpr[k] = 0.0;
-  if (ub < u1) {
-    n_lrow = c.u_lrow[ub];
-    n_col = c.u_col[ub];
-    n_cnt = c.u_cnt[ub];
-    n_m0 = c.u_m0[ub];
-    n_x0 = c.u_x0[ub];
-    n_xT0 = c.u_xT0[ub];
-    n_x0s = c.u_x0sum[ub];
+  int n_u = ub, nn_u = 0;  // (LIST) tie whose data sits in n_*; the tie after it, fetched one step earlier still
+  if (ub < end) {
+    if (LIST) {
+      n_u = c.cx_idx[ub];
+      if (ub + 256 < end) nn_u = c.cx_idx[ub + 256];
+    }
+    n_lrow = c.u_lrow[n_u];
+    n_col = c.u_col[n_u];
+    n_cnt = c.u_cnt[n_u];
+    n_m0 = c.u_m0[n_u];
+    n_x0 = c.u_x0[n_u];
+    n_xT0 = c.u_xT0[n_u];
+    n_x0s = c.u_x0sum[n_u];
 #pragma unroll
-    for (int k = 0; k < K; ++k) n_logpr[k] = c.u_logpr[(size_t)ub * K + k];
+    for (int k = 0; k < K; ++k) n_logpr[k] = c.u_logpr[(size_t)n_u * K + k];
   }
 #pragma unroll 1
   for (int it = 0; it < TPT; ++it) {
-    const int u = ub + it * 256;
-    const bool valid = u < u1;
+    const int pos = ub + it * 256;
+    const bool valid = pos < end;
+    const int u = LIST ? n_u : pos;
     // ---- stage A (per thread): tie data, S, prior; entries of SHORT ties
     int lrow = 0, i = 0, j = 0, cnt = 0;
     int64_t e0 = 0;
@@ -510,8 +543,13 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
       x0s = (double)n_x0s;
 #pragma unroll
       for (int k = 0; k < K; ++k) logpr[k] = n_logpr[k];
-      const int un = u + 256;
-      if (it + 1 < TPT && un < u1) {
+      const int posn = pos + 256;
+      if (it + 1 < TPT && posn < end) {
+        const int un = LIST ? nn_u : posn;
+        if (LIST) {
+          n_u = un;
+          if (it + 2 < TPT && posn + 256 < end) nn_u = c.cx_idx[posn + 256];
+        }
         n_lrow = c.u_lrow[un];
         n_col = c.u_col[un];
         n_cnt = c.u_cnt[un];
@@ -660,6 +698,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
           o_dk[k] = rho[k] - fv;
           ru[k] = rho[k];
           ru32[k] = (float)rho[k];
+          if (LIST) c.u_patch[(size_t)u * K + k] = (float)rho[k];
           dsum[k] += o_dk[k];
         }
         o_resid = (alive_u ? 1 : 0) - (dead ? 0 : 1);
@@ -988,9 +1027,17 @@ struct FastCfg {
 #ifndef VM_FAST_MINBLK2
 #define VM_FAST_MINBLK2 4
 #endif
-template <int K, bool ELBO>
+// SIMPLE (no ELBO): in the layers flagged VM_LC_SIMPLE the patch source is `u_patch`, whose entries of SIMPLE special ties
+// hold (-X, lo_1..lo_{K-1}) instead of a posterior: the warp evaluates those ties itself (see vm_ctx.simple_mode) from
+// the row term without its constant (ps2), the staged column term, lo and X g_k -- all O(1), so fp32 does not cancel --
+// and accounts for them exactly as the special-tie kernel would: (posterior - closed form) into the fixed-point
+// per-reporter corrections (row reporter: one atomic per row segment after an integer warp reduction) and rho_k X into fixP.
+template <int K, bool ELBO, bool SIMPLE = false>
 __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_MINBLK2 : 2) k_dense_fast(const __grid_constant__ vm_ctx c, double* catpart, int rt0, int rtn) {
+  static_assert(!(SIMPLE && ELBO), "the ELBO iterations evaluate every special tie in fp64");
   constexpr int NCH = DenseCfg<K>::NCH, TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32, CAPW = FastCfg<K>::CAPW;
+  __shared__ float ps2[SIMPLE ? K - 1 : 1][SIMPLE ? VM_FAST_MAX_TILE_H : 1];
+  __shared__ unsigned char ract[SIMPLE ? VM_FAST_MAX_TILE_H : 1], qact[SIMPLE ? TW : 1];
   __shared__ __align__(16) float qs[K - 1][TW];
   __shared__ __align__(16) float colbuf[K - 1][TW];
   __shared__ __align__(16) float stage[NW][StageCfg<K>::FLOATS];
@@ -1010,6 +1057,15 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
   const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
   const float lp0 = (float)lc[VM_LC_LP0(K)], lpk = (float)lc[VM_LC_LPK(K)], epsf = (float)c.eps;
   double cat = 0.0;
+  const bool simple_on = SIMPLE && lc[VM_LC_SIMPLE(K)] != 0.0;
+  const float* patch_src = simple_on ? c.u_patch : c.rho_u32;
+  float gk[K], p0acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    gk[k] = simple_on ? (float)lc[VM_LC_G(K, k)] : 0.f;
+    p0acc[k] = 0.f;
+  }
+  unsigned long long* fix_l = reinterpret_cast<unsigned long long*>(c.fixA) + (int64_t)l * c.M * K;
   // ---- phase 0: everything the row loop reads from global memory, once per CTA
   for (int idx = tid; idx < TW; idx += VM_DENSE_THREADS) {
 #pragma unroll
@@ -1017,6 +1073,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
       qs[k - 1][idx] = __ldg(&c.tab_q[((int64_t)l * N + jt + idx) * K + k]);
       colbuf[k - 1][idx] = 0.f;
     }
+    if (simple_on) qact[idx] = c.er_node[(int64_t)l * N + jt + idx] > 0.0 ? 1 : 0;  // column node is an active reporter
   }
   for (int r = tid; r < nrows; r += VM_DENSE_THREADS) {
     const int64_t lrow = (int64_t)l * nloc + i_lo + r;
@@ -1024,6 +1081,12 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
     for (int k = 1; k < K; ++k) ps[k - 1][r] = __ldg(&c.tab_p[lrow * K + k]);
     tp0[r] = __ldg(&c.utile_ptr[lrow * nct + ct]);
     tp1[r] = __ldg(&c.utile_ptr[lrow * nct + ct + 1]);
+    if (simple_on) {
+      const double er = c.er_node[(int64_t)l * N + (int)c.row0 + i_lo + r];
+      ract[r] = er > 0.0 ? 1 : 0;
+#pragma unroll
+      for (int k = 1; k < K; ++k) ps2[k - 1][r] = (float)(-er * lc[VM_LC_D(K, k)]);  // tab_p without its constant c_k
+    }
   }
   __syncthreads();
   // ---- phase 1: stage the patch data of this warp's rows asynchronously
@@ -1035,7 +1098,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
       for (int e = lane; e < take; e += 32) {
         vm_cp_async4(&pcol[warp][off + e], &c.u_col[ua + e]);
 #pragma unroll
-        for (int k = 0; k < K; ++k) vm_cp_async4(&pval[warp][off + e][k], &c.rho_u32[(int64_t)(ua + e) * K + k]);
+        for (int k = 0; k < K; ++k) vm_cp_async4(&pval[warp][off + e][k], &patch_src[(int64_t)(ua + e) * K + k]);
       }
       off += take;
     }
@@ -1121,15 +1184,62 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
     __syncwarp();
     const int ua = tp0[r], n = tp1[r] - ua;
     const int take = min(n, CAPW - off);
-    for (int e = lane; e < take; e += 32) {
-      float* d = rowdst + (int64_t)pcol[warp][off + e] * K;
+    long long rq[K];  // this lane's share of the row reporter's correction (fixed point)
 #pragma unroll
-      for (int k = 0; k < K; ++k) d[k] = pval[warp][off + e][k];
+    for (int k = 0; k < K; ++k) rq[k] = 0ll;
+    for (int e = lane; e < n; e += 32) {
+      int col;
+      float v[K];
+      if (e < take) {
+        col = pcol[warp][off + e];
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = pval[warp][off + e][k];
+      } else {  // more special ties than the per-warp stage holds
+        col = c.u_col[ua + e];
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = patch_src[(int64_t)(ua + e) * K + k];
+      }
+      float* d = rowdst + (int64_t)col * K;
+      if (SIMPLE && simple_on && v[0] < 0.f) {
+        // a simple special tie: (-X, lo_1, ..): evaluate it, and the closed form the sweep above counted for it
+        const float X = -v[0];
+        const int cj = col - jt;
+        float es[K], ef[K], s = 0.f, sf = 0.f;
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+          const float qk = qs[k - 1][cj];
+          es[k] = vm_ex2(fminf(ps2[k - 1][r] + qk + v[k] + X * gk[k], VM_CLAMP_LOG2));
+          s += es[k];
+          ef[k] = vm_ex2(fminf(__fadd_rn(p[k], qk), VM_CLAMP_LOG2));  // same operations as the sweep: same bits
+          sf = (k == 1) ? ef[k] : __fadd_rn(sf, ef[k]);
+        }
+        const float inv = vm_rcp(1.f + s), invf = vm_rcp(__fadd_rn(1.f, sf));
+        d[0] = inv;
+        p0acc[0] += inv * X;
+        const bool act_j = qact[cj] != 0, act_i = ract[r] != 0;
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+          const float rk = es[k] * inv, fk = __fmul_rn(ef[k], invf);
+          d[k] = rk;
+          p0acc[k] += rk * X;
+          const long long q = __double2ll_rn(((double)rk - (double)fk) * VM_FIX_SCALE);
+          if (act_j && q != 0) atomicAdd(fix_l + (int64_t)col * K + k, (unsigned long long)q);
+          if (act_i) rq[k] += q;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) d[k] = v[k];
+      }
     }
-    for (int e = take + lane; e < n; e += 32) {
-      const int col = c.u_col[ua + e];
+    if (SIMPLE && simple_on) {
 #pragma unroll
-      for (int k = 0; k < K; ++k) rowdst[(int64_t)col * K + k] = c.rho_u32[(int64_t)(ua + e) * K + k];
+      for (int k = 1; k < K; ++k) {
+        long long t = rq[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0 && t != 0)
+          atomicAdd(fix_l + (int64_t)((int)c.row0 + i_lo + r) * K + k, (unsigned long long)t);
+      }
     }
     off += take;
   }
@@ -1163,6 +1273,15 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
   if (ELBO) {
     const double v = block_sum<VM_DENSE_THREADS>(cat, sm_red);
     if (tid == 0) catpart[((int64_t)l * nrt + rt) * nct + ct] = v;
+  }
+  if (SIMPLE && simple_on) {  // rho_k X of the simple ties of this tile: their part of the next phi-shape sums (phi0)
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double v = block_sum<VM_DENSE_THREADS>((double)p0acc[k], sm_red);
+      if (tid == 0 && v != 0.0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(c.fixP) + l * K + k,
+                  (unsigned long long)__double2ll_rn(v * VM_FIXP_SCALE));
+    }
   }
 }
 
@@ -1466,7 +1585,11 @@ __global__ void __launch_bounds__(256) k_sums_reduce(const __grid_constant__ vm_
     for (int k = 0; k < K; ++k) {
       double v = (threadIdx.x < VM_S1_BLOCKS) ? s1[((int64_t)l * VM_S1_BLOCKS + threadIdx.x) * (3 + K) + 3 + k] : 0.0;
       v = block_sum<256>(v, sm);
-      if (threadIdx.x == 0) c.phi0[l * K + k] = v;
+      if (threadIdx.x == 0) {
+        // + the simple ties the fast dense kernel evaluated this iteration (0 on every other iteration)
+        if (c.simple_mode && !(flags & VM_F_INIT)) v += (double)c.fixP[l * K + k] * (1.0 / VM_FIXP_SCALE);
+        c.phi0[l * K + k] = v;
+      }
     }
 }
 
@@ -1603,14 +1726,27 @@ static int check_ctx(const vm_ctx* c) {
       return VM_EINVAL;                           \
   }
 
+// does this rho update use the fast dense kernel (for the tiles that qualify on the device)?
+template <int K>
+static bool dense_fast_eligible(const vm_ctx* c, int flags) {
+  return K <= 4 && !(flags & VM_F_NO_STORE) && c->r_mode != VM_R_CSR && ((c->N * K) & 3) == 0 && c->N >= c->tile_w &&
+         c->tile_h <= VM_FAST_MAX_TILE_H;
+}
+// ... and do the fast dense kernel / the list mode of the special-tie kernel handle the simple special ties in it?
+template <int K>
+static bool simple_iteration(const vm_ctx* c, int flags) {
+  return c->simple_mode != 0 && c->r_mode == VM_R_EGO && !(flags & VM_F_ELBO) && c->n_chunks == 0 &&
+         dense_fast_eligible<K>(c, flags);
+}
+
 template <int K>
 static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, int rtn) {
   if (rtn <= 0) return 0;
   const dim3 grid((unsigned)c->nct, (unsigned)(c->L * rtn));
   const bool elbo = flags & VM_F_ELBO, store = !(flags & VM_F_NO_STORE), csr = c->r_mode == VM_R_CSR;
   double* cp = region_cat(c);
-  const bool fast = K <= 4 && store && !csr && ((c->N * K) & 3) == 0 && c->N >= c->tile_w &&
-                    c->tile_h <= VM_FAST_MAX_TILE_H;
+  const bool fast = dense_fast_eligible<K>(c, flags);
+  const bool simple = simple_iteration<K>(c, flags);
   // The general kernel only has the tiles the fast one leaves (the partial last column tile: 157 of 6280 CTAs at config 3,
   // each a serial sweep of its rows, 32 us): it goes to the caller's aux stream, forked from and joined back into `st`,
   // so that it runs under the fast kernel instead of after it.  The two write disjoint tiles and disjoint partial slots.
@@ -1625,10 +1761,13 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, in
     cudaEventRecord(ev_fork, st);
     cudaStreamWaitEvent(aux, ev_fork, 0);
   }
-  if (fast && !side) {
-    if (elbo) k_dense_fast<(K <= 4 ? K : 2), true><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, rt0, rtn);
-    else k_dense_fast<(K <= 4 ? K : 2), false><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, rt0, rtn);
-  }
+#define LF()                                                                                                   \
+  do {                                                                                                         \
+    if (elbo) k_dense_fast<(K <= 4 ? K : 2), true><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, rt0, rtn);        \
+    else if (simple) k_dense_fast<(K <= 4 ? K : 2), false, true><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, rt0, rtn); \
+    else k_dense_fast<(K <= 4 ? K : 2), false><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, rt0, rtn);            \
+  } while (0)
+  if (fast && !side) LF();
   int rc = 0;
 #define LD(E, S, C) k_dense<K, E, S, C><<<grid, VM_DENSE_THREADS, 0, sg>>>(*c, cp, fast ? 1 : 0, rt0, rtn)
   if (csr) {
@@ -1641,13 +1780,13 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, in
   }
 #undef LD
   if (side) {
-    if (elbo) k_dense_fast<(K <= 4 ? K : 2), true><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, rt0, rtn);
-    else k_dense_fast<(K <= 4 ? K : 2), false><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, rt0, rtn);
+    LF();
     cudaEventRecord(ev_join, aux);
     cudaStreamWaitEvent(st, ev_join, 0);
     cudaEventDestroy(ev_fork);  // destruction is deferred by the runtime until the events have completed
     cudaEventDestroy(ev_join);
   }
+#undef LF
   return rc;
 }
 
@@ -1657,7 +1796,9 @@ static int launch_special(const vm_ctx* c, int flags, cudaStream_t st, int chunk
   const dim3 grid((unsigned)gridx, (unsigned)c->L);
   const bool elbo = flags & VM_F_ELBO;
 #define LS(E, M) k_special<K, E, M><<<grid, 256, 0, st>>>(*c, region_u(c), chunk)
-  if (c->r_mode == VM_R_EGO) {
+  if (chunk < 0 && simple_iteration<K>(c, flags)) {
+    k_special<K, false, VM_R_EGO, true><<<grid, 256, 0, st>>>(*c, region_u(c), chunk);
+  } else if (c->r_mode == VM_R_EGO) {
     if (elbo) LS(true, VM_R_EGO); else LS(false, VM_R_EGO);
   } else if (c->r_mode == VM_R_ALL) {
     if (elbo) LS(true, VM_R_ALL); else LS(false, VM_R_ALL);
