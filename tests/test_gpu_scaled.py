@@ -235,6 +235,22 @@ def test_simple_special_ties_sharded_rows():
             for r0, nl in (shard_rows(N, W, r) for r in range(W))]
     assert all(e.simple_mode for e in engs) and sum(e.P.U - e.P.n_cx for e in engs) == one.P.U - one.P.n_cx
     F = one.C
+    # the helper draws the priors of a shard's ties from one stream: key them by the GLOBAL tie instead, so that every
+    # decomposition starts from the same state
+    rs = np.random.RandomState(3).random_sample
+    st = dict(gamma_shp=0.1 * rs((L, N)) + 0.1, phi_shp=10.0 * rs((L, K)) + 10.0, gamma_rte=0.1 * rs((L, N)) + 0.1,
+              phi_rte=10.0 * rs((L, K)) + 10.0, nu_shp=0.5 * rs(1)[0] + 0.5)
+    table = 1 + 0.01 * np.random.RandomState(4).random_sample((1 << 16, K))
+    for e in [one] + engs:
+        P = e.P
+        keep = (P.t["u_has_x"] & P.t["u_reported"]).cpu().numpy()
+        flat = P.t["u_gflat"].cpu().numpy()
+        pr_u = np.zeros((P.U, K))
+        pr_u[:, 0] = 1.0
+        pr = table[(flat[keep] * 2654435761) % (1 << 16)]
+        pr_u[keep] = pr / pr.sum(axis=1)[:, None]
+        e.set_state(st["gamma_shp"], st["gamma_rte"], st["phi_shp"], st["phi_rte"], st["nu_shp"],
+                    PRIORS["beta_eta"] + float(np.sum(net.X.vals)), pr_u, 1e-12)
 
     def allreduce(attr):
         tot = sum(getattr(e, attr) for e in engs)
