@@ -119,13 +119,21 @@ typedef struct vm_ctx {
      lo_k = log2((pr_k+EPS)/(pr_0+EPS)), X = sum of its x: the same separable form as a tie without data, plus a per-tie
      constant and a per-layer multiple of X.  On iterations that store the slab and do not evaluate the ELBO the fast
      dense kernel evaluates these ties itself (fp32, terms of magnitude O(1): no cancellation) and the special-tie kernel
-     only visits the others (`cx_idx`); every other iteration runs the special-tie kernel over all special ties, as
+     only visits the others (`cx_idx`, `cx_*`); every other iteration runs the special-tie kernel over all special ties, as
      does any layer for which k_phi_finish cannot rule out a completely underflowed tie (layer constant VM_LC_SIMPLE). */
   int64_t simple_mode;      /* 1 = enabled (EGO mask, K <= 4, fast dense kernel eligible, serial special/dense launch) */
   int64_t n_cx;             /* special ties that are NOT simple */
-  const int32_t* cx_idx;    /* [n_cx + U] their indices, ascending; then the identity 0..U-1 (what a layer that cannot
-                               use the shortcut walks instead, through the same code) */
-  const int64_t* cx_ptr;    /* [L+1] range of cx_idx[0..n_cx) of every layer */
+  const int32_t* cx_idx;    /* [n_cx] their indices, ascending */
+  const int64_t* cx_ptr;    /* [L+1] range of cx_idx of every layer */
+  /* compacted copies of the per-tie arrays for those ties (coalesced reads in the list mode of the special-tie kernel) */
+  const int32_t* cx_lrow;   /* [n_cx] */
+  const int32_t* cx_col;
+  const int32_t* cx_cnt;
+  const int32_t* cx_m0;
+  const float* cx_x0;
+  const float* cx_xT0;
+  const float* cx_x0sum;
+  const double* cx_logpr;   /* [n_cx*K] */
   float* u_patch;           /* [U*K] patch source of the fast dense kernel on such iterations: (-X, lo_1..lo_{K-1}) for a
                                simple tie (constant over a fit), the fp32 posterior (written by the special-tie kernel) else */
   const double* simple_consts; /* [2] min over the simple ties of log(pr_0+EPS); max X */

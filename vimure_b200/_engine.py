@@ -80,6 +80,7 @@ class CaviEngine:
         self.u_patch = torch.zeros(max(U, 1), K, **f32)
         self.fixP = torch.zeros(L * K, dtype=torch.int64, device=dev)
         self.simple_consts = z(2)
+        self.cx_logpr = z(max(int(getattr(P, "n_cx", 0)), 1) if self.simple_mode else 1, K)
         assert _packing_const() == self.C["VM_SPECIAL_TIES_PER_BLOCK"]
         n_blk = max(P.n_gchunk, L * P.n_phichunk * K,
                     L * P.n_ublk * 8 * (3 + 2 * K) + P.nct * L * P.nrt + 128 + 2 * 64 + L * 64 * (3 + K)) + 64
@@ -128,13 +129,14 @@ class CaviEngine:
 
         for name in ("u_lrow", "u_col", "u_ptr", "u_cnt", "u_m0", "u_x0", "u_xT0", "utile_ptr", "ucol_ptr", "ucol_perm", "e_u", "e_m", "e_x", "e_xT",
                      "e_flags", "f_u", "f_m", "f_x", "f_xT", "lay_eptr", "g0", "u_x0sum", "sp_chunk_blk", "g_chunk_ptr", "g_chunk_lm", "g_u", "g_x", "g_xT", "g_lm_cptr", "t_u", "t_lrow",
-                     "t_col", "t_x", "rep", "r_ptr", "r_m", "r_val", "c_ptr", "c_tie", "cx_idx", "cx_ptr"):
+                     "t_col", "t_x", "rep", "r_ptr", "r_m", "r_val", "c_ptr", "c_tie", "cx_idx", "cx_ptr", "cx_lrow", "cx_col", "cx_cnt",
+                     "cx_m0", "cx_x0", "cx_xT0", "cx_x0sum"):
             setattr(c, name, ptr(P.t[name]) if name in P.t else self._dummy.data_ptr())
         for name in ("u_logpr", "alpha_theta", "beta_theta", "alpha_lambda", "beta_lambda", "gamma_shp", "gamma_rte",
                      "phi_shp", "phi_rte", "nu", "G_theta", "E_theta", "Elog_theta", "G_lambda", "E_lambda",
                      "Elog_lambda", "GE_theta", "rho_u", "rho_u32", "delta_u", "rho", "layer_consts", "tab_p", "tab_q",
                      "rowpart", "colpart", "er_node", "colsum", "dev_flags", "fixA", "fixG", "phi0", "blkpart", "red1", "red2", "red3",
-                     "elbo_out", "u_patch", "fixP", "simple_consts"):
+                     "elbo_out", "u_patch", "fixP", "simple_consts", "cx_logpr"):
             setattr(c, name, ptr(getattr(self, name)))
         c.A = self.red3.data_ptr()  # A aliases the (all-reduced) statistics vector
         self._cref = ctypes.byref(c)
@@ -163,6 +165,8 @@ class CaviEngine:
         n = 2 + 3 + 1 + (0 if csr else 1) + n_special + nch * ((1 if fast else 0) + 1) + (1 if ego else 0) + 1 + 2 + 1
         if elbo:
             n += 1 + (1 if self.mutuality else 0)
+        elif self.simple_mode and fast and not self.ctx.n_chunks:
+            n += 1  # the special-tie kernel is launched twice (layers that take the simple-tie shortcut / that cannot)
         return n
 
     # ------------------------------------------------------------------ state
@@ -188,6 +192,8 @@ class CaviEngine:
                 # are rewritten by the special-tie kernel before the dense kernel reads them
                 sm = P.t["u_simple"]
                 lp = self.u_logpr
+                if P.n_cx:
+                    torch.index_select(lp, 0, P.t["cx_idx"].to(torch.int64), out=self.cx_logpr)
                 self.u_patch.zero_()
                 self.u_patch[:, 0] = torch.where(sm, -P.t["u_x0sum"], torch.zeros_like(P.t["u_x0sum"]))
                 lo = ((lp[:, 1:] - lp[:, :1]) * 1.4426950408889634).to(torch.float32)

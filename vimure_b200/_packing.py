@@ -258,7 +258,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
     P.t["u_x0sum"] = x0sum.to(torch.float32).contiguous()
     # ---- simple special ties (include/vimure_b200.h, vm_ctx.simple_mode): no entry with a reciprocal report, off the
     # diagonal, in a full column tile.  On iterations without ELBO the fast dense kernel evaluates them and the special-tie
-    # kernel walks `cx_idx`, the others; `cx_idx` ends with the identity, for layers that cannot use the shortcut.
+    # kernel walks `cx_idx`, the others, through compacted copies of their per-tie arrays.
     P.simple_ok = bool(simple and mask.kind == "ego" and K <= 4 and (N * K) % 4 == 0 and N >= TILE_W and P.tile_h <= 128
                        and (split_e0 or not mutuality) and U > 0)
     u_simple = torch.zeros(U, dtype=torch.bool, device=dev)
@@ -270,8 +270,11 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
     P.t["u_simple"] = u_simple
     cx = torch.nonzero(~u_simple).flatten()
     P.n_cx = int(cx.numel())
-    P.t["cx_idx"] = _i32(torch.cat([cx, torch.arange(U, device=dev, dtype=torch.int64)]))
+    P.t["cx_idx"] = _i32(cx)
     P.t["cx_ptr"] = torch.searchsorted(u_l[cx].contiguous(), torch.arange(L + 1, device=dev, dtype=torch.int64)).contiguous()
+    if P.simple_ok:  # compacted copies of the per-tie arrays: the list mode of the special-tie kernel reads them coalesced
+        for name in ("lrow", "col", "cnt", "m0", "x0", "xT0", "x0sum"):
+            P.t["cx_" + name] = P.t["u_" + name][cx].contiguous()
     # layer ranges of the E1 entries (phi pass)
     lay_eptr = torch.searchsorted(e_l[e1].contiguous(), torch.arange(L + 1, device=dev, dtype=torch.int64))
     P.t["lay_eptr"] = lay_eptr.contiguous()

@@ -441,10 +441,13 @@ __device__ __forceinline__ void vm_fix_accumulate(unsigned long long* fix_l, boo
 #ifndef VM_SPECIAL_MINBLK
 #define VM_SPECIAL_MINBLK 3
 #endif
-// LIST (ego mask, no ELBO): in the layers whose simple ties the fast dense kernel evaluates (layer constant VM_LC_SIMPLE)
-// the kernel walks `cx_idx`, the special ties that are not simple, instead of every special tie, and also writes the fp32
-// posterior into `u_patch`, the dense kernel's patch source on such iterations.
-template <int K, bool ELBO, int RMODE, bool LIST = false>
+// LIST (ego mask, no ELBO), for the iterations on which the fast dense kernel evaluates the simple special ties of the
+// layers flagged VM_LC_SIMPLE.  LIST = 1 handles those layers: it walks the special ties that are NOT simple through
+// their compacted copies of the per-tie arrays (`cx_*`: coalesced; walking the original arrays at half density tripled
+// the DRAM bytes read per tie, profiles/ncu_r1_simple_dense_fast_special.txt) and also writes the fp32 posterior into
+// `u_patch`, the dense kernel's patch source on such iterations.  LIST = 2 handles the other layers exactly like LIST = 0.
+// Each block of a (layer, block) grid does its work in exactly one of the two launches and returns in the other.
+template <int K, bool ELBO, int RMODE, int LIST = 0>
 __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) : 2)) k_special(const __grid_constant__ vm_ctx c, double* part, int chunk) {
   __shared__ double s_Gl[K], s_Ell[K], s_El[K];
   const int l = blockIdx.y;
@@ -474,6 +477,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
   const float* tabp = c.tab_p;
   unsigned long long* fix_l = reinterpret_cast<unsigned long long*>(c.fixA) + (int64_t)l * M * K;
   const float cat_lp0 = (float)lc[VM_LC_LP0(K)], cat_lpk = (float)lc[VM_LC_LPK(K)], epsf = (float)eps;
+  if (LIST != 0 && (lc[VM_LC_SIMPLE(K)] != 0.0) != (LIST == 1)) return;  // the other launch owns this layer
   if (threadIdx.x < K) {
     s_Gl[threadIdx.x] = c.G_lambda[l * K + threadIdx.x];
     s_Ell[threadIdx.x] = c.Elog_lambda[l * K + threadIdx.x];
@@ -487,12 +491,10 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
 
   constexpr int TPT = VM_SPECIAL_TIES_PER_BLOCK / 256;
   // positions [base, end): tie indices themselves, or (LIST) positions in cx_idx
-  // (a layer whose simple ties cannot be left to the dense kernel walks the identity appended to cx_idx, same code)
-  int base = u0, end = u1;
-  if (LIST) {
-    const bool safe = lc[VM_LC_SIMPLE(K)] != 0.0;
-    base = safe ? (int)c.cx_ptr[l] : (int)c.n_cx + u0;
-    end = safe ? (int)c.cx_ptr[l + 1] : (int)c.n_cx + u1;
+  int base = u0, end = u1;  // positions: tie indices, or (LIST = 1) positions in the compacted arrays
+  if (LIST == 1) {
+    base = (int)c.cx_ptr[l];
+    end = (int)c.cx_ptr[l + 1];
   }
   const int ub = base + blk * VM_SPECIAL_TIES_PER_BLOCK + threadIdx.x;
   // per-tie data of the first tie (incl. its first X entry, stored inline); the next tie's is fetched while the
@@ -502,27 +504,33 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
   double n_logpr[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) n_logpr[k] = 0.0;
-  int n_u = ub, nn_u = 0;  // (LIST) tie whose data sits in n_*; the tie after it, fetched one step earlier still
+  // per-tie arrays: the originals indexed by tie, or (LIST = 1) their compacted copies indexed by position
+  const int32_t* a_lrow = (LIST == 1) ? c.cx_lrow : c.u_lrow;
+  const int32_t* a_col = (LIST == 1) ? c.cx_col : c.u_col;
+  const int32_t* a_cnt = (LIST == 1) ? c.cx_cnt : c.u_cnt;
+  const int32_t* a_m0 = (LIST == 1) ? c.cx_m0 : c.u_m0;
+  const float* a_x0 = (LIST == 1) ? c.cx_x0 : c.u_x0;
+  const float* a_xT0 = (LIST == 1) ? c.cx_xT0 : c.u_xT0;
+  const float* a_x0s = (LIST == 1) ? c.cx_x0sum : c.u_x0sum;
+  const double* a_logpr = (LIST == 1) ? c.cx_logpr : c.u_logpr;
+  int n_u = ub;  // (LIST = 1) tie index of the tie whose data sits in n_*
   if (ub < end) {
-    if (LIST) {
-      n_u = c.cx_idx[ub];
-      if (ub + 256 < end) nn_u = c.cx_idx[ub + 256];
-    }
-    n_lrow = c.u_lrow[n_u];
-    n_col = c.u_col[n_u];
-    n_cnt = c.u_cnt[n_u];
-    n_m0 = c.u_m0[n_u];
-    n_x0 = c.u_x0[n_u];
-    n_xT0 = c.u_xT0[n_u];
-    n_x0s = c.u_x0sum[n_u];
+    if (LIST == 1) n_u = c.cx_idx[ub];
+    n_lrow = a_lrow[ub];
+    n_col = a_col[ub];
+    n_cnt = a_cnt[ub];
+    n_m0 = a_m0[ub];
+    n_x0 = a_x0[ub];
+    n_xT0 = a_xT0[ub];
+    n_x0s = a_x0s[ub];
 #pragma unroll
-    for (int k = 0; k < K; ++k) n_logpr[k] = c.u_logpr[(size_t)n_u * K + k];
+    for (int k = 0; k < K; ++k) n_logpr[k] = a_logpr[(size_t)ub * K + k];
   }
 #pragma unroll 1
   for (int it = 0; it < TPT; ++it) {
     const int pos = ub + it * 256;
     const bool valid = pos < end;
-    const int u = LIST ? n_u : pos;
+    const int u = (LIST == 1) ? n_u : pos;
     // ---- stage A (per thread): tie data, S, prior; entries of SHORT ties
     int lrow = 0, i = 0, j = 0, cnt = 0;
     int64_t e0 = 0;
@@ -545,20 +553,17 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
       for (int k = 0; k < K; ++k) logpr[k] = n_logpr[k];
       const int posn = pos + 256;
       if (it + 1 < TPT && posn < end) {
-        const int un = LIST ? nn_u : posn;
-        if (LIST) {
-          n_u = un;
-          if (it + 2 < TPT && posn + 256 < end) nn_u = c.cx_idx[posn + 256];
-        }
-        n_lrow = c.u_lrow[un];
-        n_col = c.u_col[un];
-        n_cnt = c.u_cnt[un];
-        n_m0 = c.u_m0[un];
-        n_x0 = c.u_x0[un];
-        n_xT0 = c.u_xT0[un];
-        n_x0s = c.u_x0sum[un];
+        const int un = posn;
+        if (LIST == 1) n_u = c.cx_idx[un];
+        n_lrow = a_lrow[un];
+        n_col = a_col[un];
+        n_cnt = a_cnt[un];
+        n_m0 = a_m0[un];
+        n_x0 = a_x0[un];
+        n_xT0 = a_xT0[un];
+        n_x0s = a_x0s[un];
 #pragma unroll
-        for (int k = 0; k < K; ++k) n_logpr[k] = c.u_logpr[(size_t)un * K + k];
+        for (int k = 0; k < K; ++k) n_logpr[k] = a_logpr[(size_t)un * K + k];
       }
       i = lrow - l * nloc + row0;
       // the one dependent gather level: reporter cache of the first entry, prior, closed-form tables, S
@@ -698,7 +703,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
           o_dk[k] = rho[k] - fv;
           ru[k] = rho[k];
           ru32[k] = (float)rho[k];
-          if (LIST) c.u_patch[(size_t)u * K + k] = (float)rho[k];
+          if (LIST == 1) c.u_patch[(size_t)u * K + k] = (float)rho[k];
           dsum[k] += o_dk[k];
         }
         o_resid = (alive_u ? 1 : 0) - (dead ? 0 : 1);
@@ -1797,7 +1802,8 @@ static int launch_special(const vm_ctx* c, int flags, cudaStream_t st, int chunk
   const bool elbo = flags & VM_F_ELBO;
 #define LS(E, M) k_special<K, E, M><<<grid, 256, 0, st>>>(*c, region_u(c), chunk)
   if (chunk < 0 && simple_iteration<K>(c, flags)) {
-    k_special<K, false, VM_R_EGO, true><<<grid, 256, 0, st>>>(*c, region_u(c), chunk);
+    k_special<K, false, VM_R_EGO, 1><<<grid, 256, 0, st>>>(*c, region_u(c), chunk);  // layers that take the shortcut
+    k_special<K, false, VM_R_EGO, 2><<<grid, 256, 0, st>>>(*c, region_u(c), chunk);  // layers that cannot
   } else if (c->r_mode == VM_R_EGO) {
     if (elbo) LS(true, VM_R_EGO); else LS(false, VM_R_EGO);
   } else if (c->r_mode == VM_R_ALL) {
