@@ -450,13 +450,21 @@ def run_ours(args):
         from vimure_b200.sptensor import sptensor
 
         Xh = sptensor(tuple(subs_host), vals_host, shape=net.X.shape)
-        # warm-up: one small fit of the same kind first, so that the timed fit does not pay the one-off costs of this
-        # process (lazy loading of the torch kernels the packer / initialiser use: tens of ms, varying from box to box)
-        if world == 1:
-            wnet = make_network(800, L, K, config=args.config)
-            VimureModel(mutuality=True, convergence_tol=0.0).fit(wnet.X, R=wnet.R, K=K, seed=1, max_iter=3, init="fast")
-            del wnet
-            torch.cuda.synchronize(dev)
+        # warm-up: load the torch kernels of the device-side initialiser (first use of a kernel in a process costs tens of
+        # ms of lazy module loading; the packer's were loaded by the pack above).  Tiny tensors, no fit: a warm-up FIT was
+        # tried and made the timed fit's pack 3-20x slower on two boxes (profiles/bench_r1_final3_c3.json, _final4_).
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1)
+        w = torch.rand((8, K), generator=gen, dtype=torch.float64, device=dev)
+        w.mul_(0.01).add_(1.0)
+        w[:, 0] += 0.5
+        w /= w.sum(dim=-1, keepdim=True)
+        wm = torch.zeros(8, dtype=torch.bool, device=dev)
+        w.masked_fill_(wm[:, None], 0.0)
+        w[:, 0].masked_fill_(wm, 1.0)
+        torch.add(w, 1e-12, out=w).log_()
+        del w, wm, gen
+        torch.cuda.synchronize(dev)
         model = VimureModel(mutuality=True, convergence_tol=0.0)  # tol 0: never stops early -> exactly `steps` iterations
         t0 = time.time()
         model.fit(Xh, R=net.R, K=K, seed=1, max_iter=args.steps, init="fast", graphs=not args.no_graphs)
@@ -472,8 +480,7 @@ def run_ours(args):
                "d2h_bytes_per_step": d2h / args.steps, "wall_s": wall, "pack_s": model.pack_time,
                "timings_s": {k: round(v, 4) for k, v in model.timings.items()},
                "what": "VimureModel.fit(X host COO, R=EgoMask, max_iter=steps): pack + H2D + CAVI + ELBO + D2H of "
-                       "gamma/phi/nu posteriors; rho stays on the device; after one small warm-up fit (N=800) that "
-                       "loads the torch kernels of the packer"}
+                       "gamma/phi/nu posteriors; rho stays on the device"}
         del model
 
     cpu = None
