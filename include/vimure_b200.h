@@ -253,7 +253,9 @@ int vm_phase_phi(const vm_ctx* c, void* stream);
 int vm_phase_rho(const vm_ctx* c, int flags, void* stream);
 
 /* Measurement hook: launches ONLY the per-tie dense kernel of phase 3 (tables and special ties as left by the last
- * vm_phase_rho), so that its duration can be timed in isolation for the roofline figure. Results are unchanged. */
+ * vm_phase_rho), so that its duration can be timed in isolation for the roofline figure. The statistics are unchanged;
+ * with simple_mode the slab is patched from u_patch, which after an ELBO iteration still holds the posteriors of the
+ * iteration before for the ties that are not simple: treat the slab as stale until the next vm_phase_rho. */
 int vm_dense_only(const vm_ctx* c, int flags, void* stream);
 
 /* Phase 4 -- consumes (all-reduced) red3: A <- red3, `_update_nu` (model.py:820-830), refreshes the nu cache,
