@@ -192,3 +192,53 @@ def test_reference_prior_stream():
     ref = np.random.RandomState(5)
     ref.rand(L, N, N, K)
     assert prng.random_sample() == ref.random_sample()
+
+
+@pytest.mark.parametrize("mutuality", [True, False])
+def test_simple_special_tie_classification(mutuality):
+    """vm_ctx.simple_mode contract: a special tie is simple iff it has X entries, none of them with a reciprocal report
+    (all of them when mutuality is off), it is off the diagonal and lies in a full column tile; `cx_idx` lists the others
+    in ascending order with per-layer ranges `cx_ptr`, and `cx_*` are their compacted per-tie arrays."""
+    import vimure_b200.synthetic as syn
+    from vimure_b200 import _packing
+    from vimure_b200.model import shard_rows
+
+    L, N, K = 2, 1100, 2
+    net = syn.Multitensor(N=N, L=L, K=K, C=2, avg_degree=6, eta=0.5, seed=2).build_X(mutuality=0.5, seed=3)
+    tw = _packing.dense_tile_w(K)
+    n_simple = 0
+    for r in range(2):
+        row0, nloc = shard_rows(N, 2, r)
+        P = _packing.pack(net.X.subs, net.X.vals, L, N, N, K, net.R, "cpu", row0=row0, nloc=nloc, tile_h=32,
+                          mutuality=mutuality)
+        assert P.simple_ok
+        t = {k: v.numpy() for k, v in P.t.items()}
+        s = t["u_simple"]
+        n_simple += int(s.sum())
+        has_e1 = np.zeros(P.U, dtype=bool)
+        has_e1[t["e_u"][t["e1_idx"]]] = True
+        l = t["u_lrow"] // nloc
+        i = t["u_lrow"] % nloc + row0
+        expect = (t["u_cnt"] >= 1) & ~has_e1 & (i != t["u_col"]) & (t["u_col"] < (N // tw) * tw)
+        assert np.array_equal(s, expect)
+        if not mutuality:
+            assert P.I1 == 0 and np.array_equal(s, (t["u_cnt"] >= 1) & (i != t["u_col"]) & (t["u_col"] < (N // tw) * tw))
+        cx = t["cx_idx"]
+        assert P.n_cx == len(cx) and np.array_equal(cx, np.nonzero(~s)[0])
+        cp = t["cx_ptr"]
+        assert cp[0] == 0 and cp[-1] == P.n_cx
+        assert np.array_equal(np.repeat(np.arange(L), np.diff(cp)), l[cx])
+        for name in ("lrow", "col", "cnt", "m0", "x0", "xT0", "x0sum"):
+            assert np.array_equal(t["cx_" + name], t["u_" + name][cx]), name
+        # X of a simple tie = the sum of its entries
+        x = np.zeros(P.U)
+        np.add.at(x, t["e_u"], t["e_x"].astype(np.float64))
+        np.testing.assert_allclose(t["u_x0sum"][s], x[s], rtol=0, atol=1e-6)
+    assert n_simple > 0
+    # the A/B switch
+    P0 = _packing.pack(net.X.subs, net.X.vals, L, N, N, K, net.R, "cpu", tile_h=32, mutuality=mutuality, simple=False)
+    assert not P0.simple_ok and P0.n_cx == P0.U and not P0.t["u_simple"].any()
+    # no fast dense kernel (N*K % 4 != 0 or N below one column tile) -> no shortcut
+    small = syn.StandardSBM(N=300, L=1, K=2, C=2, avg_degree=4, seed=1).build_X(mutuality=0.3, seed=2)
+    Ps = _packing.pack(small.X.subs, small.X.vals, 1, 300, 300, 2, small.R, "cpu", mutuality=mutuality)
+    assert not Ps.simple_ok and Ps.n_cx == Ps.U
