@@ -465,23 +465,28 @@ def run_ours(args):
         torch.add(w, 1e-12, out=w).log_()
         del w, wm, gen
         torch.cuda.synchronize(dev)
-        model = VimureModel(mutuality=True, convergence_tol=0.0)  # tol 0: never stops early -> exactly `steps` iterations
-        t0 = time.time()
-        model.fit(Xh, R=net.R, K=K, seed=1, max_iter=args.steps, init="fast", graphs=not args.no_graphs)
-        post = model.get_posterior_estimates
-        d2h = model.gamma_shp.nbytes * 4 + model.phi_shp.nbytes * 4 + 8 * (2 + len(model.trace))
-        torch.cuda.synchronize(dev)
-        wall = time.time() - t0
-        if dist is not None:
-            t = torch.tensor([wall], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            wall = float(t.item())
+        # three consecutive complete fits from the same pinned host arrays; the MEDIAN wall time is reported (the figure
+        # is dominated by host-side set-up -- allocator, Python -- and single runs varied 0.13-0.23 s between boxes)
+        runs = []
+        for rep_i in range(3):
+            model = VimureModel(mutuality=True, convergence_tol=0.0)  # tol 0: never stops early -> exactly `steps` iterations
+            t0 = time.time()
+            model.fit(Xh, R=net.R, K=K, seed=1, max_iter=args.steps, init="fast", graphs=not args.no_graphs)
+            d2h = model.gamma_shp.nbytes * 4 + model.phi_shp.nbytes * 4 + 8 * (2 + len(model.trace))
+            torch.cuda.synchronize(dev)
+            wall = time.time() - t0
+            if dist is not None:
+                t = torch.tensor([wall], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                wall = float(t.item())
+            runs.append((wall, model.pack_time, {k: round(v, 4) for k, v in model.timings.items()}, d2h))
+            del model
+        wall, pack_s, timings, d2h = sorted(runs, key=lambda r_: r_[0])[1]
         e2e = {"value": args.steps * T / wall, "unit": "ties/s", "h2d_bytes_per_step": h2d / args.steps,
-               "d2h_bytes_per_step": d2h / args.steps, "wall_s": wall, "pack_s": model.pack_time,
-               "timings_s": {k: round(v, 4) for k, v in model.timings.items()},
+               "d2h_bytes_per_step": d2h / args.steps, "wall_s": wall, "wall_s_all_runs": [round(r_[0], 4) for r_ in runs],
+               "pack_s": pack_s, "timings_s": timings,
                "what": "VimureModel.fit(X host COO, R=EgoMask, max_iter=steps): pack + H2D + CAVI + ELBO + D2H of "
-                       "gamma/phi/nu posteriors; rho stays on the device"}
-        del model
+                       "gamma/phi/nu posteriors; rho stays on the device; median of 3 consecutive complete fits"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
