@@ -132,6 +132,11 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
     else:
         xT = xv.clone()
     P.sumX = float(xv.sum()) if I_all else 0.0
+    # named temporaries live until the function returns: release the big ones so that the allocator can reuse their blocks
+    # (in a cold process every tensor of this size is a fresh cudaMalloc, a few ms each)
+    if I_all:
+        del pos, found
+    del key, skey, order, keyT
 
     _mark("pairing")
     in_R = mask.entry_multiplicity(xl, xi, xj, xm) if I_all else xv.clone()
@@ -146,6 +151,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
     I = sel.numel()
     P.I = int(I)
     P.entry_src = sel  # position of each packed entry in the caller's COO order
+    del own, tk, o2
 
     _mark("mask+tie sort")
     # ---- special ties
