@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VM_ABI_VERSION 11
+#define VM_ABI_VERSION 12
 
 /* reporter-mask structure (how R[l,i,j,m] is represented) */
 #define VM_R_EGO 0 /* reporter m == node m reports row m and column m (vimure synthetic.py:1184-1204, _io.py:229-242) */
@@ -60,8 +60,13 @@ extern "C" {
 #define VM_R3_B 3    /* sum_J x^T_J sum_k rho_k         (model.py:1286-1290, the eta part) */
 #define VM_R3_EXTRA 4
 
-/* maximum K compiled in */
-#define VM_MAX_K 32
+/* slots of dev_flags */
+#define VM_FLAG_DEAD 0
+#define VM_FLAG_FIXNU 1
+
+/* maximum K compiled in (K = number of categories of a report, max(X)+1: 2..4 in every BASELINE config and in the
+   reference's tests; the kernels are templates on K, one translation unit per group of K) */
+#define VM_MAX_K 8
 /* special ties handled by one block of the special-tie kernel (n_ublk = ceil(max per layer / this)) */
 #ifndef VM_SPECIAL_TIES_PER_BLOCK /* (a timing variant may be built with a multiple of it: tools/ab_libs.py) */
 #define VM_SPECIAL_TIES_PER_BLOCK 1024
@@ -93,6 +98,8 @@ typedef struct vm_ctx {
   int64_t rt_end0, rt_end1, rt_end2, rt_end3;      /* cumulative row-tile ends of the chunks */
   int64_t sp_grid0, sp_grid1, sp_grid2, sp_grid3;  /* blocks per layer (max over layers) of each special-tie chunk */
   void* aux_stream;         /* cudaStream_t owned by the caller */
+  void* ev_fork;            /* two cudaEvent_t (timing disabled) owned by the caller, used to fork the aux stream from and */
+  void* ev_join;            /*   join it back into the main one; NULL: the library creates and destroys a pair per launch */
   const int64_t* sp_chunk_blk; /* [L*(VM_NCHUNK+1)] first special-tie block of each chunk, per layer */
   double eps;               /* EPS, model.py:215-218 */
   double alpha_eta, beta_eta;
@@ -111,18 +118,27 @@ typedef struct vm_ctx {
   const int64_t* ucol_ptr;  /* [L*N+1] EGO: special ties grouped by (l, col) */
   const int32_t* ucol_perm; /* [U] */
 
-  /* ---- simple special ties ----
-     A special tie is SIMPLE when none of its X entries has a reciprocal report (x^T = 0, or mutuality off), it is off the
-     diagonal and lies in a full column tile.  Its Poisson allocation is dz1_k = x whatever the parameters, and the
-     E[log theta] of its reporters is common to every k, so its posterior odds are
-        log2 rho_k/rho_0 = lo_k - S (E[lambda_k]-E[lambda_0]) log2e + X (E[log lambda_k]-E[log lambda_0]) log2e,
-     lo_k = log2((pr_k+EPS)/(pr_0+EPS)), X = sum of its x: the same separable form as a tie without data, plus a per-tie
-     constant and a per-layer multiple of X.  On iterations that store the slab and do not evaluate the ELBO the fast
-     dense kernel evaluates these ties itself (fp32, terms of magnitude O(1): no cancellation) and the special-tie kernel
-     only visits the others (`cx_idx`, `cx_*`); every other iteration runs the special-tie kernel over all special ties, as
-     does any layer for which k_phi_finish cannot rule out a completely underflowed tie (layer constant VM_LC_SIMPLE). */
+  /* ---- special ties the fast dense kernel evaluates itself ("shortcut" ties) ----
+     Ego mask, K <= 4, off the diagonal, in a full column tile, and either
+       SIMPLE: none of the tie's X entries has a reciprocal report (x^T = 0, or mutuality off).  Its Poisson allocation is
+               dz1_k = x whatever the parameters and the E[log theta] of its reporters is common to every k, so
+                  log2 rho_k/rho_0 = lo_k - S (E[lambda_k]-E[lambda_0]) log2e + X (E[log lambda_k]-E[log lambda_0]) log2e,
+               lo_k = log2((pr_k+EPS)/(pr_0+EPS)), X = sum of its x: the separable form of a tie without data plus a
+               per-tie constant and a per-layer multiple of X;  or
+       SINGLE: exactly ONE X entry, which has a reciprocal report (x^T > 0) and whose reporter is the row node or the
+               column node (always the case for entries inside an ego mask).  With f_k = z1_k/(z1_k+z2),
+               z1_k = G_theta_m G_lambda_k, z2 = G_nu x^T  (model.py:686-696):
+                  ln rho_k/rho_0 = ln2 lo_k - S (E[lambda_k]-E[lambda_0])
+                                   + x [ (f_k-f_0) E[log theta_m] + f_k E[log lambda_k] - f_0 E[log lambda_0] ],
+               every term O(1..30); the reporter's (G_theta, E[log theta]) come from a row constant or from a per-tile
+               column table in shared memory -- no gather.  The kernel also emits the tie's part of the nu statistic
+               (x z2 sum_k rho_k/(z1_k+z2), model.py:822-825) and its fp32 posterior into rho_u32 for the gamma/phi passes.
+     On iterations that store the slab and do not evaluate the ELBO the fast dense kernel evaluates these ties (fp32 from
+     fp64-prepared tables) and the special-tie kernel only visits the others (`cx_idx`, `cx_*`); every other iteration
+     runs the special-tie kernel over all special ties in fp64, as does any layer for which k_phi_finish cannot rule out
+     a completely underflowed tie (layer constant VM_LC_SIMPLE). */
   int64_t simple_mode;      /* 1 = enabled (EGO mask, K <= 4, fast dense kernel eligible, serial special/dense launch) */
-  int64_t n_cx;             /* special ties that are NOT simple */
+  int64_t n_cx;             /* special ties that take no shortcut */
   const int32_t* cx_idx;    /* [n_cx] their indices, ascending */
   const int64_t* cx_ptr;    /* [L+1] range of cx_idx of every layer */
   /* compacted copies of the per-tie arrays for those ties (coalesced reads in the list mode of the special-tie kernel) */
@@ -135,8 +151,11 @@ typedef struct vm_ctx {
   const float* cx_x0sum;
   const double* cx_logpr;   /* [n_cx*K] */
   float* u_patch;           /* [U*K] patch source of the fast dense kernel on such iterations: (-X, lo_1..lo_{K-1}) for a
-                               simple tie (constant over a fit), the fp32 posterior (written by the special-tie kernel) else */
-  const double* simple_consts; /* [2] min over the simple ties of log(pr_0+EPS); max X */
+                               shortcut tie (constant over a fit; X = x for a SINGLE tie), the fp32 posterior (written by
+                               the special-tie kernel) else */
+  const float* u_pxt;       /* [U] 0 for a SIMPLE tie; SINGLE: +x^T if the entry's reporter is the row node, -x^T if it is
+                               the column node */
+  const double* simple_consts; /* [3] over the shortcut ties: min log(pr_0+EPS); max X; max x^T */
   int64_t* fixP;            /* [L*K] fixed point 2^-30: sum over the simple ties of rho_k X (their part of phi0) */
 
   /* ---- X entries, sorted by tie ---- */
@@ -197,8 +216,10 @@ typedef struct vm_ctx {
   double* Elog_lambda;      /* [L*K] */
   double* GE_theta;         /* [L*M*2] (G_theta, Elog_theta) interleaved: one 16-byte gather per X entry */
   double* A;                /* [L*M*K] sum of rho_k over the ties reported by (l,m) */
-  double* rho_u;            /* [U*K] posterior of the special ties, fp64 */
-  float* rho_u32;           /* [U*K] fp32 copy used to patch the dense slab */
+  double* rho_u;            /* [U*K] posterior of the special ties, fp64 (as of the last update by the special-tie kernel) */
+  float* rho_u32;           /* [U*K] fp32 posterior of the special ties: patch source of the dense slab and what the gamma /
+                               phi passes gather (written by the special-tie kernel, and by the fast dense kernel for the
+                               SINGLE ties it evaluates) */
   double* delta_u;          /* [U*K] rho_u - formula value */
   float* rho;               /* [L*nloc*N*K] dense posterior slab */
 
@@ -211,12 +232,14 @@ typedef struct vm_ctx {
   float* colpart;           /* [L*nrt*N*K] */
   double* er_node;          /* [L*N] EGO: E[theta] of node n acting as reporter (0 if not an active reporter) */
   double* colsum;           /* [L*M*K] column partials reduced over the row tiles */
-  int64_t* dev_flags;       /* [8] [0]: a special tie underflowed completely in the last rho update */
+  int64_t* dev_flags;       /* [8] [0]: a special tie underflowed completely in the last rho update;
+                               [VM_FLAG_FIXNU]: fixed point 2^-30, nu statistic of the SINGLE ties the dense kernel evaluated */
   int64_t* fixG;            /* [L*M] fixed-point correction of g0: -x of the E0 entries of special ties that underflowed */
   double* phi0;             /* [L*K] sum over special ties of rho_k * u_x0sum (E0 part of the next phi-shape sums) */
   int64_t* fixA;            /* [L*M*K] EGO: per-reporter sums of (special - closed form), fixed point 2^-44, accumulated
                                with integer atomics (order-independent => bit-reproducible); slot k=0 holds only the
                                residual count (live special) - (live closed form) */
+  double* gfpart;           /* [L*ceil(M/256)*(K+4)] block partials of k_gamma_finish for k_phi_finish */
   double* blkpart;          /* [max(n_ublk, nct*L*nrt, L*n_phichunk*K, n_gchunk, ...)*4] */
   double* red1;             /* [L*M] gamma-shape sums (all-reduced by the host between phases when sharded) */
   double* red2;             /* [L*K] phi-shape sums */

@@ -260,6 +260,28 @@ def scenario_undirected(vm):
     save_fixture("undirected", X, gt.R, 1, 30, 30, 2, model_kwargs, fit_kwargs, rec)
 
 
+def scenario_sbm_n520(vm):
+    """N >= the dense kernel's column tile (512 at K=2): the fast dense kernel, the simple-tie shortcut and the partial
+    last tile are compared with the REFERENCE itself, not only with the oracle."""
+    gt = vm.synthetic.StandardSBM(N=520, M=520, L=1, K=2, C=2, avg_degree=8, sparsify=True, seed=10)
+    gt._build_X(mutuality=0.5, flag_self_reporter=True, seed=20)
+    fit_kwargs = dict(K=2, seed=1, max_iter=12, R=gt.R)
+    model_kwargs = dict(mutuality=True, convergence_tol=0.0)
+    rec = run_reference_trace(gt.X, fit_kwargs, model_kwargs)
+    save_fixture("sbm_n520", gt.X, gt.R, 1, 520, 520, 2, model_kwargs, fit_kwargs, rec, keep_rho="summary")
+
+
+def scenario_gm_n640_l2_k3(vm):
+    """Config 5's law (Multitensor / GMReciprocity, L > 1, K = 3) at a size that reaches the K = 3 fast dense kernel
+    (column tile 512) with a partial last tile."""
+    gt = vm.synthetic.Multitensor(N=640, M=640, L=2, C=2, K=3, avg_degree=8, sparsify=True, seed=7, eta=0.5)
+    gt._build_X(mutuality=0.5, flag_self_reporter=True, seed=11)
+    fit_kwargs = dict(K=3, seed=5, max_iter=11, R=gt.R)
+    model_kwargs = dict(mutuality=True, convergence_tol=0.0)
+    rec = run_reference_trace(gt.X, fit_kwargs, model_kwargs)
+    save_fixture("gm_n640_l2_k3", gt.X, gt.R, 2, 640, 640, 3, model_kwargs, fit_kwargs, rec, keep_rho="summary")
+
+
 SCENARIOS = {
     "f1_over": lambda vm: scenario_f1(vm, "over"),
     "f1_under": lambda vm: scenario_f1(vm, "under"),
@@ -271,6 +293,8 @@ SCENARIOS = {
     "karnataka_vil1": scenario_karnataka,
     "rho_prior": scenario_rho_prior,
     "undirected": scenario_undirected,
+    "sbm_n520": scenario_sbm_n520,
+    "gm_n640_l2_k3": scenario_gm_n640_l2_k3,
 }
 
 if __name__ == "__main__":

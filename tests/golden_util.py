@@ -6,7 +6,9 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ALL_FIXTURES = ["f1_over", "f1_under", "sbm_k3", "gm_l2_k3", "nomut", "dense_reporting", "custom_mask",
-                "karnataka_vil1", "rho_prior", "undirected"]
+                "karnataka_vil1", "rho_prior", "undirected", "sbm_n520", "gm_n640_l2_k3"]
+# fixtures large enough (N >= the dense kernel's column tile of 512) to reach the fast dense kernel and its shortcut ties
+LARGE_FIXTURES = ["sbm_n520", "gm_n640_l2_k3"]
 
 
 class Golden:

@@ -196,9 +196,11 @@ def test_reference_prior_stream():
 
 @pytest.mark.parametrize("mutuality", [True, False])
 def test_simple_special_tie_classification(mutuality):
-    """vm_ctx.simple_mode contract: a special tie is simple iff it has X entries, none of them with a reciprocal report
-    (all of them when mutuality is off), it is off the diagonal and lies in a full column tile; `cx_idx` lists the others
-    in ascending order with per-layer ranges `cx_ptr`, and `cx_*` are their compacted per-tie arrays."""
+    """vm_ctx.simple_mode contract: a special tie is SIMPLE iff it has X entries, none of them with a reciprocal report
+    (all of them when mutuality is off), it is off the diagonal and lies in a full column tile; it is SINGLE iff it has
+    exactly one X entry, that entry has a reciprocal report and was reported by the row or the column node (same position
+    constraints); `cx_idx` lists the other special ties in ascending order with per-layer ranges `cx_ptr`, and `cx_*` are
+    their compacted per-tie arrays."""
     import vimure_b200.synthetic as syn
     from vimure_b200 import _packing
     from vimure_b200.model import shard_rows
@@ -206,7 +208,7 @@ def test_simple_special_tie_classification(mutuality):
     L, N, K = 2, 1100, 2
     net = syn.Multitensor(N=N, L=L, K=K, C=2, avg_degree=6, eta=0.5, seed=2).build_X(mutuality=0.5, seed=3)
     tw = _packing.dense_tile_w(K)
-    n_simple = 0
+    n_simple = n_single = 0
     for r in range(2):
         row0, nloc = shard_rows(N, 2, r)
         P = _packing.pack(net.X.subs, net.X.vals, L, N, N, K, net.R, "cpu", row0=row0, nloc=nloc, tile_h=32,
@@ -221,10 +223,21 @@ def test_simple_special_tie_classification(mutuality):
         i = t["u_lrow"] % nloc + row0
         expect = (t["u_cnt"] >= 1) & ~has_e1 & (i != t["u_col"]) & (t["u_col"] < (N // tw) * tw)
         assert np.array_equal(s, expect)
+        g = t["u_single"]
+        inside = (i != t["u_col"]) & (t["u_col"] < (N // tw) * tw)
+        expect_g = (t["u_cnt"] == 1) & (t["u_xT0"] != 0) & inside & ((t["u_m0"] == i) | (t["u_m0"] == t["u_col"]))
         if not mutuality:
-            assert P.I1 == 0 and np.array_equal(s, (t["u_cnt"] >= 1) & (i != t["u_col"]) & (t["u_col"] < (N // tw) * tw))
+            assert P.I1 == 0 and np.array_equal(s, (t["u_cnt"] >= 1) & inside) and not g.any()
+        else:
+            assert np.array_equal(g, expect_g) and g.any() and not (g & s).any()
+            n_single += int(g.sum())
+            # patch constants: X = the entry's x; +x^T when the row node reported, -x^T when the column node did
+            assert np.array_equal(t["u_px"][g], t["u_x0"][g])
+            assert np.array_equal(t["u_pxt"][g], np.where(t["u_m0"][g] == i[g], t["u_xT0"][g], -t["u_xT0"][g]))
+            assert (t["u_pxt"][~g] == 0).all() and (t["u_pxt"][g] != 0).all()
+        assert np.array_equal(t["u_px"][s], t["u_x0sum"][s]) and (t["u_px"][~(s | g)] == 0).all()
         cx = t["cx_idx"]
-        assert P.n_cx == len(cx) and np.array_equal(cx, np.nonzero(~s)[0])
+        assert P.n_cx == len(cx) and np.array_equal(cx, np.nonzero(~(s | g))[0])
         cp = t["cx_ptr"]
         assert cp[0] == 0 and cp[-1] == P.n_cx
         assert np.array_equal(np.repeat(np.arange(L), np.diff(cp)), l[cx])
@@ -234,10 +247,12 @@ def test_simple_special_tie_classification(mutuality):
         x = np.zeros(P.U)
         np.add.at(x, t["e_u"], t["e_x"].astype(np.float64))
         np.testing.assert_allclose(t["u_x0sum"][s], x[s], rtol=0, atol=1e-6)
-    assert n_simple > 0
-    # the A/B switch
+    assert n_simple > 0 and (n_single > 0) == mutuality
+    # the A/B switches
     P0 = _packing.pack(net.X.subs, net.X.vals, L, N, N, K, net.R, "cpu", tile_h=32, mutuality=mutuality, simple=False)
-    assert not P0.simple_ok and P0.n_cx == P0.U and not P0.t["u_simple"].any()
+    assert not P0.simple_ok and P0.n_cx == P0.U and not P0.t["u_simple"].any() and not P0.t["u_single"].any()
+    P1 = _packing.pack(net.X.subs, net.X.vals, L, N, N, K, net.R, "cpu", tile_h=32, mutuality=mutuality, single=False)
+    assert P1.simple_ok and not P1.t["u_single"].any() and P1.n_cx == P1.U - int(P1.t["u_simple"].sum())
     # no fast dense kernel (N*K % 4 != 0 or N below one column tile) -> no shortcut
     small = syn.StandardSBM(N=300, L=1, K=2, C=2, avg_degree=4, seed=1).build_X(mutuality=0.3, seed=2)
     Ps = _packing.pack(small.X.subs, small.X.vals, 1, 300, 300, 2, small.R, "cpu", mutuality=mutuality)

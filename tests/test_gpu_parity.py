@@ -8,7 +8,7 @@ import warnings
 import numpy as np
 import pytest
 
-from tests.golden_util import ALL_FIXTURES, Golden
+from tests.golden_util import ALL_FIXTURES, LARGE_FIXTURES, Golden
 
 pytestmark = pytest.mark.gpu
 
@@ -99,6 +99,38 @@ def test_per_iteration_parity_with_reference(name):
         np.testing.assert_allclose(rho.sum(axis=1), z["rho_final_colsum"], rtol=1e-5)
         np.testing.assert_allclose(rho.sum(axis=2), z["rho_final_rowsum"], rtol=1e-5)
         assert int(np.argmax(rho, -1).sum()) == int(z["rho_argmax_sum"])
+
+
+@pytest.mark.parametrize("name", LARGE_FIXTURES)
+@pytest.mark.parametrize("tile_h", [128, 32])
+def test_shortcut_iterations_parity_with_reference(name, tile_h):
+    """The iterations WITHOUT ELBO are the ones the production loop runs 9 times out of 10: there the fast dense kernel
+    evaluates the SIMPLE and SINGLE special ties itself in fp32 (vm_ctx.simple_mode).  Goldens with N >= 512 reach that
+    path: parameters after every such iteration against the unmodified reference (rtol 1e-5), the ELBO on the reference's
+    cadence (iteration 1, 10, last) within 1e-6, final rho / argmax as in the per-iteration test."""
+    g = Golden(name)
+    eng, P = make_engine(g, tile_h=tile_h)
+    assert eng.simple_mode and int(P.t["u_single"].sum()) > 0 and int(P.t["u_simple"].sum()) > 0
+    z = g.z
+    K = g.K
+    for it in range(g.n_iter):
+        elbo_it = it == 0 or (it + 1) % 10 == 0 or it == g.n_iter - 1
+        eng.iterate(1, elbo_last=elbo_it)
+        if it == 1:  # the layers did take the shortcut (flag written by k_phi_finish)
+            lc = eng.layer_consts.cpu().numpy().reshape(g.L, 3 * K + 5)
+            assert (lc[:, 2 * K + 4] == 1.0).all()
+        p = eng.params()
+        for k in ("gamma_shp", "gamma_rte", "phi_shp", "phi_rte"):
+            np.testing.assert_allclose(p[k], z["it_" + k][it], rtol=RTOL_PARAM, err_msg=f"{k} it{it}")
+        np.testing.assert_allclose(p["nu_shp"], z["it_nu_shp"][it], rtol=RTOL_PARAM, err_msg=f"nu_shp it{it}")
+        if elbo_it:
+            np.testing.assert_allclose(eng.elbo(), z["it_elbo"][it], rtol=RTOL_ELBO, err_msg=f"elbo it{it}")
+    rho = eng.rho_slab().cpu().numpy().astype(np.float64)
+    t = z["rho_final_ties"]
+    np.testing.assert_allclose(rho[t[:, 0], t[:, 1], t[:, 2]], z["rho_final_vals"], rtol=2e-5, atol=1e-30)
+    np.testing.assert_allclose(rho.sum(axis=1), z["rho_final_colsum"], rtol=1e-5)
+    np.testing.assert_allclose(rho.sum(axis=2), z["rho_final_rowsum"], rtol=1e-5)
+    assert int(np.argmax(rho, -1).sum()) == int(z["rho_argmax_sum"])
 
 
 @pytest.mark.parametrize("name", ["f1_over", "karnataka_vil1", "gm_l2_k3", "dense_reporting"])

@@ -60,7 +60,7 @@ def main():
         p = eng.params()
         vec = np.concatenate([p["gamma_shp"].ravel(), p["gamma_rte"].ravel(), p["phi_shp"].ravel(), p["phi_rte"].ravel(),
                               [p["nu_shp"]]])
-        rho_u = eng.rho_u.clone()
+        rho_u = eng.rho_u32.clone()
         if ref is None:
             ref = (vec, rho_u)
             d = dr = 0.0

@@ -79,7 +79,12 @@ class CaviEngine:
         self.simple_mode = bool(getattr(P, "simple_ok", False)) and not overlap
         self.u_patch = torch.zeros(max(U, 1), K, **f32)
         self.fixP = torch.zeros(L * K, dtype=torch.int64, device=dev)
-        self.simple_consts = z(2)
+        self.simple_consts = z(3)
+        self.gfpart = z(L * ((M + 255) // 256) * (K + 4))
+        # fork/join events of the aux stream, created once (vm_ctx.ev_fork / ev_join)
+        self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_fork.record()
+        self._ev_join.record()
         self.cx_logpr = z(max(int(getattr(P, "n_cx", 0)), 1) if self.simple_mode else 1, K)
         assert _packing_const() == self.C["VM_SPECIAL_TIES_PER_BLOCK"]
         n_blk = max(P.n_gchunk, L * P.n_phichunk * K,
@@ -130,15 +135,16 @@ class CaviEngine:
         for name in ("u_lrow", "u_col", "u_ptr", "u_cnt", "u_m0", "u_x0", "u_xT0", "utile_ptr", "ucol_ptr", "ucol_perm", "e_u", "e_m", "e_x", "e_xT",
                      "e_flags", "f_u", "f_m", "f_x", "f_xT", "lay_eptr", "g0", "u_x0sum", "sp_chunk_blk", "g_chunk_ptr", "g_chunk_lm", "g_u", "g_x", "g_xT", "g_lm_cptr", "t_u", "t_lrow",
                      "t_col", "t_x", "rep", "r_ptr", "r_m", "r_val", "c_ptr", "c_tie", "cx_idx", "cx_ptr", "cx_lrow", "cx_col", "cx_cnt",
-                     "cx_m0", "cx_x0", "cx_xT0", "cx_x0sum"):
+                     "cx_m0", "cx_x0", "cx_xT0", "cx_x0sum", "u_pxt"):
             setattr(c, name, ptr(P.t[name]) if name in P.t else self._dummy.data_ptr())
         for name in ("u_logpr", "alpha_theta", "beta_theta", "alpha_lambda", "beta_lambda", "gamma_shp", "gamma_rte",
                      "phi_shp", "phi_rte", "nu", "G_theta", "E_theta", "Elog_theta", "G_lambda", "E_lambda",
                      "Elog_lambda", "GE_theta", "rho_u", "rho_u32", "delta_u", "rho", "layer_consts", "tab_p", "tab_q",
                      "rowpart", "colpart", "er_node", "colsum", "dev_flags", "fixA", "fixG", "phi0", "blkpart", "red1", "red2", "red3",
-                     "elbo_out", "u_patch", "fixP", "simple_consts", "cx_logpr"):
+                     "elbo_out", "u_patch", "fixP", "simple_consts", "cx_logpr", "gfpart"):
             setattr(c, name, ptr(getattr(self, name)))
         c.A = self.red3.data_ptr()  # A aliases the (all-reduced) statistics vector
+        c.ev_fork, c.ev_join = self._ev_fork.cuda_event, self._ev_join.cuda_event
         self._cref = ctypes.byref(c)
         self.n_launch = 0
         self._graphs = None  # flags -> captured CUDA graph of one iteration (small, launch-bound problems)
@@ -188,19 +194,21 @@ class CaviEngine:
             torch.add(pr, float(eps), out=self.u_logpr)  # log(pr_rho + EPS), model.py:559, without temporaries
             self.u_logpr.log_()
             if self.simple_mode:
-                # patch entries of the simple ties: (-X, lo_1..lo_{K-1}), lo_k = log2((pr_k+EPS)/(pr_0+EPS)); the others
+                # patch entries of the shortcut ties: (-X, lo_1..lo_{K-1}), lo_k = log2((pr_k+EPS)/(pr_0+EPS)); the others
                 # are rewritten by the special-tie kernel before the dense kernel reads them
-                sm = P.t["u_simple"]
+                sm = P.t["u_simple"] | P.t["u_single"]
                 lp = self.u_logpr
                 if P.n_cx:
                     torch.index_select(lp, 0, P.t["cx_idx"].to(torch.int64), out=self.cx_logpr)
+                px = P.t["u_px"]
                 self.u_patch.zero_()
-                self.u_patch[:, 0] = torch.where(sm, -P.t["u_x0sum"], torch.zeros_like(P.t["u_x0sum"]))
+                self.u_patch[:, 0] = torch.where(sm, -px, torch.zeros_like(px))
                 lo = ((lp[:, 1:] - lp[:, :1]) * 1.4426950408889634).to(torch.float32)
                 self.u_patch[:, 1:] = torch.where(sm[:, None], lo, torch.zeros_like(lo))
                 big = torch.full_like(lp[:, 0], 1e300)
                 self.simple_consts[0] = torch.where(sm, lp[:, 0], big).min().clamp(max=0.0)
-                self.simple_consts[1] = torch.where(sm, P.t["u_x0sum"], torch.zeros_like(P.t["u_x0sum"])).max().to(torch.float64)
+                self.simple_consts[1] = px.max().to(torch.float64)
+                self.simple_consts[2] = P.t["u_pxt"].abs().max().to(torch.float64)
         st = self._stream()
         _capi.check(self.lib.vm_refresh_cache(self._cref, st), "vm_refresh_cache")
         _capi.check(self.lib.vm_init_stats(self._cref, st), "vm_init_stats")

@@ -21,7 +21,7 @@ def dense_tile_w(K):
 
     w = int(_capi.load().vm_dense_tile_w(int(K)))
     if w <= 0:
-        raise ValueError("vimure_b200 supports 2 <= K <= 8 (got K=%d)" % K)
+        raise ValueError("vimure_b200 supports 2 <= K <= 8 = VM_MAX_K (got K=%d)" % K)
     return w
 
 GAMMA_CHUNK = 256
@@ -73,7 +73,7 @@ class Packed:
 
 
 def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64, mutuality=True, split_e0=True,
-         simple=None):
+         simple=None, single=None):
     """Build the packed layout.
 
     X_subs : (4, I) integer array-like (l, i, j, m);  X_vals : (I,) counts;  mask : masks.ReporterMask.
@@ -82,11 +82,15 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
         visited (needed when a prior is so small that exp(E[log theta]) can underflow to 0, where model.py:692 gives 0).
     simple : classify the special ties whose posterior the fast dense kernel can evaluate itself (default: yes, unless the
         environment says VM_NO_SIMPLE=1 -- the A/B switch of the tests and tools).
+    single : ... including the ties with exactly one report that has a reciprocal report (default: yes, unless
+        VM_NO_SINGLE=1).
     """
-    if simple is None:
-        import os
+    import os
 
+    if simple is None:
         simple = os.environ.get("VM_NO_SIMPLE") != "1"
+    if single is None:
+        single = os.environ.get("VM_NO_SINGLE") != "1"
     dev = torch.device(device)
     nloc = N - row0 if nloc is None else int(nloc)
     _mark = _Trace(dev)
@@ -262,19 +266,31 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
         x0sum = torch.zeros(U, dtype=torch.float64, device=dev)
     P.t["g0"] = g0.contiguous()
     P.t["u_x0sum"] = x0sum.to(torch.float32).contiguous()
-    # ---- simple special ties (include/vimure_b200.h, vm_ctx.simple_mode): no entry with a reciprocal report, off the
-    # diagonal, in a full column tile.  On iterations without ELBO the fast dense kernel evaluates them and the special-tie
-    # kernel walks `cx_idx`, the others, through compacted copies of their per-tie arrays.
+    # ---- shortcut ties (include/vimure_b200.h, vm_ctx.simple_mode): off the diagonal, in a full column tile, and either
+    # SIMPLE (no entry with a reciprocal report) or SINGLE (exactly one entry, with a reciprocal report, reported by the row
+    # or the column node).  On iterations without ELBO the fast dense kernel evaluates them and the special-tie kernel walks
+    # `cx_idx`, the others, through compacted copies of their per-tie arrays.
     P.simple_ok = bool(simple and mask.kind == "ego" and K <= 4 and (N * K) % 4 == 0 and N >= TILE_W and P.tile_h <= 128
                        and (split_e0 or not mutuality) and U > 0)
     u_simple = torch.zeros(U, dtype=torch.bool, device=dev)
+    u_single = torch.zeros(U, dtype=torch.bool, device=dev)
     if P.simple_ok:
         has_e1 = torch.zeros(U, dtype=torch.bool, device=dev)
         if P.I1:
             has_e1[P.t["e_u"][e1].to(torch.int64)] = True
-        u_simple = P.t["u_has_x"] & ~has_e1 & (u_i != u_col) & (u_col < (N // TILE_W) * TILE_W)
+        inside = (u_i != u_col) & (u_col < (N // TILE_W) * TILE_W)
+        u_simple = P.t["u_has_x"] & ~has_e1 & inside
+        if mutuality and split_e0 and single:
+            m0 = P.t["u_m0"].to(torch.int64)
+            u_single = (P.t["u_cnt"] == 1) & has_e1 & inside & ((m0 == u_i) | (m0 == u_col))
     P.t["u_simple"] = u_simple
-    cx = torch.nonzero(~u_simple).flatten()
+    P.t["u_single"] = u_single
+    # patch constants of the shortcut ties: X (= x of a SINGLE tie's entry) and +-x^T (sign: reported by the row / column node)
+    zf = torch.zeros(U, dtype=torch.float32, device=dev)
+    P.t["u_px"] = torch.where(u_simple, P.t["u_x0sum"], torch.where(u_single, P.t["u_x0"], zf)).contiguous()
+    P.t["u_pxt"] = torch.where(u_single, torch.where(P.t["u_m0"].to(torch.int64) == u_i, P.t["u_xT0"], -P.t["u_xT0"]),
+                               zf).contiguous()
+    cx = torch.nonzero(~(u_simple | u_single)).flatten()
     P.n_cx = int(cx.numel())
     P.t["cx_idx"] = _i32(cx)
     P.t["cx_ptr"] = torch.searchsorted(u_l[cx].contiguous(), torch.arange(L + 1, device=dev, dtype=torch.int64)).contiguous()

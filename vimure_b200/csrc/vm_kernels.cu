@@ -50,6 +50,21 @@ static bool vm_debug_sync() {
 #define UP_P0(K) (3 + (K))  // + k: rho_k * u_x0sum (E0 part of the next phi-shape sums)
 #define UP_SLOTS(K) (3 + 2 * (K))
 
+// fp32 posterior of one special tie (K consecutive floats, 4K-byte aligned for K = 2, 4)
+template <int K>
+__device__ __forceinline__ void vm_load_rho32(const float* p, float* r) {
+  if (K == 2) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    r[0] = v.x; r[1] = v.y;
+  } else if (K == 4) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) r[k] = p[k];
+  }
+}
+
 // =====================================================================================================
 // phase gamma
 // =====================================================================================================
@@ -83,17 +98,15 @@ __global__ void __launch_bounds__(256) k_gamma_partial(const __grid_constant__ v
       x[q] = ok ? c.g_x[p] : 0.f;
       xT[q] = ok ? c.g_xT[p] : 0.f;
     }
-    double r[4][K];
+    float r[4][K];  // the fp32 posterior of the tie (8 bytes at K=2: half the gather of the fp64 copy)
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int k = 0; k < K; ++k) r[q][k] = c.rho_u[u[q] * K + k];
+    for (int q = 0; q < 4; ++q) vm_load_rho32<K>(c.rho_u32 + u[q] * K, r[q]);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       double dz1[K], dz2[K];
       vm_alloc<K>(mut, (double)x[q], (double)xT[q], Gth, Gl, Gnu, dz1, dz2);  // x == 0 for padding lanes
 #pragma unroll
-      for (int k = 0; k < K; ++k) acc += r[q][k] * dz1[k];
+      for (int k = 0; k < K; ++k) acc += (double)r[q][k] * dz1[k];
     }
   }
   acc = warp_sum(acc);
@@ -115,31 +128,75 @@ __global__ void __launch_bounds__(256) k_gamma_reduce(const __grid_constant__ vm
 // =====================================================================================================
 // phase phi
 // =====================================================================================================
-__device__ __forceinline__ void vm_store_theta_cache(const vm_ctx& c, int64_t lm, double shp, double rte) {
-  const double el = vm_digamma(shp) - log(rte);
+__device__ __forceinline__ void vm_store_theta_cache(const vm_ctx& c, int64_t lm, double shp, double rte, double& et,
+                                                     double& el) {
+  el = vm_digamma(shp) - log(rte);
+  et = shp / rte;
   const double g = exp(el);
   c.Elog_theta[lm] = el;
   c.G_theta[lm] = g;
-  c.E_theta[lm] = shp / rte;
+  c.E_theta[lm] = et;
   c.GE_theta[2 * lm] = g;
   c.GE_theta[2 * lm + 1] = el;
 }
 
+// per-block partials of k_gamma_finish, consumed by k_phi_finish: sum_m E[theta_m] A[m,k] (k < K), sum_m E[theta_m],
+// max E[theta], max -E[log theta], max E[log theta]
+#define VM_GF_SLOTS(K) ((K) + 4)
+#define VM_GF_THREADS 256
+
 // `_update_gamma` (model.py:698-718) from the (all-reduced) shape sums and A, then the theta part of
 // `_update_cache` (model.py:676).  gamma_rte[l,m] = beta + sum_k A[l,m,k] E[lambda_lk].
+// Grid (ceil(M/256), L).  The same pass produces the block partials of what `_update_phi` needs from the NEW theta
+// (phi_rte[l,k] = beta + sum_m E[theta_lm] A[l,m,k], model.py:742-749) and clears the fixed-point accumulators of the
+// coming rho update (fixA: consumed by the last k_stats_ego; fixG: consumed by k_gamma_reduce just before).
 template <int K>
-__global__ void k_gamma_finish(const __grid_constant__ vm_ctx c) {
-  const int64_t lm = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lm >= c.L * c.M) return;
-  const int l = (int)(lm / c.M);
-  const double shp = c.alpha_theta[lm] + c.red1[lm];
-  double r = 0.0;
+__global__ void __launch_bounds__(VM_GF_THREADS) k_gamma_finish(const __grid_constant__ vm_ctx c) {
+  __shared__ double sm[VM_GF_THREADS / 32];
+  const int l = blockIdx.y;
+  const int64_t m = (int64_t)blockIdx.x * VM_GF_THREADS + threadIdx.x;
+  double acc[K + 1];
 #pragma unroll
-  for (int k = 0; k < K; ++k) r += c.A[lm * K + k] * c.E_lambda[l * K + k];
-  const double rte = c.beta_theta[lm] + r;
-  c.gamma_shp[lm] = shp;
-  c.gamma_rte[lm] = rte;
-  vm_store_theta_cache(c, lm, shp, rte);
+  for (int k = 0; k <= K; ++k) acc[k] = 0.0;
+  double emax = 0.0, nelmax = -1e300, elmax = -1e300;
+  if (m < c.M) {
+    const int64_t lm = (int64_t)l * c.M + m;
+    const double shp = c.alpha_theta[lm] + c.red1[lm];
+    double r = 0.0, a[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      a[k] = c.A[lm * K + k];
+      r += a[k] * c.E_lambda[l * K + k];
+    }
+    const double rte = c.beta_theta[lm] + r;
+    c.gamma_shp[lm] = shp;
+    c.gamma_rte[lm] = rte;
+    double et, el;
+    vm_store_theta_cache(c, lm, shp, rte, et, el);
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = et * a[k];
+    acc[K] = et;
+    emax = et;
+    nelmax = -el;
+    elmax = el;
+    if (c.r_mode == VM_R_EGO) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) c.fixA[lm * K + k] = 0;
+    }
+    c.fixG[lm] = 0;
+  }
+  double* out = c.gfpart + ((int64_t)l * gridDim.x + blockIdx.x) * VM_GF_SLOTS(K);
+#pragma unroll
+  for (int k = 0; k <= K; ++k) {
+    const double v = block_sum<VM_GF_THREADS>(acc[k], sm);
+    if (threadIdx.x == 0) out[k] = v;
+  }
+  emax = block_max<VM_GF_THREADS>(emax, sm);
+  if (threadIdx.x == 0) out[K + 1] = emax;
+  nelmax = block_max<VM_GF_THREADS>(nelmax, sm);
+  if (threadIdx.x == 0) out[K + 2] = nelmax;
+  elmax = block_max<VM_GF_THREADS>(elmax, sm);
+  if (threadIdx.x == 0) out[K + 3] = elmax;
 }
 
 // `_sp_uttkrp_lambda` (model.py:880-887): per-layer sums of rho_k*dz1_k over the X entries (new theta cache).
@@ -170,19 +227,19 @@ __global__ void __launch_bounds__(256) k_phi_partial(const __grid_constant__ vm_
       x[q] = ok ? c.f_x[e] : 0.f;
       xT[q] = ok ? c.f_xT[e] : 0.f;
     }
-    double r[4][K], Gth[4];
+    float r[4][K];
+    double Gth[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       Gth[q] = c.G_theta[(int64_t)l * c.M + m[q]];
-#pragma unroll
-      for (int k = 0; k < K; ++k) r[q][k] = c.rho_u[u[q] * K + k];
+      vm_load_rho32<K>(c.rho_u32 + u[q] * K, r[q]);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       double dz1[K], dz2[K];
       vm_alloc<K>(mut, (double)x[q], (double)xT[q], Gth[q], Gl, Gnu, dz1, dz2);  // x == 0 for padding
 #pragma unroll
-      for (int k = 0; k < K; ++k) acc[k] += r[q][k] * dz1[k];
+      for (int k = 0; k < K; ++k) acc[k] += (double)r[q][k] * dz1[k];
     }
   }
 #pragma unroll
@@ -208,42 +265,41 @@ __global__ void __launch_bounds__(256) k_phi_reduce(const __grid_constant__ vm_c
 // =====================================================================================================
 // phase rho
 // =====================================================================================================
-// `_update_phi` (model.py:729-749): phi_rte[l,k] = beta + sum_m E[theta_lm](new) A[l,m,k]; lambda part of the cache;
-// then the per-layer constants of the closed-form tie posterior.
+// `_update_phi` (model.py:729-749): phi_rte[l,k] = beta + sum_m E[theta_lm](new) A[l,m,k] from the block partials of
+// k_gamma_finish; lambda part of the cache; then the per-layer constants of the closed-form tie posterior.
 template <int K>
-__global__ void __launch_bounds__(1024) k_phi_finish(const __grid_constant__ vm_ctx c) {
-  __shared__ double sm[32];
+__global__ void __launch_bounds__(256) k_phi_finish(const __grid_constant__ vm_ctx c) {
+  __shared__ double sm[8];
   __shared__ double rte_s[K + 1];
   const int l = blockIdx.x;
-  const int64_t M = c.M;
+  const int64_t nb = (c.M + VM_GF_THREADS - 1) / VM_GF_THREADS;
+  const double* gp = c.gfpart + (int64_t)l * nb * VM_GF_SLOTS(K);
   double acc[K + 1];
-  double emax = 0.0, nelmin = -1e300;  // max E[theta]; max of -E[log theta]
+  double emax = 0.0, nelmax = -1e300, elmax = -1e300;  // max E[theta]; max of -E[log theta]; max E[log theta]
 #pragma unroll
   for (int k = 0; k <= K; ++k) acc[k] = 0.0;
-  for (int64_t m = threadIdx.x; m < M; m += 1024) {
-    const double et = c.E_theta[l * M + m];
+  for (int64_t b = threadIdx.x; b < nb; b += 256) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] += et * c.A[(l * M + m) * K + k];
-    acc[K] += et;
-    emax = fmax(emax, et);
-    if (c.simple_mode) nelmin = fmax(nelmin, -c.Elog_theta[l * M + m]);
+    for (int k = 0; k <= K; ++k) acc[k] += gp[b * VM_GF_SLOTS(K) + k];
+    emax = fmax(emax, gp[b * VM_GF_SLOTS(K) + K + 1]);
+    nelmax = fmax(nelmax, gp[b * VM_GF_SLOTS(K) + K + 2]);
+    elmax = fmax(elmax, gp[b * VM_GF_SLOTS(K) + K + 3]);
   }
 #pragma unroll
   for (int k = 0; k <= K; ++k) {
-    const double v = block_sum<1024>(acc[k], sm);
+    const double v = block_sum<256>(acc[k], sm);
     if (threadIdx.x == 0) rte_s[k] = v;
   }
-  emax = block_max<1024>(emax, sm);
-  if (c.simple_mode) {
-    nelmin = block_max<1024>(nelmin, sm);
-    if (threadIdx.x < K) c.fixP[l * K + threadIdx.x] = 0;
-  }
-  if (c.r_mode == VM_R_EGO)
-    for (int64_t t = threadIdx.x; t < M * K; t += 1024) c.fixA[(int64_t)l * M * K + t] = 0;
-  for (int64_t t = threadIdx.x; t < M; t += 1024) c.fixG[(int64_t)l * M + t] = 0;  // consumed by k_gamma_reduce already
+  emax = block_max<256>(emax, sm);
+  nelmax = block_max<256>(nelmax, sm);
+  elmax = block_max<256>(elmax, sm);
+  if (c.simple_mode && threadIdx.x < K) c.fixP[l * K + threadIdx.x] = 0;
   if (threadIdx.x == 0) {
-    if (l == 0) c.dev_flags[0] = 0;
-    double El[K], Ell[K];
+    if (l == 0) {
+      c.dev_flags[VM_FLAG_DEAD] = 0;
+      c.dev_flags[VM_FLAG_FIXNU] = 0;
+    }
+    double El[K], Ell[K], Gl[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const double shp = c.alpha_lambda[l * K + k] + c.red2[l * K + k];
@@ -253,7 +309,8 @@ __global__ void __launch_bounds__(1024) k_phi_finish(const __grid_constant__ vm_
       const double el = vm_digamma(shp) - log(rte);
       Ell[k] = el;
       c.Elog_lambda[l * K + k] = el;
-      c.G_lambda[l * K + k] = exp(el);
+      Gl[k] = exp(el);
+      c.G_lambda[l * K + k] = Gl[k];
       El[k] = shp / rte;
       c.E_lambda[l * K + k] = El[k];
     }
@@ -272,14 +329,26 @@ __global__ void __launch_bounds__(1024) k_phi_finish(const __grid_constant__ vm_
     // no closed-form row can underflow completely if even the largest possible S keeps k=0 alive
     const double s_max = (c.r_mode == VM_R_EGO) ? 2.0 * emax : rte_s[K];
     lc[VM_LC_DEAD(K)] = (c.r_mode == VM_R_CSR || lp0 - s_max * El[0] < VM_DEAD_LN + 8.0) ? 1.0 : 0.0;
-    // simple special ties (see vm_ctx.simple_mode): evaluated by the fast dense kernel only if none of them can underflow
-    // completely: log-weight of k=0 >= min log(pr_0+EPS) - S_max E[lambda_0] + X_max min(0, min E[log theta] + E[log lambda_0])
 #pragma unroll
     for (int k = 0; k < K; ++k) lc[VM_LC_G(K, k)] = (Ell[k] - Ell[0]) * VM_LOG2E;
+    // shortcut ties (see vm_ctx.simple_mode): evaluated by the fast dense kernel only if
+    //  (i) none of them can underflow completely: the log-weight of k=0 is
+    //      >= min log(pr_0+EPS) - S_max E[lambda_0] + X_max min(0, min E[log theta] + E[log lambda_0])
+    //      (a SINGLE tie's dz1_0 lies in [0, x], so the same bound holds for it), and
+    //  (ii) the fp32 Poisson split of the SINGLE ties stays in range: z2 = G_nu x^T and z1 = G_theta G_lambda_k
+    //       within [1e-30, 1e30] at their largest / z2 at its smallest (x^T >= 1)
     bool simple_ok = false;
     if (c.simple_mode && c.r_mode == VM_R_EGO && c.may_dead == 0 && lc[VM_LC_DEAD(K)] == 0.0) {
-      const double lw0 = c.simple_consts[0] - s_max * El[0] + c.simple_consts[1] * fmin(0.0, -nelmin + Ell[0]);
+      const double lw0 = c.simple_consts[0] - s_max * El[0] + c.simple_consts[1] * fmin(0.0, -nelmax + Ell[0]);
       simple_ok = lw0 >= VM_DEAD_LN + 8.0;
+      if (c.mutuality) {
+        const double gnu = c.nu[VM_NU_G];
+        double glmax = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) glmax = fmax(glmax, Gl[k]);
+        simple_ok = simple_ok && gnu >= 1e-30 && gnu * fmax(1.0, c.simple_consts[2]) <= 1e30 &&
+                    exp(fmin(elmax, 80.0)) * glmax <= 1e30;
+      }
     }
     lc[VM_LC_SIMPLE(K)] = simple_ok ? 1.0 : 0.0;
   }
@@ -289,7 +358,10 @@ __global__ void __launch_bounds__(1024) k_phi_finish(const __grid_constant__ vm_
 // initial state has been injected.
 __global__ void k_refresh_cache(const __grid_constant__ vm_ctx c) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < c.L * c.M) vm_store_theta_cache(c, t, c.gamma_shp[t], c.gamma_rte[t]);
+  if (t < c.L * c.M) {
+    double et, el;
+    vm_store_theta_cache(c, t, c.gamma_shp[t], c.gamma_rte[t], et, el);
+  }
   if (t < c.L * c.K) {
     const double el = vm_digamma(c.phi_shp[t]) - log(c.phi_rte[t]);
     c.Elog_lambda[t] = el;
@@ -652,7 +724,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
       if (!alive_u) {
 #pragma unroll
         for (int k = 0; k < K; ++k) rho[k] = 0.0;
-        c.dev_flags[0] = 1;  // benign race: every writer stores the same value
+        c.dev_flags[VM_FLAG_DEAD] = 1;  // benign race: every writer stores the same value
         // its E0 entries no longer contribute x to the gamma-shape sums: take them out of the constant g0
         if (cnt > 0) {
           const int64_t ef = c.u_ptr[u];
@@ -815,9 +887,6 @@ __device__ __forceinline__ void vm_store_chunk(float* dst, int lane, const float
   } else if (K == 4) {
 #pragma unroll
     for (int t = 0; t < 4; ++t) d4[32 * t + lane] = make_float4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
-  } else if (K > 8) {  // many categories: natural layout (every lane owns 16*K contiguous bytes), no stage
-#pragma unroll
-    for (int v = 0; v < K; ++v) d4[K * lane + v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
   } else {
     float4* s4 = reinterpret_cast<float4*>(stage);
 #pragma unroll
@@ -830,7 +899,7 @@ __device__ __forceinline__ void vm_store_chunk(float* dst, int lane, const float
 }
 template <int K>
 struct StageCfg {
-  static constexpr int FLOATS = (K == 2 || K == 4 || K > 8) ? 4 : 128 * K;  // per-warp stage (unused for K = 2, 4, > 8)
+  static constexpr int FLOATS = (K == 2 || K == 4) ? 4 : 128 * K;  // per-warp stage (unused for K = 2, 4)
 };
 
 // 4 ties of one lane. a[t][k] are the log2-odds; results in o[t*K+k].
@@ -1023,35 +1092,55 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS) k_dense(const __grid_constan
 // in the row loop waits on a load.
 #define VM_FAST_MAX_TILE_H 128
 
+#ifndef VM_FAST_CAPW
+#define VM_FAST_CAPW 320
+#endif
 template <int K>
 struct FastCfg {
-  // special ties staged per warp (all the rows of the warp); the rest are fetched directly
-  static constexpr int CAPW = (K <= 2) ? 384 : (K == 4) ? 192 : 64;
+  // special ties staged per warp (all the rows of the warp); the rest are fetched directly.  A warp owns tile_h/8 = 16
+  // row segments of TW = 512 ties: ~300 special ties at the density of config 3 (3.7 %)
+  static constexpr int CAPW = VM_FAST_CAPW;
 };
 
 #ifndef VM_FAST_MINBLK2
 #define VM_FAST_MINBLK2 4
 #endif
-// SIMPLE (no ELBO): in the layers flagged VM_LC_SIMPLE the patch source is `u_patch`, whose entries of SIMPLE special ties
-// hold (-X, lo_1..lo_{K-1}) instead of a posterior: the warp evaluates those ties itself (see vm_ctx.simple_mode) from
-// the row term without its constant (ps2), the staged column term, lo and X g_k -- all O(1), so fp32 does not cancel --
-// and accounts for them exactly as the special-tie kernel would: (posterior - closed form) into the fixed-point
-// per-reporter corrections (row reporter: one atomic per row segment after an integer warp reduction) and rho_k X into fixP.
+
+// shared memory of k_dense_fast (dynamic: more than the 48 KB a static allocation may hold)
+template <int K, bool SIMPLE>
+struct FastSmem {
+  static constexpr int TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32, CAPW = FastCfg<K>::CAPW, TH = VM_FAST_MAX_TILE_H;
+  float qs[K - 1][TW];      // column terms of the log2-odds
+  float colbuf[K - 1][TW];  // cross-warp column sums
+  float stage[NW][StageCfg<K>::FLOATS];
+  float pval[NW][CAPW][K];  // staged patch data of the warp's rows
+  int pcol[NW][CAPW];
+  float ps[K - 1][TH];      // row terms
+  int tp0[TH], tp1[TH];     // special-tie range of every row segment
+  double sm_red[8];
+  // ---- shortcut ties (SIMPLE instantiation only)
+  float pxt[SIMPLE ? NW : 1][SIMPLE ? CAPW : 1];
+  float ps2[SIMPLE ? K - 1 : 1][SIMPLE ? TH : 1];    // row terms without their constant
+  float qg[SIMPLE ? TW : 1], qel[SIMPLE ? TW : 1];   // G_theta, E[log theta] log2e of the column nodes as reporters
+  float rg[SIMPLE ? TH : 1], rel[SIMPLE ? TH : 1];   // ... of the row nodes
+  float lam[SIMPLE ? 3 * K + 1 : 1];  // G_lambda_k | G_lambda_k - G_lambda_0 | E[log lambda_k] log2e | G_nu
+  unsigned char ract[SIMPLE ? TH : 1], qact[SIMPLE ? TW : 1];  // node is an active reporter
+};
+
+// SIMPLE (no ELBO): in the layers flagged VM_LC_SIMPLE the patch source is `u_patch`, whose entries of the shortcut ties
+// (vm_ctx.simple_mode) hold (-X, lo_1..lo_{K-1}) instead of a posterior, with `u_pxt` = 0 (SIMPLE tie) or +-x^T (SINGLE
+// tie, sign = which of the two nodes reported).  The warp evaluates those ties itself from the row term without its
+// constant (ps2), the staged column term, lo and the data term -- all O(1..30), so fp32 does not cancel -- and accounts
+// for them exactly as the special-tie kernel would: (posterior - closed form) into the fixed-point per-reporter
+// corrections (row reporter: one atomic per row segment after an integer warp reduction), rho_k X of the SIMPLE ties into
+// fixP, the nu statistic of the SINGLE ties into dev_flags[VM_FLAG_FIXNU], their fp32 posterior into rho_u32.
 template <int K, bool ELBO, bool SIMPLE = false>
 __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_MINBLK2 : 2) k_dense_fast(const __grid_constant__ vm_ctx c, double* catpart, int rt0, int rtn) {
   static_assert(!(SIMPLE && ELBO), "the ELBO iterations evaluate every special tie in fp64");
   constexpr int NCH = DenseCfg<K>::NCH, TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32, CAPW = FastCfg<K>::CAPW;
-  __shared__ float ps2[SIMPLE ? K - 1 : 1][SIMPLE ? VM_FAST_MAX_TILE_H : 1];
-  __shared__ unsigned char ract[SIMPLE ? VM_FAST_MAX_TILE_H : 1], qact[SIMPLE ? TW : 1];
-  __shared__ __align__(16) float qs[K - 1][TW];
-  __shared__ __align__(16) float colbuf[K - 1][TW];
-  __shared__ __align__(16) float stage[NW][StageCfg<K>::FLOATS];
-  __shared__ float ps[K - 1][VM_FAST_MAX_TILE_H];
-  __shared__ int tp0[VM_FAST_MAX_TILE_H], tp1[VM_FAST_MAX_TILE_H];
-  __shared__ int pcol[NW][CAPW];
-  __shared__ float pval[NW][CAPW][K];
-  __shared__ double sm_red[8];
-  const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
+  extern __shared__ __align__(16) unsigned char vm_fast_smem[];
+  FastSmem<K, SIMPLE>& S = *reinterpret_cast<FastSmem<K, SIMPLE>*>(vm_fast_smem);
+  const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt, M = (int)c.M;
   const int ct = blockIdx.x;
   const int l = blockIdx.y / rtn, rt = rt0 + (blockIdx.y - l * rtn);  // row tiles [rt0, rt0+rtn) of every layer
   if (!vm_fast_tile<K>(c, l, ct)) return;
@@ -1064,7 +1153,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
   double cat = 0.0;
   const bool simple_on = SIMPLE && lc[VM_LC_SIMPLE(K)] != 0.0;
   const float* patch_src = simple_on ? c.u_patch : c.rho_u32;
-  float gk[K], p0acc[K];
+  float gk[K], p0acc[K], nuacc = 0.f;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     gk[k] = simple_on ? (float)lc[VM_LC_G(K, k)] : 0.f;
@@ -1075,35 +1164,55 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
   for (int idx = tid; idx < TW; idx += VM_DENSE_THREADS) {
 #pragma unroll
     for (int k = 1; k < K; ++k) {
-      qs[k - 1][idx] = __ldg(&c.tab_q[((int64_t)l * N + jt + idx) * K + k]);
-      colbuf[k - 1][idx] = 0.f;
+      S.qs[k - 1][idx] = __ldg(&c.tab_q[((int64_t)l * N + jt + idx) * K + k]);
+      S.colbuf[k - 1][idx] = 0.f;
     }
-    if (simple_on) qact[idx] = c.er_node[(int64_t)l * N + jt + idx] > 0.0 ? 1 : 0;  // column node is an active reporter
+    if (simple_on) {
+      const int j = jt + idx;
+      S.qact[idx] = c.er_node[(int64_t)l * N + j] > 0.0 ? 1 : 0;  // column node is an active reporter
+      double2 ge = make_double2(0.0, 0.0);
+      if (j < M) ge = *reinterpret_cast<const double2*>(c.GE_theta + 2 * ((int64_t)l * M + j));
+      S.qg[idx] = (float)ge.x;
+      S.qel[idx] = (float)(ge.y * VM_LOG2E);
+    }
   }
   for (int r = tid; r < nrows; r += VM_DENSE_THREADS) {
     const int64_t lrow = (int64_t)l * nloc + i_lo + r;
 #pragma unroll
-    for (int k = 1; k < K; ++k) ps[k - 1][r] = __ldg(&c.tab_p[lrow * K + k]);
-    tp0[r] = __ldg(&c.utile_ptr[lrow * nct + ct]);
-    tp1[r] = __ldg(&c.utile_ptr[lrow * nct + ct + 1]);
+    for (int k = 1; k < K; ++k) S.ps[k - 1][r] = __ldg(&c.tab_p[lrow * K + k]);
+    S.tp0[r] = __ldg(&c.utile_ptr[lrow * nct + ct]);
+    S.tp1[r] = __ldg(&c.utile_ptr[lrow * nct + ct + 1]);
     if (simple_on) {
-      const double er = c.er_node[(int64_t)l * N + (int)c.row0 + i_lo + r];
-      ract[r] = er > 0.0 ? 1 : 0;
+      const int i = (int)c.row0 + i_lo + r;
+      const double er = c.er_node[(int64_t)l * N + i];
+      S.ract[r] = er > 0.0 ? 1 : 0;
 #pragma unroll
-      for (int k = 1; k < K; ++k) ps2[k - 1][r] = (float)(-er * lc[VM_LC_D(K, k)]);  // tab_p without its constant c_k
+      for (int k = 1; k < K; ++k) S.ps2[k - 1][r] = (float)(-er * lc[VM_LC_D(K, k)]);  // tab_p without its constant c_k
+      double2 ge = make_double2(0.0, 0.0);
+      if (i < M) ge = *reinterpret_cast<const double2*>(c.GE_theta + 2 * ((int64_t)l * M + i));
+      S.rg[r] = (float)ge.x;
+      S.rel[r] = (float)(ge.y * VM_LOG2E);
     }
+  }
+  if (simple_on && tid < K) {
+    const double g0 = c.G_lambda[l * K], gkk = c.G_lambda[l * K + tid];
+    S.lam[tid] = (float)gkk;
+    S.lam[K + tid] = (float)(gkk - g0);
+    S.lam[2 * K + tid] = (float)(c.Elog_lambda[l * K + tid] * VM_LOG2E);
+    if (tid == 0) S.lam[3 * K] = (float)c.nu[VM_NU_G];
   }
   __syncthreads();
   // ---- phase 1: stage the patch data of this warp's rows asynchronously
   {
     int off = 0;
     for (int r = warp; r < nrows; r += NW) {
-      const int ua = tp0[r], n = tp1[r] - ua;
+      const int ua = S.tp0[r], n = S.tp1[r] - ua;
       const int take = min(n, CAPW - off);
       for (int e = lane; e < take; e += 32) {
-        vm_cp_async4(&pcol[warp][off + e], &c.u_col[ua + e]);
+        vm_cp_async4(&S.pcol[warp][off + e], &c.u_col[ua + e]);
 #pragma unroll
-        for (int k = 0; k < K; ++k) vm_cp_async4(&pval[warp][off + e][k], &patch_src[(int64_t)(ua + e) * K + k]);
+        for (int k = 0; k < K; ++k) vm_cp_async4(&S.pval[warp][off + e][k], &patch_src[(int64_t)(ua + e) * K + k]);
+        if (simple_on) vm_cp_async4(&S.pxt[warp][off + e], &c.u_pxt[ua + e]);
       }
       off += take;
     }
@@ -1129,7 +1238,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
     const int64_t lrow = (int64_t)l * nloc + i_lo + r;
     float p[K];
 #pragma unroll
-    for (int k = 1; k < K; ++k) p[k] = ps[k - 1][r];
+    for (int k = 1; k < K; ++k) p[k] = S.ps[k - 1][r];
     float rowacc[K];
 #pragma unroll
     for (int k = 1; k < K; ++k) rowacc[k] = 0.f;
@@ -1139,7 +1248,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
     for (int ch = 0; ch < NCH; ++ch) {
       float qv[K][4];
 #pragma unroll
-      for (int k = 1; k < K; ++k) vm_load_q4<K>(&qs[k - 1][ch * 128], lane, qv[k]);
+      for (int k = 1; k < K; ++k) vm_load_q4<K>(&S.qs[k - 1][ch * 128], lane, qv[k]);
       float o[4 * K];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -1161,7 +1270,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
         }
         if (ELBO) cat += (double)vm_formula_cat<K>(&o[t * K], s, false, lp0, lpk, epsf);
       }
-      vm_store_chunk<K>(dst + (int64_t)ch * 128 * K, lane, o, stage[warp]);
+      vm_store_chunk<K>(dst + (int64_t)ch * 128 * K, lane, o, S.stage[warp]);
       if (ch < 5) {  // step `ch` of the previous row's reduction (same order as warp_sum: 16, 8, 4, 2, 1)
 #pragma unroll
         for (int k = 1; k < K; ++k) prev[k] += __shfl_down_sync(0xffffffffu, prev[k], 16 >> ch);
@@ -1187,49 +1296,87 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
       waited = true;
     }
     __syncwarp();
-    const int ua = tp0[r], n = tp1[r] - ua;
+    const int ua = S.tp0[r], n = S.tp1[r] - ua;
     const int take = min(n, CAPW - off);
     long long rq[K];  // this lane's share of the row reporter's correction (fixed point)
 #pragma unroll
     for (int k = 0; k < K; ++k) rq[k] = 0ll;
     for (int e = lane; e < n; e += 32) {
       int col;
-      float v[K];
+      float v[K], xt = 0.f;
       if (e < take) {
-        col = pcol[warp][off + e];
+        col = S.pcol[warp][off + e];
 #pragma unroll
-        for (int k = 0; k < K; ++k) v[k] = pval[warp][off + e][k];
+        for (int k = 0; k < K; ++k) v[k] = S.pval[warp][off + e][k];
+        if (SIMPLE && simple_on) xt = S.pxt[warp][off + e];
       } else {  // more special ties than the per-warp stage holds
         col = c.u_col[ua + e];
 #pragma unroll
         for (int k = 0; k < K; ++k) v[k] = patch_src[(int64_t)(ua + e) * K + k];
+        if (SIMPLE && simple_on) xt = c.u_pxt[ua + e];
       }
       float* d = rowdst + (int64_t)col * K;
       if (SIMPLE && simple_on && v[0] < 0.f) {
-        // a simple special tie: (-X, lo_1, ..): evaluate it, and the closed form the sweep above counted for it
+        // a shortcut tie: (-X, lo_1, ..): evaluate it, and the closed form the sweep above counted for it
         const float X = -v[0];
         const int cj = col - jt;
+        const bool single = xt != 0.f;
+        float dat[K], iden[K], z2 = 0.f;  // dat_k: data term of the log2-odds against k = 0
+#pragma unroll
+        for (int k = 0; k < K; ++k) iden[k] = 0.f;
+        if (!single) {
+#pragma unroll
+          for (int k = 1; k < K; ++k) dat[k] = X * gk[k];
+        } else {
+          // Poisson split of the tie's one report between the theta lambda_k signal and the reciprocity term
+          // (model.py:686-696): f_k = z1_k/(z1_k+z2); data term x[(f_k-f_0) E[log theta] + f_k E[log lambda_k] - f_0 E[log lambda_0]]
+          const bool rowrep = xt > 0.f;
+          const float g = rowrep ? S.rg[r] : S.qg[cj];
+          const float el = rowrep ? S.rel[r] : S.qel[cj];
+          z2 = S.lam[3 * K] * fabsf(xt);
+          float f[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const float z1 = g * S.lam[k];
+            iden[k] = __frcp_rn(z1 + z2);
+            f[k] = z1 * iden[k];
+          }
+          const float t0 = z2 * g * iden[0];
+#pragma unroll
+          for (int k = 1; k < K; ++k)
+            dat[k] = X * ((t0 * iden[k] * S.lam[K + k]) * el + (f[k] * S.lam[2 * K + k] - f[0] * S.lam[2 * K]));
+        }
         float es[K], ef[K], s = 0.f, sf = 0.f;
 #pragma unroll
         for (int k = 1; k < K; ++k) {
-          const float qk = qs[k - 1][cj];
-          es[k] = vm_ex2(fminf(ps2[k - 1][r] + qk + v[k] + X * gk[k], VM_CLAMP_LOG2));
+          const float qk = S.qs[k - 1][cj];
+          es[k] = vm_ex2(fminf(S.ps2[k - 1][r] + qk + v[k] + dat[k], VM_CLAMP_LOG2));
           s += es[k];
           ef[k] = vm_ex2(fminf(__fadd_rn(p[k], qk), VM_CLAMP_LOG2));  // same operations as the sweep: same bits
           sf = (k == 1) ? ef[k] : __fadd_rn(sf, ef[k]);
         }
-        const float inv = vm_rcp(1.f + s), invf = vm_rcp(__fadd_rn(1.f, sf));
+        const float inv = __frcp_rn(1.f + s), invf = vm_rcp(__fadd_rn(1.f, sf));
         d[0] = inv;
-        p0acc[0] += inv * X;
-        const bool act_j = qact[cj] != 0, act_i = ract[r] != 0;
+        float nu_t = inv * iden[0];
+        if (!single) p0acc[0] += inv * X;
+        const bool act_j = S.qact[cj] != 0, act_i = S.ract[r] != 0;
 #pragma unroll
         for (int k = 1; k < K; ++k) {
           const float rk = es[k] * inv, fk = __fmul_rn(ef[k], invf);
           d[k] = rk;
-          p0acc[k] += rk * X;
+          if (!single) p0acc[k] += rk * X;
+          nu_t += rk * iden[k];
           const long long q = __double2ll_rn(((double)rk - (double)fk) * VM_FIX_SCALE);
           if (act_j && q != 0) atomicAdd(fix_l + (int64_t)col * K + k, (unsigned long long)q);
           if (act_i) rq[k] += q;
+        }
+        if (single) {
+          // sum_k dz2_k rho_k = x z2 sum_k rho_k/(z1_k+z2)  (model.py:822-825), and the posterior the gamma/phi passes gather
+          nuacc += X * z2 * nu_t;
+          float* ru = c.rho_u32 + (int64_t)(ua + e) * K;
+          ru[0] = inv;
+#pragma unroll
+          for (int k = 1; k < K; ++k) ru[k] = es[k] * inv;
         }
       } else {
 #pragma unroll
@@ -1265,7 +1412,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
 #pragma unroll
         for (int k = 1; k < K; ++k)
 #pragma unroll
-          for (int t = 0; t < 4; ++t) colbuf[k - 1][ch * 128 + vm_tie_of<K>(lane, t)] += colacc[ch][k - 1][t];
+          for (int t = 0; t < 4; ++t) S.colbuf[k - 1][ch * 128 + vm_tie_of<K>(lane, t)] += colacc[ch][k - 1][t];
     }
     __syncthreads();
   }
@@ -1273,20 +1420,25 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
     float* cp = c.colpart + (((int64_t)l * nrt + rt) * N + jt + idx) * K;
     cp[0] = 0.f;
 #pragma unroll
-    for (int k = 1; k < K; ++k) cp[k] = colbuf[k - 1][idx];
+    for (int k = 1; k < K; ++k) cp[k] = S.colbuf[k - 1][idx];
   }
   if (ELBO) {
-    const double v = block_sum<VM_DENSE_THREADS>(cat, sm_red);
+    const double v = block_sum<VM_DENSE_THREADS>(cat, S.sm_red);
     if (tid == 0) catpart[((int64_t)l * nrt + rt) * nct + ct] = v;
   }
-  if (SIMPLE && simple_on) {  // rho_k X of the simple ties of this tile: their part of the next phi-shape sums (phi0)
+  if (SIMPLE && simple_on) {
+    // rho_k X of the SIMPLE ties of this tile: their part of the next phi-shape sums (phi0); nu statistic of the SINGLE ties
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      const double v = block_sum<VM_DENSE_THREADS>((double)p0acc[k], sm_red);
+      const double v = block_sum<VM_DENSE_THREADS>((double)p0acc[k], S.sm_red);
       if (tid == 0 && v != 0.0)
         atomicAdd(reinterpret_cast<unsigned long long*>(c.fixP) + l * K + k,
                   (unsigned long long)__double2ll_rn(v * VM_FIXP_SCALE));
     }
+    const double vn = block_sum<VM_DENSE_THREADS>((double)nuacc, S.sm_red);
+    if (tid == 0 && vn != 0.0)
+      atomicAdd(reinterpret_cast<unsigned long long*>(c.dev_flags) + VM_FLAG_FIXNU,
+                (unsigned long long)__double2ll_rn(vn * VM_FIXP_SCALE));
   }
 }
 
@@ -1501,7 +1653,7 @@ __global__ void __launch_bounds__(256) k_init_delta_all(const __grid_constant__ 
 template <int K>
 __global__ void __launch_bounds__(256) k_elbo_b(const __grid_constant__ vm_ctx c, double* part) {
   __shared__ double sm[8];
-  bool any = c.dev_flags[0] != 0 || c.may_dead != 0;
+  bool any = c.dev_flags[VM_FLAG_DEAD] != 0 || c.may_dead != 0;
   for (int l = 0; l < (int)c.L && !any; ++l) any = c.layer_consts[(int64_t)l * VM_LC_STRIDE(K) + VM_LC_DEAD(K)] != 0.0;
   if (!any) {
     if (threadIdx.x == 0) part[blockIdx.x] = 0.0;
@@ -1580,7 +1732,8 @@ __global__ void __launch_bounds__(256) k_sums_reduce(const __grid_constant__ vm_
   b = block_sum<256>(b, sm);
   if (threadIdx.x == 0) {
     double* ex = c.red3 + c.L * c.M * c.K;
-    ex[VM_R3_NU] = nu;
+    // + the SINGLE ties the fast dense kernel evaluated this iteration (0 on every other iteration)
+    ex[VM_R3_NU] = nu + ((c.simple_mode && !(flags & VM_F_INIT)) ? (double)c.dev_flags[VM_FLAG_FIXNU] * (1.0 / VM_FIXP_SCALE) : 0.0);
     ex[VM_R3_CAT] = cat;
     ex[VM_R3_T2] = t2;
     ex[VM_R3_B] = elbo ? c.b_all - b : 0.0;
@@ -1744,6 +1897,24 @@ static bool simple_iteration(const vm_ctx* c, int flags) {
          dense_fast_eligible<K>(c, flags);
 }
 
+// dynamic shared memory of the fast dense kernel (opt-in above 48 KB; set once per process and instantiation)
+template <int K, bool ELBO, bool SIMPLE>
+static cudaError_t fast_setup() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(k_dense_fast<K, ELBO, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(FastSmem<K, SIMPLE>));
+  done = (e == cudaSuccess);
+  return e;
+}
+template <int K>
+static cudaError_t fast_setup_all() {
+  cudaError_t e;
+  if ((e = fast_setup<(K <= 4 ? K : 2), true, false>()) != cudaSuccess) return e;
+  if ((e = fast_setup<(K <= 4 ? K : 2), false, true>()) != cudaSuccess) return e;
+  return fast_setup<(K <= 4 ? K : 2), false, false>();
+}
+
 template <int K>
 static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, int rtn) {
   if (rtn <= 0) return 0;
@@ -1752,25 +1923,40 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, in
   double* cp = region_cat(c);
   const bool fast = dense_fast_eligible<K>(c, flags);
   const bool simple = simple_iteration<K>(c, flags);
+  constexpr int KF = (K <= 4 ? K : 2);
+  if (fast) {
+    const cudaError_t e = fast_setup_all<K>();
+    if (e != cudaSuccess) return (int)e;
+  }
   // The general kernel only has the tiles the fast one leaves (the partial last column tile: 157 of 6280 CTAs at config 3,
   // each a serial sweep of its rows, 32 us): it goes to the caller's aux stream, forked from and joined back into `st`,
   // so that it runs under the fast kernel instead of after it.  The two write disjoint tiles and disjoint partial slots.
+  // The fork/join events are the caller's (vm_ctx.ev_fork / ev_join, created once per engine); without them a pair is
+  // created and destroyed here.
   cudaStream_t aux = (cudaStream_t)c->aux_stream;
   const bool side = fast && aux != nullptr && aux != st;
   cudaStream_t sg = side ? aux : st;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  if (side) {
+  cudaEvent_t ev_fork = (cudaEvent_t)c->ev_fork, ev_join = (cudaEvent_t)c->ev_join;
+  bool own_events = false;
+  if (side && (ev_fork == nullptr || ev_join == nullptr)) {
+    ev_fork = ev_join = nullptr;
     if (cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)
-      return (int)cudaGetLastError();
+        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      const cudaError_t e = cudaGetLastError();
+      if (ev_fork) cudaEventDestroy(ev_fork);
+      return (int)e;
+    }
+    own_events = true;
+  }
+  if (side) {
     cudaEventRecord(ev_fork, st);
     cudaStreamWaitEvent(aux, ev_fork, 0);
   }
-#define LF()                                                                                                   \
-  do {                                                                                                         \
-    if (elbo) k_dense_fast<(K <= 4 ? K : 2), true><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, rt0, rtn);        \
-    else if (simple) k_dense_fast<(K <= 4 ? K : 2), false, true><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, rt0, rtn); \
-    else k_dense_fast<(K <= 4 ? K : 2), false><<<grid, VM_DENSE_THREADS, 0, st>>>(*c, cp, rt0, rtn);            \
+#define LF()                                                                                                             \
+  do {                                                                                                                   \
+    if (elbo) k_dense_fast<KF, true><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<KF, false>), st>>>(*c, cp, rt0, rtn);       \
+    else if (simple) k_dense_fast<KF, false, true><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<KF, true>), st>>>(*c, cp, rt0, rtn); \
+    else k_dense_fast<KF, false><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<KF, false>), st>>>(*c, cp, rt0, rtn);           \
   } while (0)
   if (fast && !side) LF();
   int rc = 0;
@@ -1788,8 +1974,10 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, in
     LF();
     cudaEventRecord(ev_join, aux);
     cudaStreamWaitEvent(st, ev_join, 0);
-    cudaEventDestroy(ev_fork);  // destruction is deferred by the runtime until the events have completed
-    cudaEventDestroy(ev_join);
+    if (own_events) {
+      cudaEventDestroy(ev_fork);  // destruction is deferred by the runtime until the events have completed
+      cudaEventDestroy(ev_join);
+    }
   }
 #undef LF
   return rc;
@@ -1832,7 +2020,11 @@ static int launch_rho_kernels(const vm_ctx* c, int flags, cudaStream_t st) {
   if (e != cudaSuccess) return (int)e;
   for (int q = 0; q < VM_NCHUNK; ++q) {
     e = cudaEventCreateWithFlags(&ev[q], cudaEventDisableTiming);
-    if (e != cudaSuccess) return (int)e;
+    if (e != cudaSuccess) {
+      cudaEventDestroy(ev_fork);
+      for (int p = 0; p < q; ++p) cudaEventDestroy(ev[p]);
+      return (int)e;
+    }
   }
   // main stream: special-tie chunks back to back; aux stream (the caller gives it a HIGHER priority): dense chunk q as
   // soon as special chunk q is done, so that dense CTAs take every slot that frees up and the special-tie kernel of the
@@ -1895,6 +2087,11 @@ static int tu_init_stats(const vm_ctx* c, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  {  // function attributes are set here, outside any stream capture
+    cudaError_t e = cudaSuccess;
+    DISPATCH_K(c->K, e = fast_setup_all<K>());
+    if (e != cudaSuccess) return (int)e;
+  }
   if (c->r_mode == VM_R_EGO) {
     cudaMemsetAsync(c->fixA, 0, (size_t)(c->L * c->M * c->K) * sizeof(int64_t), st);
     VM_CHECK_LAUNCH();
@@ -1938,7 +2135,7 @@ static int tu_phase_phi(const vm_ctx* c, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH_K(c->K, (k_gamma_finish<K><<<(unsigned)cdiv(c->L * c->M, 256), 256, 0, st>>>(*c)));
+  DISPATCH_K(c->K, (k_gamma_finish<K><<<dim3((unsigned)cdiv(c->M, VM_GF_THREADS), (unsigned)c->L), VM_GF_THREADS, 0, st>>>(*c)));
   VM_CHECK_LAUNCH();
   DISPATCH_K(c->K, (k_phi_partial<K><<<dim3((unsigned)c->n_phichunk, (unsigned)c->L), 256, 0, st>>>(*c, c->blkpart)));
   VM_CHECK_LAUNCH();
@@ -1951,7 +2148,7 @@ static int tu_phase_rho(const vm_ctx* c, int flags, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH_K(c->K, (k_phi_finish<K><<<(unsigned)c->L, 1024, 0, st>>>(*c)));
+  DISPATCH_K(c->K, (k_phi_finish<K><<<(unsigned)c->L, 256, 0, st>>>(*c)));
   VM_CHECK_LAUNCH();
   if (c->r_mode != VM_R_CSR) {
     DISPATCH_K(c->K, (k_tables<K><<<(unsigned)cdiv(c->L * c->N, 256), 256, 0, st>>>(*c)));

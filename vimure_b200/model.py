@@ -231,6 +231,12 @@ class VimureModel(TransformerMixin, BaseEstimator):
             group = True if world > 1 else None
         self._world, self._rank = world, rank
         row0, nloc = shard_rows(self.N, world, rank)
+        if world > 1:
+            # Every rank must draw the same initial gamma/phi/nu and derive the same restart seeds, or the replicated
+            # parameters diverge and the ranks leave the loop at different iterations (a hang in the next all-reduce).
+            # With seed=None the reference seeds from the OS; here rank 0 does and the others adopt its choice.
+            self.prng = np.random.RandomState(_agree_int(
+                int(np.random.SeedSequence().generate_state(1)[0] % (2**31 - 1)) if seed is None else int(seed), dev))
 
         self.timings = {"check_params": t_check}
         with torch.cuda.device(dev):
@@ -243,7 +249,10 @@ class VimureModel(TransformerMixin, BaseEstimator):
                                              row0=row0, nloc=nloc, tile_h=int(extra_params.get("tile_h", 128)),
                                              mutuality=self.mutuality, split_e0=split_e0)
             if self.undirected:  # model.py:127-132: X must be symmetric in (i, j)
-                if not bool(torch.all(P.t["e_xT"] == P.t["e_x"])):
+                asym = int(not bool(torch.all(P.t["e_xT"] == P.t["e_x"])))
+                if world > 1:  # every rank raises, or none does
+                    asym = _agree_int(asym, dev, op="max")
+                if asym:
                     msg = "If undirected is True, the given network has to be symmetric wrt l and m!"
                     self.logger.error(msg)
                     raise ValueError(msg)
@@ -305,6 +314,8 @@ class VimureModel(TransformerMixin, BaseEstimator):
                     t_start = time.time()
                     eng.iterate(n, elbo_last=True, store=self._store_rho, store_last=True)
                     new_elbo = eng.elbo()  # the one D2H scalar (also syncs)
+                    if world > 1:  # identical on every rank by construction; rank 0's value decides all the same
+                        new_elbo = _agree_float(new_elbo, dev)
                     runtime = (time.time() - t_start) / n
                     # `_check_for_convergence`, model.py:1036-1056
                     if np.isnan(new_elbo):
@@ -483,16 +494,18 @@ class VimureModel(TransformerMixin, BaseEstimator):
                     pr = 1 + 0.01 * _packing.reference_prior_draws(self.prng, L, N, K, want)
                     pr[:, 0] += bias0
             else:
-                pr = 1 + 0.01 * self.prng.random_sample((len(kidx), K))
+                # one draw of the host stream whatever the number of ties this rank owns, then a counter-based uniform
+                # keyed by the GLOBAL tie (undirected: by the unordered pair, so that (i,j) and (j,i) get the same
+                # prior, model.py:477-478, even when they live on different ranks)
+                key0 = int(self.prng.randint(0, 2**31 - 1))
+                tie = flat[kidx]
+                if self.undirected:
+                    l_ = tie // (N * N)
+                    i_ = (tie // N) % N
+                    j_ = tie % N
+                    tie = (l_ * N + np.minimum(i_, j_)) * N + np.maximum(i_, j_)
+                pr = 1 + 0.01 * _keyed_uniform(key0, tie, K)
                 pr[:, 0] += bias0
-                if self.undirected:  # same draw for (i,j) and (j,i): key the draw on the unordered pair
-                    l_ = flat[kidx] // (N * N)
-                    i_ = (flat[kidx] // N) % N
-                    j_ = flat[kidx] % N
-                    pair = (l_ * N + np.minimum(i_, j_)) * N + np.maximum(i_, j_)
-                    _, first = np.unique(pair, return_index=True)
-                    _, inv = np.unique(pair, return_inverse=True)
-                    pr = pr[first][inv]
             pr /= pr.sum(axis=-1)[:, None]
             pr_u[kidx] = pr
         else:
@@ -736,6 +749,37 @@ class VimureModel(TransformerMixin, BaseEstimator):
     def get_posterior_estimates(self):
         """Posterior estimates nu, theta, lambda, rho (reference model.py:1191-1214)."""
         return {"nu": self.G_exp_nu_f, "theta": self.G_exp_theta_f, "lambda": self.G_exp_lambda_f, "rho": self.rho_f}
+
+
+def _agree_int(v, dev, op="bcast"):
+    """Rank 0's integer (op="bcast") or the maximum over the ranks (op="max"), on every rank."""
+    t = torch.tensor([int(v)], dtype=torch.int64, device=dev)
+    if op == "max":
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    else:
+        torch.distributed.broadcast(t, src=0)
+    return int(t.item())
+
+
+def _agree_float(v, dev):
+    t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+    torch.distributed.broadcast(t, src=0)
+    return float(t.item())
+
+
+def _keyed_uniform(key, ids, K):
+    """Counter-based uniforms in [0, 1): (len(ids), K) doubles, a pure function of (key, id, k) -- splitmix64 finaliser.
+    Used where the draw must not depend on how the ties are distributed over ranks."""
+    ids = np.asarray(ids, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        x = (ids[:, None] * np.uint64(K) + np.arange(K, dtype=np.uint64)[None, :]) + \
+            np.uint64(key) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0x9E3779B97F4A7C15)
+        x ^= x >> np.uint64(30)
+        x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27)
+        x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+    return (x >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
 
 
 def shard_rows(N, world, rank):
