@@ -64,9 +64,11 @@ extern "C" {
 #define VM_FLAG_DEAD 0
 #define VM_FLAG_FIXNU 1
 
-/* maximum K compiled in (K = number of categories of a report, max(X)+1: 2..4 in every BASELINE config and in the
-   reference's tests; the kernels are templates on K, one translation unit per group of K) */
-#define VM_MAX_K 8
+/* maximum K compiled in.  K = number of categories of a report; when the caller does not pass K the reference defaults to
+   max(X)+1 (model.py:179-196), which for count data easily exceeds 8 -- hence 32, although every BASELINE config has
+   K <= 3.  The kernels are templates on K, one translation unit per group of K (vimure_b200/build.py); K > 4 only
+   instantiates the general kernels. */
+#define VM_MAX_K 32
 /* special ties handled by one block of the special-tie kernel (n_ublk = ceil(max per layer / this)) */
 #ifndef VM_SPECIAL_TIES_PER_BLOCK /* (a timing variant may be built with a multiple of it: tools/ab_libs.py) */
 #define VM_SPECIAL_TIES_PER_BLOCK 1024
@@ -303,6 +305,30 @@ int vm_infer(const vm_ctx* c, int mode, double threshold, uint8_t* out, void* st
  * keyed by `seed` and the GLOBAL tie id: reproducible, independent of launch geometry and of the sharding.  The stream is
  * not numpy's (the reference draws with numpy.random.default_rng(seed)). */
 int vm_sample(const vm_ctx* c, int64_t n_trials, uint64_t seed, uint8_t* out, void* stream);
+
+/* ---- device-side synthetic reports (the "next" row f2 of SURVEY.md section 8) ----------------------------------------
+ * Samples the observed network X of the reference's `_build_X` under the self-reporter (ego) mask
+ * (synthetic.py:138-209; mask synthetic.py:1184-1204) for ONE node-row block [row0, row0+nloc), sparsely, with a
+ * counter-based RNG keyed by (seed, layer, reporter, partner): every rank generates exactly the entries of its own rows
+ * (plus, with emit_transposed, the reciprocal entries X[l,j,i,m] whose row j it does not own, so that its shard pairs
+ * without any exchange), and all ranks agree on every entry.  Output: unordered COO (o_l,o_i,o_j,o_m,o_x); *counter = the
+ * number of entries produced -- if it exceeds `cap` the arrays hold only the first `cap` and the caller retries with more room. */
+typedef struct vm_synth {
+  int64_t L, N, M, K;
+  int64_t row0, nloc;
+  int64_t emit_transposed;   /* also emit X[l,j,i,m] for owned (i,j) when row j is not owned */
+  uint64_t seed;
+  double eta;                /* mutuality of the reports, in [0,1) */
+  const double* theta;       /* [L*M] reporter reliabilities */
+  const int64_t* y_key;      /* [nY] sorted keys (l*N+i)*N+j of the true ties Y (ground truth, a few per node) */
+  const int32_t* y_val;      /* [nY] Y_lij >= 1 */
+  int64_t nY;
+  int64_t cap;               /* capacity of the output arrays */
+  int32_t* o_l; int32_t* o_i; int32_t* o_j; int32_t* o_m; int32_t* o_x;
+  int64_t* counter;          /* [1] device */
+} vm_synth;
+int64_t vm_synth_size(void);
+int vm_synth_ego(const vm_synth* s, void* stream);
 
 /* Special functions exposed for testing the device implementations against scipy. */
 int vm_test_special(const double* x, double* out_digamma, double* out_lgamma, int64_t n, void* stream);

@@ -1,5 +1,5 @@
 """Edge cases of the path against the CPU oracle: completely underflowed rows (Q3), a large EPS (closed form no longer
-negligible), a layer without any report, reporters that are a subset of the nodes (M < N), K = 8 (the largest K compiled in)."""
+negligible), a layer without any report, reporters that are a subset of the nodes (M < N), K = 12 (a general-kernel-only K; the default K = max(X)+1 of count data lands there)."""
 import numpy as np
 import pytest
 
@@ -127,7 +127,7 @@ def test_layer_without_reports_and_subset_of_reporters():
     _run(2, 56, 40, 2, subs, vals, mask, spec, _state(2, 40, 2, 4), PRI, iters=4)
 
 
-def test_k8_largest_k_compiled_in():
-    net = _net(40, 40, 1, 8, seed=21, law="gm", eta=0.5)
+def test_k12_large_k_build():
+    net = _net(40, 40, 1, 12, seed=21, law="gm", eta=0.5)
     spec = {"kind": "ego", "rep": np.ones((1, 40), dtype=np.uint8), "diag": True}
-    _run(1, 40, 40, 8, np.stack(net.X.subs), net.X.vals, net.R, spec, _state(1, 40, 8, 6), PRI, iters=3)
+    _run(1, 40, 40, 12, np.stack(net.X.subs), net.X.vals, net.R, spec, _state(1, 40, 12, 6), PRI, iters=3)

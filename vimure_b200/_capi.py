@@ -17,10 +17,8 @@ _ctx_cls = None
 _consts = None
 
 
-def _parse_header():
-    src = open(HEADER).read()
-    consts = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+(VM_\w+)\s+\(?(-?\d+)\)?\s", src)}
-    body = re.search(r"typedef struct vm_ctx \{(.*?)\}\s*vm_ctx;", src, re.S).group(1)
+def _parse_struct(src, name):
+    body = re.search(r"typedef struct %s \{(.*?)\}\s*%s;" % (name, name), src, re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = []
     for decl in body.split(";"):
@@ -37,12 +35,36 @@ def _parse_header():
                 ctype = ctypes.c_void_p
             elif base == "int64_t":
                 ctype = ctypes.c_int64
+            elif base == "uint64_t":
+                ctype = ctypes.c_uint64
             elif base == "double":
                 ctype = ctypes.c_double
             else:
-                raise RuntimeError("vm_ctx may only hold int64_t/double/pointers, got %r" % decl)
+                raise RuntimeError("%s may only hold int64_t/double/pointers, got %r" % (name, decl))
             fields.append((name, ctype))
-    return fields, consts
+    return fields
+
+
+def _parse_header():
+    src = open(HEADER).read()
+    consts = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+(VM_\w+)\s+\(?(-?\d+)\)?\s", src)}
+    return _parse_struct(src, "vm_ctx"), consts
+
+
+_synth_cls = None
+
+
+def synth_class():
+    """ctypes mirror of `vm_synth` (device-side synthetic reports), generated from the header."""
+    global _synth_cls
+    if _synth_cls is None:
+        fields = _parse_struct(open(HEADER).read(), "vm_synth")
+
+        class VmSynth(ctypes.Structure):
+            _fields_ = fields
+
+        _synth_cls = VmSynth
+    return _synth_cls
 
 
 def header_symbols():
@@ -105,6 +127,8 @@ def open_library(path):
         "vm_infer": (i, [P, i, d, vp, vp]),
         "vm_sample": (i, [P, i64, ctypes.c_uint64, vp, vp]),
         "vm_test_special": (i, [vp, vp, vp, i64, vp]),
+        "vm_synth_size": (i64, []),
+        "vm_synth_ego": (i, [ctypes.POINTER(synth_class()), vp]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -113,6 +137,8 @@ def open_library(path):
     if lib.vm_ctx_size() != ctypes.sizeof(Ctx):
         raise RuntimeError("vm_ctx layout mismatch: library %d bytes, python mirror %d bytes (stale build?)"
                            % (lib.vm_ctx_size(), ctypes.sizeof(Ctx)))
+    if lib.vm_synth_size() != ctypes.sizeof(synth_class()):
+        raise RuntimeError("vm_synth layout mismatch between header and library (stale build?)")
     if lib.vm_abi_version() != consts()["VM_ABI_VERSION"]:
         raise RuntimeError("vimure_b200: ABI version mismatch between header and library (stale build?)")
     return lib

@@ -21,7 +21,7 @@ def dense_tile_w(K):
 
     w = int(_capi.load().vm_dense_tile_w(int(K)))
     if w <= 0:
-        raise ValueError("vimure_b200 supports 2 <= K <= 8 = VM_MAX_K (got K=%d)" % K)
+        raise ValueError("vimure_b200 supports 2 <= K <= 32 = VM_MAX_K (got K=%d)" % K)
     return w
 
 GAMMA_CHUNK = 256
@@ -113,14 +113,28 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
         return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
     small = max(L, N, M) < 2**31
-    xl, xi, xj, xm = (_up(X_subs[d], small).to(torch.int64) for d in range(4))
-    xv = _up(X_vals, small and np.asarray(X_vals).dtype.kind in "iu").to(torch.float64)
-    I_all = xv.numel()
-    if I_all:
+    xl, xi, xj, xm = (_up(X_subs[d], small) for d in range(4))
+    xv = _up(X_vals, small and (torch.is_tensor(X_vals) or np.asarray(X_vals).dtype.kind in "iu"))
+    if xv.numel():
         mx = torch.stack([xl.max(), xi.max(), xj.max(), xm.max(), -torch.stack([xl.min(), xi.min(), xj.min(), xm.min()]).min()])
         mx = mx.cpu().numpy()
         if mx[0] >= L or mx[1] >= N or mx[2] >= N or mx[3] >= M or mx[4] > 0:
             raise ValueError("X has subscripts outside its shape")
+    P.sumX_owned = None
+    keep_idx = None
+    if nloc < N and xv.numel():
+        # a row-block shard only needs the entries of its own rows (i in the block) and their reciprocals (j in the block):
+        # everything else is dropped BEFORE the 64-bit keys, the sorts and the pairing (sharded ingestion; with G ranks
+        # about 2/G of the list survives)
+        own_i = (xi >= row0) & (xi < row0 + nloc)
+        need = own_i | ((xj >= row0) & (xj < row0 + nloc))
+        P.sumX_owned = float(xv[own_i].sum())
+        keep_idx = torch.nonzero(need).flatten()
+        xl, xi, xj, xm, xv = xl[keep_idx], xi[keep_idx], xj[keep_idx], xm[keep_idx], xv[keep_idx]
+        del own_i, need
+    xl, xi, xj, xm = (t.to(torch.int64) for t in (xl, xi, xj, xm))
+    xv = xv.to(torch.float64)
+    I_all = xv.numel()
 
     _mark("h2d+check")
     # ---- reciprocal pairing: xT[I] = X[l, j, i, m]   (model.py:152-161)
@@ -154,7 +168,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
     sel = sel[o2]
     I = sel.numel()
     P.I = int(I)
-    P.entry_src = sel  # position of each packed entry in the caller's COO order
+    P.entry_src = sel if keep_idx is None else keep_idx[sel]  # position of each packed entry in the caller's COO order
     del own, tk, o2
 
     _mark("mask+tie sort")

@@ -887,6 +887,9 @@ __device__ __forceinline__ void vm_store_chunk(float* dst, int lane, const float
   } else if (K == 4) {
 #pragma unroll
     for (int t = 0; t < 4; ++t) d4[32 * t + lane] = make_float4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
+  } else if (K > 8) {  // many categories: natural layout (every lane owns 16*K contiguous bytes), no stage
+#pragma unroll
+    for (int v = 0; v < K; ++v) d4[K * lane + v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
   } else {
     float4* s4 = reinterpret_cast<float4*>(stage);
 #pragma unroll
@@ -899,7 +902,7 @@ __device__ __forceinline__ void vm_store_chunk(float* dst, int lane, const float
 }
 template <int K>
 struct StageCfg {
-  static constexpr int FLOATS = (K == 2 || K == 4) ? 4 : 128 * K;  // per-warp stage (unused for K = 2, 4)
+  static constexpr int FLOATS = (K == 2 || K == 4 || K > 8) ? 4 : 128 * K;  // per-warp stage (unused for K = 2, 4, > 8)
 };
 
 // 4 ties of one lane. a[t][k] are the log2-odds; results in o[t*K+k].
@@ -1124,8 +1127,56 @@ struct FastSmem {
   float qg[SIMPLE ? TW : 1], qel[SIMPLE ? TW : 1];   // G_theta, E[log theta] log2e of the column nodes as reporters
   float rg[SIMPLE ? TH : 1], rel[SIMPLE ? TH : 1];   // ... of the row nodes
   float lam[SIMPLE ? 3 * K + 1 : 1];  // G_lambda_k | G_lambda_k - G_lambda_0 | E[log lambda_k] log2e | G_nu
+  unsigned long long rowfix[SIMPLE ? NW : 1][SIMPLE ? TH / NW : 1][K - 1];  // row reporters' corrections (fixed point)
+  int poff[SIMPLE ? NW : 1][SIMPLE ? TH / NW + 1 : 1];         // first staged entry of each of the warp's rows
   unsigned char ract[SIMPLE ? TH : 1], qact[SIMPLE ? TW : 1];  // node is an active reporter
 };
+
+// One shortcut tie (vm_ctx.simple_mode): v = (-X, lo_1..lo_{K-1}), xt = 0 (SIMPLE) or +-x^T (SINGLE; sign = the row / the
+// column node reported).  Returns its posterior rho[0..K), the closed form the row sweep counted for it fcf[1..K) (same
+// operations as the sweep: same bits), and its part of the nu statistic.  One code path for both kinds (no divergence):
+// a SIMPLE tie is the z2 = 0 limit, f_k = 1.
+template <int K, typename SM>
+__device__ __forceinline__ void vm_eval_shortcut(const SM& S, const float* gk, int r, int cj,
+                                                 const float* v, float xt, float* rho, float* fcf, float& nu_c) {
+  const float X = -v[0];
+  const bool single = xt != 0.f, rowrep = xt > 0.f;
+  // Poisson split of a SINGLE tie's one report between the theta lambda_k signal and the reciprocity term
+  // (model.py:686-696): f_k = z1_k/(z1_k+z2); data term x[(f_k-f_0) E[log theta] + f_k E[log lambda_k] - f_0 E[log lambda_0]]
+  const float g = single ? (rowrep ? S.rg[r] : S.qg[cj]) : 1.f;
+  const float el = single ? (rowrep ? S.rel[r] : S.qel[cj]) : 0.f;
+  const float z2 = S.lam[3 * K] * fabsf(xt);
+  float f[K], iden[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float z1 = g * S.lam[k];
+    iden[k] = vm_rcp(z1 + z2);
+    f[k] = single ? z1 * iden[k] : 1.f;
+  }
+  const float t0 = z2 * g * iden[0];
+  float s = 0.f, sf = 0.f, es[K], ef[K];
+#pragma unroll
+  for (int k = 1; k < K; ++k) {
+    const float dat = single ? X * ((t0 * iden[k] * S.lam[K + k]) * el + (f[k] * S.lam[2 * K + k] - f[0] * S.lam[2 * K]))
+                             : X * gk[k];
+    const float qk = S.qs[k - 1][cj];
+    es[k] = vm_ex2(fminf(S.ps2[k - 1][r] + qk + v[k] + dat, VM_CLAMP_LOG2));
+    s += es[k];
+    ef[k] = vm_ex2(fminf(__fadd_rn(S.ps[k - 1][r], qk), VM_CLAMP_LOG2));
+    sf = (k == 1) ? ef[k] : __fadd_rn(sf, ef[k]);
+  }
+  const float inv = vm_rcp(1.f + s), invf = vm_rcp(__fadd_rn(1.f, sf));
+  rho[0] = inv;
+  float nu_t = inv * iden[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) {
+    rho[k] = es[k] * inv;
+    fcf[k] = __fmul_rn(ef[k], invf);
+    nu_t += rho[k] * iden[k];
+  }
+  // sum_k dz2_k rho_k = x z2 sum_k rho_k/(z1_k+z2)  (model.py:822-825); 0 for a SIMPLE tie (z2 = 0)
+  nu_c = X * z2 * nu_t;
+}
 
 // SIMPLE (no ELBO): in the layers flagged VM_LC_SIMPLE the patch source is `u_patch`, whose entries of the shortcut ties
 // (vm_ctx.simple_mode) hold (-X, lo_1..lo_{K-1}) instead of a posterior, with `u_pxt` = 0 (SIMPLE tie) or +-x^T (SINGLE
@@ -1194,6 +1245,9 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
       S.rel[r] = (float)(ge.y * VM_LOG2E);
     }
   }
+  if (SIMPLE) {
+    for (int t = tid; t < NW * (VM_FAST_MAX_TILE_H / NW) * (K - 1); t += VM_DENSE_THREADS) (&S.rowfix[0][0][0])[t] = 0ull;
+  }
   if (simple_on && tid < K) {
     const double g0 = c.G_lambda[l * K], gkk = c.G_lambda[l * K + tid];
     S.lam[tid] = (float)gkk;
@@ -1203,11 +1257,13 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
   }
   __syncthreads();
   // ---- phase 1: stage the patch data of this warp's rows asynchronously
+  int n_staged = 0, n_myrows = 0;
   {
-    int off = 0;
-    for (int r = warp; r < nrows; r += NW) {
+    int off = 0, q = 0;
+    for (int r = warp; r < nrows; r += NW, ++q) {
       const int ua = S.tp0[r], n = S.tp1[r] - ua;
       const int take = min(n, CAPW - off);
+      if (SIMPLE && lane == 0) S.poff[warp][q] = off;
       for (int e = lane; e < take; e += 32) {
         vm_cp_async4(&S.pcol[warp][off + e], &c.u_col[ua + e]);
 #pragma unroll
@@ -1216,6 +1272,9 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
       }
       off += take;
     }
+    if (SIMPLE && lane == 0) S.poff[warp][q] = off;
+    n_staged = off;
+    n_myrows = q;
     vm_cp_async_commit();
   }
   // ---- phase 2: the rows (no global loads on the critical path)
@@ -1294,103 +1353,98 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
     if (!waited) {
       vm_cp_async_wait_all();
       waited = true;
+      __syncwarp();
+      if (SIMPLE && simple_on) {
+        // Evaluate the shortcut ties of ALL the warp's rows now, 32 at a time with every lane busy (a row segment alone
+        // holds ~19 special ties of mixed kinds); the posterior replaces the tie's patch entry in shared memory, so the
+        // per-row loop below only copies.  Statistics as the special-tie kernel would account for them.
+        for (int e = lane; e < n_staged; e += 32) {
+          float v[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) v[k] = S.pval[warp][e][k];
+          if (v[0] < 0.f) {
+            int q = 0;
+#pragma unroll 4
+            for (int t = 1; t < n_myrows; ++t) q += (S.poff[warp][t] <= e) ? 1 : 0;
+            const int rr = warp + NW * q;
+            const int col = S.pcol[warp][e], cj = col - jt;
+            const float xt = S.pxt[warp][e];
+            float rk[K], fk[K], nu_c;
+            vm_eval_shortcut<K>(S, gk, rr, cj, v, xt, rk, fk, nu_c);
+            const bool act_j = S.qact[cj] != 0, act_i = S.ract[rr] != 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) S.pval[warp][e][k] = rk[k];
+#pragma unroll
+            for (int k = 1; k < K; ++k) {
+              const long long fq = __double2ll_rn(((double)rk[k] - (double)fk[k]) * VM_FIX_SCALE);
+              if (act_j && fq != 0) atomicAdd(fix_l + (int64_t)col * K + k, (unsigned long long)fq);
+              if (act_i && fq != 0) atomicAdd(&S.rowfix[warp][q][k - 1], (unsigned long long)fq);
+            }
+            if (xt != 0.f) {  // SINGLE: nu statistic, and the posterior the gamma / phi passes gather
+              nuacc += nu_c;
+              float* ru = c.rho_u32 + (int64_t)(S.tp0[rr] + (e - S.poff[warp][q])) * K;
+#pragma unroll
+              for (int k = 0; k < K; ++k) ru[k] = rk[k];
+            } else {  // SIMPLE: rho_k X, its part of the next phi-shape sums
+              const float X = -v[0];
+#pragma unroll
+              for (int k = 0; k < K; ++k) p0acc[k] += rk[k] * X;
+            }
+          }
+        }
+        __syncwarp();
+      }
     }
     __syncwarp();
     const int ua = S.tp0[r], n = S.tp1[r] - ua;
     const int take = min(n, CAPW - off);
-    long long rq[K];  // this lane's share of the row reporter's correction (fixed point)
-#pragma unroll
-    for (int k = 0; k < K; ++k) rq[k] = 0ll;
+    const int qrow = (r - warp) / NW;
     for (int e = lane; e < n; e += 32) {
       int col;
-      float v[K], xt = 0.f;
+      float v[K];
       if (e < take) {
         col = S.pcol[warp][off + e];
 #pragma unroll
         for (int k = 0; k < K; ++k) v[k] = S.pval[warp][off + e][k];
-        if (SIMPLE && simple_on) xt = S.pxt[warp][off + e];
-      } else {  // more special ties than the per-warp stage holds
+      } else {  // more special ties than the per-warp stage holds: fetched (and, if a shortcut tie, evaluated) here
         col = c.u_col[ua + e];
 #pragma unroll
         for (int k = 0; k < K; ++k) v[k] = patch_src[(int64_t)(ua + e) * K + k];
-        if (SIMPLE && simple_on) xt = c.u_pxt[ua + e];
+        if (SIMPLE && simple_on && v[0] < 0.f) {
+          const int cj = col - jt;
+          const float xt = c.u_pxt[ua + e];
+          float rk[K], fk[K], nu_c;
+          vm_eval_shortcut<K>(S, gk, r, cj, v, xt, rk, fk, nu_c);
+          const bool act_j = S.qact[cj] != 0, act_i = S.ract[r] != 0;
+#pragma unroll
+          for (int k = 1; k < K; ++k) {
+            const long long fq = __double2ll_rn(((double)rk[k] - (double)fk[k]) * VM_FIX_SCALE);
+            if (act_j && fq != 0) atomicAdd(fix_l + (int64_t)col * K + k, (unsigned long long)fq);
+            if (act_i && fq != 0) atomicAdd(&S.rowfix[warp][qrow][k - 1], (unsigned long long)fq);
+          }
+          if (xt != 0.f) {
+            nuacc += nu_c;
+            float* ru = c.rho_u32 + (int64_t)(ua + e) * K;
+#pragma unroll
+            for (int k = 0; k < K; ++k) ru[k] = rk[k];
+          } else {
+            const float X = -v[0];
+#pragma unroll
+            for (int k = 0; k < K; ++k) p0acc[k] += rk[k] * X;
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) v[k] = rk[k];
+        }
       }
       float* d = rowdst + (int64_t)col * K;
-      if (SIMPLE && simple_on && v[0] < 0.f) {
-        // a shortcut tie: (-X, lo_1, ..): evaluate it, and the closed form the sweep above counted for it
-        const float X = -v[0];
-        const int cj = col - jt;
-        const bool single = xt != 0.f;
-        float dat[K], iden[K], z2 = 0.f;  // dat_k: data term of the log2-odds against k = 0
 #pragma unroll
-        for (int k = 0; k < K; ++k) iden[k] = 0.f;
-        if (!single) {
-#pragma unroll
-          for (int k = 1; k < K; ++k) dat[k] = X * gk[k];
-        } else {
-          // Poisson split of the tie's one report between the theta lambda_k signal and the reciprocity term
-          // (model.py:686-696): f_k = z1_k/(z1_k+z2); data term x[(f_k-f_0) E[log theta] + f_k E[log lambda_k] - f_0 E[log lambda_0]]
-          const bool rowrep = xt > 0.f;
-          const float g = rowrep ? S.rg[r] : S.qg[cj];
-          const float el = rowrep ? S.rel[r] : S.qel[cj];
-          z2 = S.lam[3 * K] * fabsf(xt);
-          float f[K];
-#pragma unroll
-          for (int k = 0; k < K; ++k) {
-            const float z1 = g * S.lam[k];
-            iden[k] = __frcp_rn(z1 + z2);
-            f[k] = z1 * iden[k];
-          }
-          const float t0 = z2 * g * iden[0];
-#pragma unroll
-          for (int k = 1; k < K; ++k)
-            dat[k] = X * ((t0 * iden[k] * S.lam[K + k]) * el + (f[k] * S.lam[2 * K + k] - f[0] * S.lam[2 * K]));
-        }
-        float es[K], ef[K], s = 0.f, sf = 0.f;
-#pragma unroll
-        for (int k = 1; k < K; ++k) {
-          const float qk = S.qs[k - 1][cj];
-          es[k] = vm_ex2(fminf(S.ps2[k - 1][r] + qk + v[k] + dat[k], VM_CLAMP_LOG2));
-          s += es[k];
-          ef[k] = vm_ex2(fminf(__fadd_rn(p[k], qk), VM_CLAMP_LOG2));  // same operations as the sweep: same bits
-          sf = (k == 1) ? ef[k] : __fadd_rn(sf, ef[k]);
-        }
-        const float inv = __frcp_rn(1.f + s), invf = vm_rcp(__fadd_rn(1.f, sf));
-        d[0] = inv;
-        float nu_t = inv * iden[0];
-        if (!single) p0acc[0] += inv * X;
-        const bool act_j = S.qact[cj] != 0, act_i = S.ract[r] != 0;
-#pragma unroll
-        for (int k = 1; k < K; ++k) {
-          const float rk = es[k] * inv, fk = __fmul_rn(ef[k], invf);
-          d[k] = rk;
-          if (!single) p0acc[k] += rk * X;
-          nu_t += rk * iden[k];
-          const long long q = __double2ll_rn(((double)rk - (double)fk) * VM_FIX_SCALE);
-          if (act_j && q != 0) atomicAdd(fix_l + (int64_t)col * K + k, (unsigned long long)q);
-          if (act_i) rq[k] += q;
-        }
-        if (single) {
-          // sum_k dz2_k rho_k = x z2 sum_k rho_k/(z1_k+z2)  (model.py:822-825), and the posterior the gamma/phi passes gather
-          nuacc += X * z2 * nu_t;
-          float* ru = c.rho_u32 + (int64_t)(ua + e) * K;
-          ru[0] = inv;
-#pragma unroll
-          for (int k = 1; k < K; ++k) ru[k] = es[k] * inv;
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < K; ++k) d[k] = v[k];
-      }
+      for (int k = 0; k < K; ++k) d[k] = v[k];
     }
-    if (SIMPLE && simple_on) {
-#pragma unroll
-      for (int k = 1; k < K; ++k) {
-        long long t = rq[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0 && t != 0)
-          atomicAdd(fix_l + (int64_t)((int)c.row0 + i_lo + r) * K + k, (unsigned long long)t);
+    if (SIMPLE && simple_on) {  // the row reporter's correction: one global atomic per row segment and category
+      __syncwarp();
+      if (lane < K - 1) {
+        const unsigned long long t = S.rowfix[warp][qrow][lane];
+        if (t != 0ull) atomicAdd(fix_l + (int64_t)((int)c.row0 + i_lo + r) * K + 1 + lane, t);
       }
     }
     off += take;
@@ -1909,10 +1963,14 @@ static cudaError_t fast_setup() {
 }
 template <int K>
 static cudaError_t fast_setup_all() {
-  cudaError_t e;
-  if ((e = fast_setup<(K <= 4 ? K : 2), true, false>()) != cudaSuccess) return e;
-  if ((e = fast_setup<(K <= 4 ? K : 2), false, true>()) != cudaSuccess) return e;
-  return fast_setup<(K <= 4 ? K : 2), false, false>();
+  if constexpr (K <= 4) {  // the fast kernel is only instantiated (and eligible) for K <= 4
+    cudaError_t e;
+    if ((e = fast_setup<K, true, false>()) != cudaSuccess) return e;
+    if ((e = fast_setup<K, false, true>()) != cudaSuccess) return e;
+    return fast_setup<K, false, false>();
+  } else {
+    return cudaSuccess;
+  }
 }
 
 template <int K>
@@ -1923,7 +1981,6 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, in
   double* cp = region_cat(c);
   const bool fast = dense_fast_eligible<K>(c, flags);
   const bool simple = simple_iteration<K>(c, flags);
-  constexpr int KF = (K <= 4 ? K : 2);
   if (fast) {
     const cudaError_t e = fast_setup_all<K>();
     if (e != cudaSuccess) return (int)e;
@@ -1954,9 +2011,11 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, in
   }
 #define LF()                                                                                                             \
   do {                                                                                                                   \
-    if (elbo) k_dense_fast<KF, true><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<KF, false>), st>>>(*c, cp, rt0, rtn);       \
-    else if (simple) k_dense_fast<KF, false, true><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<KF, true>), st>>>(*c, cp, rt0, rtn); \
-    else k_dense_fast<KF, false><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<KF, false>), st>>>(*c, cp, rt0, rtn);           \
+    if constexpr (K <= 4) {                                                                                              \
+      if (elbo) k_dense_fast<K, true><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<K, false>), st>>>(*c, cp, rt0, rtn);       \
+      else if (simple) k_dense_fast<K, false, true><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<K, true>), st>>>(*c, cp, rt0, rtn); \
+      else k_dense_fast<K, false><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<K, false>), st>>>(*c, cp, rt0, rtn);           \
+    }                                                                                                                    \
   } while (0)
   if (fast && !side) LF();
   int rc = 0;
@@ -1990,8 +2049,10 @@ static int launch_special(const vm_ctx* c, int flags, cudaStream_t st, int chunk
   const bool elbo = flags & VM_F_ELBO;
 #define LS(E, M) k_special<K, E, M><<<grid, 256, 0, st>>>(*c, region_u(c), chunk)
   if (chunk < 0 && simple_iteration<K>(c, flags)) {
-    k_special<K, false, VM_R_EGO, 1><<<grid, 256, 0, st>>>(*c, region_u(c), chunk);  // layers that take the shortcut
-    k_special<K, false, VM_R_EGO, 2><<<grid, 256, 0, st>>>(*c, region_u(c), chunk);  // layers that cannot
+    if constexpr (K <= 4) {  // (simple_iteration is never true for larger K)
+      k_special<K, false, VM_R_EGO, 1><<<grid, 256, 0, st>>>(*c, region_u(c), chunk);  // layers that take the shortcut
+      k_special<K, false, VM_R_EGO, 2><<<grid, 256, 0, st>>>(*c, region_u(c), chunk);  // layers that cannot
+    }
   } else if (c->r_mode == VM_R_EGO) {
     if (elbo) LS(true, VM_R_EGO); else LS(false, VM_R_EGO);
   } else if (c->r_mode == VM_R_ALL) {

@@ -211,6 +211,64 @@ class SparseSyntheticNetwork:
         return self
 
 
+    # ------------------------------------------------------------------ X on the device
+    def build_X_device(self, mutuality=0.5, sh_theta=2.0, sc_theta=0.5, seed=None, theta=None, device="cuda", row0=0,
+                       nloc=None, emit_transposed=False):
+        """Device-side `build_X` (the `vm_synth_ego` kernels of include/vimure_b200.h): the same law, sampled with a
+        counter-based RNG keyed by (seed, layer, reporter, partner), for the node-row block [row0, row0+nloc) only.
+
+        Returns (subs, vals): int32 tensors (4, n) and (n,) ON THE DEVICE -- the entries X[l,i,j,m] with i in the block and,
+        with `emit_transposed`, the reciprocal entries X[l,j,i,m] whose row the block does not own (so that the shard can
+        be paired without an exchange).  Every rank that evaluates an entry gets the same value, whatever its block.
+        Also sets self.theta, self.R, self.mutuality (not self.X: use `sptensor(tuple(subs.cpu()), vals.cpu(), ...)`)."""
+        import ctypes
+
+        import torch
+
+        from . import _capi
+
+        N, M, L = self.N, self.M, self.L
+        nloc = N - row0 if nloc is None else int(nloc)
+        sd = self.seed if seed is None else seed
+        eta = float(mutuality)
+        if eta < 0 or eta >= 1:
+            raise ValueError("The mutuality parameter has to be in [0, 1)!")
+        if theta is None:
+            theta = np.random.RandomState(sd).gamma(shape=sh_theta, scale=sc_theta, size=(L, M))
+        self.theta = theta
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("build_X_device needs a CUDA device (host counterpart: build_X)")
+        lib = _capi.load()
+        ykey = (self.Y_subs[0] * N + self.Y_subs[1]) * N + self.Y_subs[2]
+        o = np.argsort(ykey, kind="stable")
+        yk = torch.from_numpy(np.ascontiguousarray(ykey[o])).to(dev)
+        yv = torch.from_numpy(np.ascontiguousarray(self.Y_vals[o]).astype(np.int32)).to(dev)
+        th = torch.from_numpy(np.ascontiguousarray(theta, dtype=np.float64)).to(dev)
+        counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        S = _capi.synth_class()()
+        S.L, S.N, S.M, S.K, S.row0, S.nloc = L, N, M, self.K, int(row0), nloc
+        S.emit_transposed = int(bool(emit_transposed))
+        S.seed = int(sd) & (2**64 - 1)
+        S.eta = eta
+        S.theta, S.y_key, S.y_val, S.nY = th.data_ptr(), yk.data_ptr(), yv.data_ptr(), int(yk.numel())
+        S.counter = counter.data_ptr()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        # pass 1 counts (cap = 0: nothing is stored), pass 2 fills arrays of exactly that size
+        S.cap = 0
+        _capi.check(lib.vm_synth_ego(ctypes.byref(S), stream), "vm_synth_ego (count)")
+        n = int(counter.item())
+        out = torch.empty((5, max(n, 1)), dtype=torch.int32, device=dev)
+        S.cap = n
+        S.o_l, S.o_i, S.o_j, S.o_m, S.o_x = (out[d].data_ptr() for d in range(5))
+        _capi.check(lib.vm_synth_ego(ctypes.byref(S), stream), "vm_synth_ego (fill)")
+        if int(counter.item()) != n:
+            raise RuntimeError("vm_synth_ego: the two passes disagree (%d vs %d entries)" % (int(counter.item()), n))
+        self.R = EgoMask(L, N, M, diag=True)
+        self.mutuality = eta
+        return out[:4, :n], out[4, :n]
+
+
 def StandardSBM(N=100, M=None, L=1, K=2, C=2, avg_degree=2.0, structure="assortative", seed=10):
     """Sparse counterpart of `vimure.synthetic.StandardSBM` (call `.build_X(...)` afterwards)."""
     return SparseSyntheticNetwork(N=N, M=M, L=L, K=K, C=C, avg_degree=avg_degree, eta=None, structure=structure, seed=seed)
