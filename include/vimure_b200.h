@@ -120,7 +120,7 @@ typedef struct vm_ctx {
   const int64_t* ucol_ptr;  /* [L*N+1] EGO: special ties grouped by (l, col) */
   const int32_t* ucol_perm; /* [U] */
 
-  /* ---- special ties the fast dense kernel evaluates itself ("shortcut" ties) ----
+  /* ---- shortcut ties: special ties whose posterior needs neither fp64 nor the entry list ----
      Ego mask, K <= 4, off the diagonal, in a full column tile, and either
        SIMPLE: none of the tie's X entries has a reciprocal report (x^T = 0, or mutuality off).  Its Poisson allocation is
                dz1_k = x whatever the parameters and the E[log theta] of its reporters is common to every k, so
@@ -132,15 +132,17 @@ typedef struct vm_ctx {
                z1_k = G_theta_m G_lambda_k, z2 = G_nu x^T  (model.py:686-696):
                   ln rho_k/rho_0 = ln2 lo_k - S (E[lambda_k]-E[lambda_0])
                                    + x [ (f_k-f_0) E[log theta_m] + f_k E[log lambda_k] - f_0 E[log lambda_0] ],
-               every term O(1..30); the reporter's (G_theta, E[log theta]) come from a row constant or from a per-tile
-               column table in shared memory -- no gather.  The kernel also emits the tie's part of the nu statistic
-               (x z2 sum_k rho_k/(z1_k+z2), model.py:822-825) and its fp32 posterior into rho_u32 for the gamma/phi passes.
-     On iterations that store the slab and do not evaluate the ELBO the fast dense kernel evaluates these ties (fp32 from
-     fp64-prepared tables) and the special-tie kernel only visits the others (`cx_idx`, `cx_*`); every other iteration
-     runs the special-tie kernel over all special ties in fp64, as does any layer for which k_phi_finish cannot rule out
-     a completely underflowed tie (layer constant VM_LC_SIMPLE). */
+               every term O(1..30).
+     On iterations that store the slab and do not evaluate the ELBO a light fp32 kernel (k_shortcut: one thread per tie,
+     coalesced per-tie constants + one 16-byte per-node table gather, no entry list, no fp64 transcendental) evaluates
+     these ties -- posterior into rho_u32, (posterior - closed form) into the fixed-point per-reporter corrections, the
+     SINGLE ties' part of the nu statistic (x z2 sum_k rho_k/(z1_k+z2), model.py:822-825) -- and the fp64 special-tie
+     kernel only visits the others (`cx_idx`, `cx_*`); every other iteration runs the special-tie kernel over all special
+     ties in fp64, as does any layer for which k_phi_finish cannot rule out a completely underflowed tie or an fp32 range
+     problem (layer constant VM_LC_SIMPLE). */
   int64_t simple_mode;      /* 1 = enabled (EGO mask, K <= 4, fast dense kernel eligible, serial special/dense launch) */
   int64_t n_cx;             /* special ties that take no shortcut */
+  int64_t n_cxblk;          /* blocks per layer of the special-tie kernel in list mode: ceil(max per-layer count / 1024) */
   const int32_t* cx_idx;    /* [n_cx] their indices, ascending */
   const int64_t* cx_ptr;    /* [L+1] range of cx_idx of every layer */
   /* compacted copies of the per-tie arrays for those ties (coalesced reads in the list mode of the special-tie kernel) */
@@ -152,11 +154,12 @@ typedef struct vm_ctx {
   const float* cx_xT0;
   const float* cx_x0sum;
   const double* cx_logpr;   /* [n_cx*K] */
-  float* u_patch;           /* [U*K] patch source of the fast dense kernel on such iterations: (-X, lo_1..lo_{K-1}) for a
-                               shortcut tie (constant over a fit; X = x for a SINGLE tie), the fp32 posterior (written by
-                               the special-tie kernel) else */
+  const float* u_px;        /* [U] X of a shortcut tie (sum of its x; the one report's x for a SINGLE tie), 0 = no shortcut */
   const float* u_pxt;       /* [U] 0 for a SIMPLE tie; SINGLE: +x^T if the entry's reporter is the row node, -x^T if it is
                                the column node */
+  const float* u_lo;        /* [U*(K-1)] lo_k = log2((pr_k+EPS)/(pr_0+EPS)), k >= 1 (constant over a fit) */
+  float* nodetab;           /* [L*N*stride] per node: q_1..q_{K-1} (= -E[theta] d_k), G_theta, E[log theta] log2e, active;
+                               stride = 4 floats at K = 2, 8 at K = 3, 4 (written by k_tables) */
   const double* simple_consts; /* [3] over the shortcut ties: min log(pr_0+EPS); max X; max x^T */
   int64_t* fixP;            /* [L*K] fixed point 2^-30: sum over the simple ties of rho_k X (their part of phi0) */
 
@@ -220,8 +223,7 @@ typedef struct vm_ctx {
   double* A;                /* [L*M*K] sum of rho_k over the ties reported by (l,m) */
   double* rho_u;            /* [U*K] posterior of the special ties, fp64 (as of the last update by the special-tie kernel) */
   float* rho_u32;           /* [U*K] fp32 posterior of the special ties: patch source of the dense slab and what the gamma /
-                               phi passes gather (written by the special-tie kernel, and by the fast dense kernel for the
-                               SINGLE ties it evaluates) */
+                               phi passes gather (written by the special-tie kernel and by the shortcut-tie kernel) */
   double* delta_u;          /* [U*K] rho_u - formula value */
   float* rho;               /* [L*nloc*N*K] dense posterior slab */
 
@@ -235,7 +237,7 @@ typedef struct vm_ctx {
   double* er_node;          /* [L*N] EGO: E[theta] of node n acting as reporter (0 if not an active reporter) */
   double* colsum;           /* [L*M*K] column partials reduced over the row tiles */
   int64_t* dev_flags;       /* [8] [0]: a special tie underflowed completely in the last rho update;
-                               [VM_FLAG_FIXNU]: fixed point 2^-30, nu statistic of the SINGLE ties the dense kernel evaluated */
+                               [VM_FLAG_FIXNU]: fixed point 2^-30, nu statistic of the SINGLE ties the shortcut kernel evaluated */
   int64_t* fixG;            /* [L*M] fixed-point correction of g0: -x of the E0 entries of special ties that underflowed */
   double* phi0;             /* [L*K] sum over special ties of rho_k * u_x0sum (E0 part of the next phi-shape sums) */
   int64_t* fixA;            /* [L*M*K] EGO: per-reporter sums of (special - closed form), fixed point 2^-44, accumulated
@@ -278,9 +280,8 @@ int vm_phase_phi(const vm_ctx* c, void* stream);
 int vm_phase_rho(const vm_ctx* c, int flags, void* stream);
 
 /* Measurement hook: launches ONLY the per-tie dense kernel of phase 3 (tables and special ties as left by the last
- * vm_phase_rho), so that its duration can be timed in isolation for the roofline figure. The statistics are unchanged;
- * with simple_mode the slab is patched from u_patch, which after an ELBO iteration still holds the posteriors of the
- * iteration before for the ties that are not simple: treat the slab as stale until the next vm_phase_rho. */
+ * vm_phase_rho), so that its duration can be timed in isolation for the roofline figure. The statistics are unchanged
+ * and the slab is rewritten with the same values. */
 int vm_dense_only(const vm_ctx* c, int flags, void* stream);
 
 /* Phase 4 -- consumes (all-reduced) red3: A <- red3, `_update_nu` (model.py:820-830), refreshes the nu cache,

@@ -33,7 +33,7 @@ def main():
     dev = torch.device("cuda", 0)
     net = bench.make_network(N, L, K, config=a.config)
     P = _packing.pack(net.X.subs, net.X.vals, L, N, net.M, K, net.R, dev, tile_h=128)
-    st, prng = bench.draw_state(net, K)
+    st, prng = bench.draw_state(L, net.M, K)
     keep = (P.t["u_has_x"] & P.t["u_reported"]).cpu().numpy()
     pr_u = np.zeros((P.U, K))
     pr_u[:, 0] = 1.0

@@ -77,7 +77,9 @@ class CaviEngine:
         self.phi0 = z(L * K)
         # simple special ties (see include/vimure_b200.h): patch source of the fast dense kernel, their phi0 part
         self.simple_mode = bool(getattr(P, "simple_ok", False)) and not overlap
-        self.u_patch = torch.zeros(max(U, 1), K, **f32)
+        self.u_lo = torch.zeros(max(U, 1), K - 1, **f32)
+        stride = 4 if K == 2 else (8 if K <= 6 else K + 2)
+        self.nodetab = torch.zeros(L * N * stride if self.simple_mode else 4, **f32)
         self.fixP = torch.zeros(L * K, dtype=torch.int64, device=dev)
         self.simple_consts = z(3)
         self.gfpart = z(L * ((M + 255) // 256) * (K + 4))
@@ -107,6 +109,7 @@ class CaviEngine:
         c.b_all = float(P.b_all)
         c.simple_mode = int(self.simple_mode)
         c.n_cx = int(getattr(P, "n_cx", U))
+        c.n_cxblk = int(getattr(P, "n_cxblk", P.n_ublk))
         # special/dense overlap: worthwhile once the special-tie kernel is long enough to matter
         self.aux_stream = None
         if overlap is None:
@@ -135,13 +138,13 @@ class CaviEngine:
         for name in ("u_lrow", "u_col", "u_ptr", "u_cnt", "u_m0", "u_x0", "u_xT0", "utile_ptr", "ucol_ptr", "ucol_perm", "e_u", "e_m", "e_x", "e_xT",
                      "e_flags", "f_u", "f_m", "f_x", "f_xT", "lay_eptr", "g0", "u_x0sum", "sp_chunk_blk", "g_chunk_ptr", "g_chunk_lm", "g_u", "g_x", "g_xT", "g_lm_cptr", "t_u", "t_lrow",
                      "t_col", "t_x", "rep", "r_ptr", "r_m", "r_val", "c_ptr", "c_tie", "cx_idx", "cx_ptr", "cx_lrow", "cx_col", "cx_cnt",
-                     "cx_m0", "cx_x0", "cx_xT0", "cx_x0sum", "u_pxt"):
+                     "cx_m0", "cx_x0", "cx_xT0", "cx_x0sum", "u_px", "u_pxt"):
             setattr(c, name, ptr(P.t[name]) if name in P.t else self._dummy.data_ptr())
         for name in ("u_logpr", "alpha_theta", "beta_theta", "alpha_lambda", "beta_lambda", "gamma_shp", "gamma_rte",
                      "phi_shp", "phi_rte", "nu", "G_theta", "E_theta", "Elog_theta", "G_lambda", "E_lambda",
                      "Elog_lambda", "GE_theta", "rho_u", "rho_u32", "delta_u", "rho", "layer_consts", "tab_p", "tab_q",
                      "rowpart", "colpart", "er_node", "colsum", "dev_flags", "fixA", "fixG", "phi0", "blkpart", "red1", "red2", "red3",
-                     "elbo_out", "u_patch", "fixP", "simple_consts", "cx_logpr", "gfpart"):
+                     "elbo_out", "u_lo", "nodetab", "fixP", "simple_consts", "cx_logpr", "gfpart"):
             setattr(c, name, ptr(getattr(self, name)))
         c.A = self.red3.data_ptr()  # A aliases the (all-reduced) statistics vector
         c.ev_fork, c.ev_join = self._ev_fork.cuda_event, self._ev_join.cuda_event
@@ -172,7 +175,7 @@ class CaviEngine:
         if elbo:
             n += 1 + (1 if self.mutuality else 0)
         elif self.simple_mode and fast and not self.ctx.n_chunks:
-            n += 1  # the special-tie kernel is launched twice (layers that take the simple-tie shortcut / that cannot)
+            n += 2  # the special-tie kernel is launched twice (layers that take the shortcut / that cannot) + k_shortcut
         return n
 
     # ------------------------------------------------------------------ state
@@ -194,20 +197,15 @@ class CaviEngine:
             torch.add(pr, float(eps), out=self.u_logpr)  # log(pr_rho + EPS), model.py:559, without temporaries
             self.u_logpr.log_()
             if self.simple_mode:
-                # patch entries of the shortcut ties: (-X, lo_1..lo_{K-1}), lo_k = log2((pr_k+EPS)/(pr_0+EPS)); the others
-                # are rewritten by the special-tie kernel before the dense kernel reads them
+                # constants of the shortcut ties: lo_k = log2((pr_k+EPS)/(pr_0+EPS)); prior of the others compacted
                 sm = P.t["u_simple"] | P.t["u_single"]
                 lp = self.u_logpr
                 if P.n_cx:
                     torch.index_select(lp, 0, P.t["cx_idx"].to(torch.int64), out=self.cx_logpr)
-                px = P.t["u_px"]
-                self.u_patch.zero_()
-                self.u_patch[:, 0] = torch.where(sm, -px, torch.zeros_like(px))
-                lo = ((lp[:, 1:] - lp[:, :1]) * 1.4426950408889634).to(torch.float32)
-                self.u_patch[:, 1:] = torch.where(sm[:, None], lo, torch.zeros_like(lo))
+                self.u_lo.copy_(((lp[:, 1:] - lp[:, :1]) * 1.4426950408889634).to(torch.float32))
                 big = torch.full_like(lp[:, 0], 1e300)
                 self.simple_consts[0] = torch.where(sm, lp[:, 0], big).min().clamp(max=0.0)
-                self.simple_consts[1] = px.max().to(torch.float64)
+                self.simple_consts[1] = P.t["u_px"].max().to(torch.float64)
                 self.simple_consts[2] = P.t["u_pxt"].abs().max().to(torch.float64)
         st = self._stream()
         _capi.check(self.lib.vm_refresh_cache(self._cref, st), "vm_refresh_cache")
@@ -227,30 +225,39 @@ class CaviEngine:
         base = 0 if store else F["VM_F_NO_STORE"]
         last = (0 if (store or store_last) else F["VM_F_NO_STORE"]) | (F["VM_F_ELBO"] if elbo_last else 0)
         st = self._stream()
-        if self.group is None and self._graphs is not None:
+        if self._graphs is not None:
             for it in range(n):
                 self._graph(last if it == n - 1 else base).replay()
         elif self.group is None:
             _capi.check(self.lib.vm_run(self._cref, int(n), base, last, st), "vm_run")
         else:
             for it in range(n):
-                fl = last if it == n - 1 else base
-                _capi.check(self.lib.vm_phase_gamma(self._cref, st), "vm_phase_gamma")
-                self._allreduce(self.red1)
-                _capi.check(self.lib.vm_phase_phi(self._cref, st), "vm_phase_phi")
-                self._allreduce(self.red2)
-                _capi.check(self.lib.vm_phase_rho(self._cref, fl, st), "vm_phase_rho")
-                self._allreduce(self.red3)
-                _capi.check(self.lib.vm_phase_finish(self._cref, fl, st), "vm_phase_finish")
+                self._sharded_iteration(last if it == n - 1 else base)
         self.n_launch += (n - 1) * self.kernels_per_iteration(False, store) + \
             self.kernels_per_iteration(elbo_last, store or store_last)
         self.rho_valid = bool(store or store_last)
         self.rho_is_prior = False
 
+    def _sharded_iteration(self, flags):
+        """One iteration of a row-block shard: the four phases with the three statistics all-reduces between them."""
+        st = self._stream()
+        _capi.check(self.lib.vm_phase_gamma(self._cref, st), "vm_phase_gamma")
+        self._allreduce(self.red1)
+        _capi.check(self.lib.vm_phase_phi(self._cref, st), "vm_phase_phi")
+        self._allreduce(self.red2)
+        _capi.check(self.lib.vm_phase_rho(self._cref, int(flags), st), "vm_phase_rho")
+        self._allreduce(self.red3)
+        _capi.check(self.lib.vm_phase_finish(self._cref, int(flags), st), "vm_phase_finish")
+
     def enable_graphs(self):
-        """Replay one captured CUDA graph per iteration instead of ~17 launches (for launch-bound small problems;
-        single rank only -- the NCCL all-reduces of the sharded path sit between the phases)."""
-        if self.group is None and self._graphs is None:
+        """Replay one captured CUDA graph per iteration instead of ~17 launches.  On a sharded fit the graph holds the
+        whole iteration INCLUDING the three NCCL all-reduces (every rank captures the same sequence), so that nothing
+        waits for the host between the phases; VM_DIST_GRAPHS=0 keeps the sharded path on eager launches."""
+        import os
+
+        if self.group is not None and os.environ.get("VM_DIST_GRAPHS", "1") == "0":
+            return False
+        if self._graphs is None:
             self._graphs = {}
         return self._graphs is not None
 
@@ -277,8 +284,12 @@ class CaviEngine:
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 g.capture_begin(capture_error_mode="thread_local")
+                rc = 0
                 try:
-                    rc = self.lib.vm_iteration(self._cref, int(flags), self._stream())
+                    if self.group is None:
+                        rc = self.lib.vm_iteration(self._cref, int(flags), self._stream())
+                    else:
+                        self._sharded_iteration(flags)
                 finally:
                     g.capture_end()
                 _capi.check(rc, "vm_iteration (capture)")
@@ -302,9 +313,6 @@ class CaviEngine:
         """Launch only the per-tie dense kernel (measurement hook, see vm_dense_only)."""
         _capi.check(self.lib.vm_dense_only(self._cref, int(flags), self._stream()), "vm_dense_only")
         self.n_launch += 1
-        if self.simple_mode:
-            # after an ELBO iteration u_patch still holds the posteriors of the iteration before: timing only
-            self.rho_valid = False
 
     def elbo(self):
         return float(self.elbo_out[0].item())

@@ -308,6 +308,8 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
     P.n_cx = int(cx.numel())
     P.t["cx_idx"] = _i32(cx)
     P.t["cx_ptr"] = torch.searchsorted(u_l[cx].contiguous(), torch.arange(L + 1, device=dev, dtype=torch.int64)).contiguous()
+    n_cxl = int((P.t["cx_ptr"][1:] - P.t["cx_ptr"][:-1]).max()) if L else 0
+    P.n_cxblk = max(1, (n_cxl + SPECIAL_TIES_PER_BLOCK - 1) // SPECIAL_TIES_PER_BLOCK)
     if P.simple_ok:  # compacted copies of the per-tie arrays: the list mode of the special-tie kernel reads them coalesced
         for name in ("lrow", "col", "cnt", "m0", "x0", "xT0", "x0sum"):
             P.t["cx_" + name] = P.t["u_" + name][cx].contiguous()

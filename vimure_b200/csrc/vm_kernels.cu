@@ -381,6 +381,12 @@ __device__ __forceinline__ double vm_Er(const vm_ctx& c, int l, int n) {
   return (n < (int)c.M && c.rep[(int64_t)l * c.M + n]) ? c.E_theta[(int64_t)l * c.M + n] : 0.0;
 }
 
+// per-node table of the shortcut-tie kernel (k_shortcut): q_1..q_{K-1}, G_theta, E[log theta] log2e, active flag
+template <int K>
+struct NodeTab {
+  static constexpr int STRIDE = (K == 2) ? 4 : (K <= 6 ? 8 : K + 2);
+};
+
 // Row/column tables of the separable log2-odds: a_k(l,i,j) = tab_p[lrow,k] + tab_q[l,j,k] since for the ego mask
 // S = E[theta_i]+E[theta_j], and for the all-reporter mask S is a per-layer constant.
 template <int K>
@@ -394,6 +400,16 @@ __global__ void k_tables(const __grid_constant__ vm_ctx c) {
     c.er_node[t] = er;
 #pragma unroll
     for (int k = 0; k < K; ++k) c.tab_q[t * K + k] = (float)(-er * lc[VM_LC_D(K, k)]);
+    if (c.simple_mode) {  // per-node table of the shortcut-tie kernel
+      float* nt = c.nodetab + t * NodeTab<K>::STRIDE;
+#pragma unroll
+      for (int k = 1; k < K; ++k) nt[k - 1] = (float)(-er * lc[VM_LC_D(K, k)]);
+      double2 ge = make_double2(0.0, 0.0);
+      if (n < (int)c.M) ge = *reinterpret_cast<const double2*>(c.GE_theta + 2 * ((int64_t)l * c.M + n));
+      nt[K - 1] = (float)ge.x;
+      nt[K] = (float)(ge.y * VM_LOG2E);
+      nt[K + 1] = er > 0.0 ? 1.f : 0.f;
+    }
   }
   if (t < np) {
     const int l = (int)(t / c.nloc), i = (int)(t - (int64_t)l * c.nloc) + (int)c.row0;
@@ -513,12 +529,12 @@ __device__ __forceinline__ void vm_fix_accumulate(unsigned long long* fix_l, boo
 #ifndef VM_SPECIAL_MINBLK
 #define VM_SPECIAL_MINBLK 3
 #endif
-// LIST (ego mask, no ELBO), for the iterations on which the fast dense kernel evaluates the simple special ties of the
-// layers flagged VM_LC_SIMPLE.  LIST = 1 handles those layers: it walks the special ties that are NOT simple through
-// their compacted copies of the per-tie arrays (`cx_*`: coalesced; walking the original arrays at half density tripled
-// the DRAM bytes read per tie, profiles/ncu_r1_simple_dense_fast_special.txt) and also writes the fp32 posterior into
-// `u_patch`, the dense kernel's patch source on such iterations.  LIST = 2 handles the other layers exactly like LIST = 0.
-// Each block of a (layer, block) grid does its work in exactly one of the two launches and returns in the other.
+// LIST (ego mask, no ELBO), for the iterations on which k_shortcut evaluates the shortcut ties of the layers flagged
+// VM_LC_SIMPLE.  LIST = 1 handles those layers: it walks the special ties that take NO shortcut through their compacted
+// copies of the per-tie arrays (`cx_*`: coalesced; walking the original arrays at low density multiplied the DRAM bytes
+// read per tie, profiles/ncu_r1_simple_dense_fast_special.txt); its grid covers that list only (n_cxblk blocks per
+// layer).  LIST = 2 handles the other layers exactly like LIST = 0.  Each block of a (layer, block) grid does its work
+// in exactly one of the two launches and returns in the other.
 template <int K, bool ELBO, int RMODE, int LIST = 0>
 __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) : 2)) k_special(const __grid_constant__ vm_ctx c, double* part, int chunk) {
   __shared__ double s_Gl[K], s_Ell[K], s_El[K];
@@ -775,7 +791,6 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
           o_dk[k] = rho[k] - fv;
           ru[k] = rho[k];
           ru32[k] = (float)rho[k];
-          if (LIST == 1) c.u_patch[(size_t)u * K + k] = (float)rho[k];
           dsum[k] += o_dk[k];
         }
         o_resid = (alive_u ? 1 : 0) - (dead ? 0 : 1);
@@ -1109,8 +1124,8 @@ struct FastCfg {
 #define VM_FAST_MINBLK2 4
 #endif
 
-// shared memory of k_dense_fast (dynamic: more than the 48 KB a static allocation may hold)
-template <int K, bool SIMPLE>
+// shared memory of k_dense_fast (dynamic: K >= 3 needs more than the 48 KB a static allocation may hold)
+template <int K>
 struct FastSmem {
   static constexpr int TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32, CAPW = FastCfg<K>::CAPW, TH = VM_FAST_MAX_TILE_H;
   float qs[K - 1][TW];      // column terms of the log2-odds
@@ -1121,77 +1136,14 @@ struct FastSmem {
   float ps[K - 1][TH];      // row terms
   int tp0[TH], tp1[TH];     // special-tie range of every row segment
   double sm_red[8];
-  // ---- shortcut ties (SIMPLE instantiation only)
-  float pxt[SIMPLE ? NW : 1][SIMPLE ? CAPW : 1];
-  float ps2[SIMPLE ? K - 1 : 1][SIMPLE ? TH : 1];    // row terms without their constant
-  float qg[SIMPLE ? TW : 1], qel[SIMPLE ? TW : 1];   // G_theta, E[log theta] log2e of the column nodes as reporters
-  float rg[SIMPLE ? TH : 1], rel[SIMPLE ? TH : 1];   // ... of the row nodes
-  float lam[SIMPLE ? 3 * K + 1 : 1];  // G_lambda_k | G_lambda_k - G_lambda_0 | E[log lambda_k] log2e | G_nu
-  unsigned long long rowfix[SIMPLE ? NW : 1][SIMPLE ? TH / NW : 1][K - 1];  // row reporters' corrections (fixed point)
-  int poff[SIMPLE ? NW : 1][SIMPLE ? TH / NW + 1 : 1];         // first staged entry of each of the warp's rows
-  unsigned char ract[SIMPLE ? TH : 1], qact[SIMPLE ? TW : 1];  // node is an active reporter
 };
 
-// One shortcut tie (vm_ctx.simple_mode): v = (-X, lo_1..lo_{K-1}), xt = 0 (SIMPLE) or +-x^T (SINGLE; sign = the row / the
-// column node reported).  Returns its posterior rho[0..K), the closed form the row sweep counted for it fcf[1..K) (same
-// operations as the sweep: same bits), and its part of the nu statistic.  One code path for both kinds (no divergence):
-// a SIMPLE tie is the z2 = 0 limit, f_k = 1.
-template <int K, typename SM>
-__device__ __forceinline__ void vm_eval_shortcut(const SM& S, const float* gk, int r, int cj,
-                                                 const float* v, float xt, float* rho, float* fcf, float& nu_c) {
-  const float X = -v[0];
-  const bool single = xt != 0.f, rowrep = xt > 0.f;
-  // Poisson split of a SINGLE tie's one report between the theta lambda_k signal and the reciprocity term
-  // (model.py:686-696): f_k = z1_k/(z1_k+z2); data term x[(f_k-f_0) E[log theta] + f_k E[log lambda_k] - f_0 E[log lambda_0]]
-  const float g = single ? (rowrep ? S.rg[r] : S.qg[cj]) : 1.f;
-  const float el = single ? (rowrep ? S.rel[r] : S.qel[cj]) : 0.f;
-  const float z2 = S.lam[3 * K] * fabsf(xt);
-  float f[K], iden[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const float z1 = g * S.lam[k];
-    iden[k] = vm_rcp(z1 + z2);
-    f[k] = single ? z1 * iden[k] : 1.f;
-  }
-  const float t0 = z2 * g * iden[0];
-  float s = 0.f, sf = 0.f, es[K], ef[K];
-#pragma unroll
-  for (int k = 1; k < K; ++k) {
-    const float dat = single ? X * ((t0 * iden[k] * S.lam[K + k]) * el + (f[k] * S.lam[2 * K + k] - f[0] * S.lam[2 * K]))
-                             : X * gk[k];
-    const float qk = S.qs[k - 1][cj];
-    es[k] = vm_ex2(fminf(S.ps2[k - 1][r] + qk + v[k] + dat, VM_CLAMP_LOG2));
-    s += es[k];
-    ef[k] = vm_ex2(fminf(__fadd_rn(S.ps[k - 1][r], qk), VM_CLAMP_LOG2));
-    sf = (k == 1) ? ef[k] : __fadd_rn(sf, ef[k]);
-  }
-  const float inv = vm_rcp(1.f + s), invf = vm_rcp(__fadd_rn(1.f, sf));
-  rho[0] = inv;
-  float nu_t = inv * iden[0];
-#pragma unroll
-  for (int k = 1; k < K; ++k) {
-    rho[k] = es[k] * inv;
-    fcf[k] = __fmul_rn(ef[k], invf);
-    nu_t += rho[k] * iden[k];
-  }
-  // sum_k dz2_k rho_k = x z2 sum_k rho_k/(z1_k+z2)  (model.py:822-825); 0 for a SIMPLE tie (z2 = 0)
-  nu_c = X * z2 * nu_t;
-}
-
-// SIMPLE (no ELBO): in the layers flagged VM_LC_SIMPLE the patch source is `u_patch`, whose entries of the shortcut ties
-// (vm_ctx.simple_mode) hold (-X, lo_1..lo_{K-1}) instead of a posterior, with `u_pxt` = 0 (SIMPLE tie) or +-x^T (SINGLE
-// tie, sign = which of the two nodes reported).  The warp evaluates those ties itself from the row term without its
-// constant (ps2), the staged column term, lo and the data term -- all O(1..30), so fp32 does not cancel -- and accounts
-// for them exactly as the special-tie kernel would: (posterior - closed form) into the fixed-point per-reporter
-// corrections (row reporter: one atomic per row segment after an integer warp reduction), rho_k X of the SIMPLE ties into
-// fixP, the nu statistic of the SINGLE ties into dev_flags[VM_FLAG_FIXNU], their fp32 posterior into rho_u32.
-template <int K, bool ELBO, bool SIMPLE = false>
+template <int K, bool ELBO>
 __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_MINBLK2 : 2) k_dense_fast(const __grid_constant__ vm_ctx c, double* catpart, int rt0, int rtn) {
-  static_assert(!(SIMPLE && ELBO), "the ELBO iterations evaluate every special tie in fp64");
   constexpr int NCH = DenseCfg<K>::NCH, TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32, CAPW = FastCfg<K>::CAPW;
   extern __shared__ __align__(16) unsigned char vm_fast_smem[];
-  FastSmem<K, SIMPLE>& S = *reinterpret_cast<FastSmem<K, SIMPLE>*>(vm_fast_smem);
-  const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt, M = (int)c.M;
+  FastSmem<K>& S = *reinterpret_cast<FastSmem<K>*>(vm_fast_smem);
+  const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
   const int ct = blockIdx.x;
   const int l = blockIdx.y / rtn, rt = rt0 + (blockIdx.y - l * rtn);  // row tiles [rt0, rt0+rtn) of every layer
   if (!vm_fast_tile<K>(c, l, ct)) return;
@@ -1202,29 +1154,13 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
   const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
   const float lp0 = (float)lc[VM_LC_LP0(K)], lpk = (float)lc[VM_LC_LPK(K)], epsf = (float)c.eps;
   double cat = 0.0;
-  const bool simple_on = SIMPLE && lc[VM_LC_SIMPLE(K)] != 0.0;
-  const float* patch_src = simple_on ? c.u_patch : c.rho_u32;
-  float gk[K], p0acc[K], nuacc = 0.f;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    gk[k] = simple_on ? (float)lc[VM_LC_G(K, k)] : 0.f;
-    p0acc[k] = 0.f;
-  }
-  unsigned long long* fix_l = reinterpret_cast<unsigned long long*>(c.fixA) + (int64_t)l * c.M * K;
+  const float* patch_src = c.rho_u32;
   // ---- phase 0: everything the row loop reads from global memory, once per CTA
   for (int idx = tid; idx < TW; idx += VM_DENSE_THREADS) {
 #pragma unroll
     for (int k = 1; k < K; ++k) {
       S.qs[k - 1][idx] = __ldg(&c.tab_q[((int64_t)l * N + jt + idx) * K + k]);
       S.colbuf[k - 1][idx] = 0.f;
-    }
-    if (simple_on) {
-      const int j = jt + idx;
-      S.qact[idx] = c.er_node[(int64_t)l * N + j] > 0.0 ? 1 : 0;  // column node is an active reporter
-      double2 ge = make_double2(0.0, 0.0);
-      if (j < M) ge = *reinterpret_cast<const double2*>(c.GE_theta + 2 * ((int64_t)l * M + j));
-      S.qg[idx] = (float)ge.x;
-      S.qel[idx] = (float)(ge.y * VM_LOG2E);
     }
   }
   for (int r = tid; r < nrows; r += VM_DENSE_THREADS) {
@@ -1233,48 +1169,21 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
     for (int k = 1; k < K; ++k) S.ps[k - 1][r] = __ldg(&c.tab_p[lrow * K + k]);
     S.tp0[r] = __ldg(&c.utile_ptr[lrow * nct + ct]);
     S.tp1[r] = __ldg(&c.utile_ptr[lrow * nct + ct + 1]);
-    if (simple_on) {
-      const int i = (int)c.row0 + i_lo + r;
-      const double er = c.er_node[(int64_t)l * N + i];
-      S.ract[r] = er > 0.0 ? 1 : 0;
-#pragma unroll
-      for (int k = 1; k < K; ++k) S.ps2[k - 1][r] = (float)(-er * lc[VM_LC_D(K, k)]);  // tab_p without its constant c_k
-      double2 ge = make_double2(0.0, 0.0);
-      if (i < M) ge = *reinterpret_cast<const double2*>(c.GE_theta + 2 * ((int64_t)l * M + i));
-      S.rg[r] = (float)ge.x;
-      S.rel[r] = (float)(ge.y * VM_LOG2E);
-    }
-  }
-  if (SIMPLE) {
-    for (int t = tid; t < NW * (VM_FAST_MAX_TILE_H / NW) * (K - 1); t += VM_DENSE_THREADS) (&S.rowfix[0][0][0])[t] = 0ull;
-  }
-  if (simple_on && tid < K) {
-    const double g0 = c.G_lambda[l * K], gkk = c.G_lambda[l * K + tid];
-    S.lam[tid] = (float)gkk;
-    S.lam[K + tid] = (float)(gkk - g0);
-    S.lam[2 * K + tid] = (float)(c.Elog_lambda[l * K + tid] * VM_LOG2E);
-    if (tid == 0) S.lam[3 * K] = (float)c.nu[VM_NU_G];
   }
   __syncthreads();
   // ---- phase 1: stage the patch data of this warp's rows asynchronously
-  int n_staged = 0, n_myrows = 0;
   {
-    int off = 0, q = 0;
-    for (int r = warp; r < nrows; r += NW, ++q) {
+    int off = 0;
+    for (int r = warp; r < nrows; r += NW) {
       const int ua = S.tp0[r], n = S.tp1[r] - ua;
       const int take = min(n, CAPW - off);
-      if (SIMPLE && lane == 0) S.poff[warp][q] = off;
       for (int e = lane; e < take; e += 32) {
         vm_cp_async4(&S.pcol[warp][off + e], &c.u_col[ua + e]);
 #pragma unroll
         for (int k = 0; k < K; ++k) vm_cp_async4(&S.pval[warp][off + e][k], &patch_src[(int64_t)(ua + e) * K + k]);
-        if (simple_on) vm_cp_async4(&S.pxt[warp][off + e], &c.u_pxt[ua + e]);
       }
       off += take;
     }
-    if (SIMPLE && lane == 0) S.poff[warp][q] = off;
-    n_staged = off;
-    n_myrows = q;
     vm_cp_async_commit();
   }
   // ---- phase 2: the rows (no global loads on the critical path)
@@ -1353,52 +1262,10 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
     if (!waited) {
       vm_cp_async_wait_all();
       waited = true;
-      __syncwarp();
-      if (SIMPLE && simple_on) {
-        // Evaluate the shortcut ties of ALL the warp's rows now, 32 at a time with every lane busy (a row segment alone
-        // holds ~19 special ties of mixed kinds); the posterior replaces the tie's patch entry in shared memory, so the
-        // per-row loop below only copies.  Statistics as the special-tie kernel would account for them.
-        for (int e = lane; e < n_staged; e += 32) {
-          float v[K];
-#pragma unroll
-          for (int k = 0; k < K; ++k) v[k] = S.pval[warp][e][k];
-          if (v[0] < 0.f) {
-            int q = 0;
-#pragma unroll 4
-            for (int t = 1; t < n_myrows; ++t) q += (S.poff[warp][t] <= e) ? 1 : 0;
-            const int rr = warp + NW * q;
-            const int col = S.pcol[warp][e], cj = col - jt;
-            const float xt = S.pxt[warp][e];
-            float rk[K], fk[K], nu_c;
-            vm_eval_shortcut<K>(S, gk, rr, cj, v, xt, rk, fk, nu_c);
-            const bool act_j = S.qact[cj] != 0, act_i = S.ract[rr] != 0;
-#pragma unroll
-            for (int k = 0; k < K; ++k) S.pval[warp][e][k] = rk[k];
-#pragma unroll
-            for (int k = 1; k < K; ++k) {
-              const long long fq = __double2ll_rn(((double)rk[k] - (double)fk[k]) * VM_FIX_SCALE);
-              if (act_j && fq != 0) atomicAdd(fix_l + (int64_t)col * K + k, (unsigned long long)fq);
-              if (act_i && fq != 0) atomicAdd(&S.rowfix[warp][q][k - 1], (unsigned long long)fq);
-            }
-            if (xt != 0.f) {  // SINGLE: nu statistic, and the posterior the gamma / phi passes gather
-              nuacc += nu_c;
-              float* ru = c.rho_u32 + (int64_t)(S.tp0[rr] + (e - S.poff[warp][q])) * K;
-#pragma unroll
-              for (int k = 0; k < K; ++k) ru[k] = rk[k];
-            } else {  // SIMPLE: rho_k X, its part of the next phi-shape sums
-              const float X = -v[0];
-#pragma unroll
-              for (int k = 0; k < K; ++k) p0acc[k] += rk[k] * X;
-            }
-          }
-        }
-        __syncwarp();
-      }
     }
     __syncwarp();
     const int ua = S.tp0[r], n = S.tp1[r] - ua;
     const int take = min(n, CAPW - off);
-    const int qrow = (r - warp) / NW;
     for (int e = lane; e < n; e += 32) {
       int col;
       float v[K];
@@ -1406,46 +1273,14 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
         col = S.pcol[warp][off + e];
 #pragma unroll
         for (int k = 0; k < K; ++k) v[k] = S.pval[warp][off + e][k];
-      } else {  // more special ties than the per-warp stage holds: fetched (and, if a shortcut tie, evaluated) here
+      } else {  // more special ties than the per-warp stage holds
         col = c.u_col[ua + e];
 #pragma unroll
         for (int k = 0; k < K; ++k) v[k] = patch_src[(int64_t)(ua + e) * K + k];
-        if (SIMPLE && simple_on && v[0] < 0.f) {
-          const int cj = col - jt;
-          const float xt = c.u_pxt[ua + e];
-          float rk[K], fk[K], nu_c;
-          vm_eval_shortcut<K>(S, gk, r, cj, v, xt, rk, fk, nu_c);
-          const bool act_j = S.qact[cj] != 0, act_i = S.ract[r] != 0;
-#pragma unroll
-          for (int k = 1; k < K; ++k) {
-            const long long fq = __double2ll_rn(((double)rk[k] - (double)fk[k]) * VM_FIX_SCALE);
-            if (act_j && fq != 0) atomicAdd(fix_l + (int64_t)col * K + k, (unsigned long long)fq);
-            if (act_i && fq != 0) atomicAdd(&S.rowfix[warp][qrow][k - 1], (unsigned long long)fq);
-          }
-          if (xt != 0.f) {
-            nuacc += nu_c;
-            float* ru = c.rho_u32 + (int64_t)(ua + e) * K;
-#pragma unroll
-            for (int k = 0; k < K; ++k) ru[k] = rk[k];
-          } else {
-            const float X = -v[0];
-#pragma unroll
-            for (int k = 0; k < K; ++k) p0acc[k] += rk[k] * X;
-          }
-#pragma unroll
-          for (int k = 0; k < K; ++k) v[k] = rk[k];
-        }
       }
       float* d = rowdst + (int64_t)col * K;
 #pragma unroll
       for (int k = 0; k < K; ++k) d[k] = v[k];
-    }
-    if (SIMPLE && simple_on) {  // the row reporter's correction: one global atomic per row segment and category
-      __syncwarp();
-      if (lane < K - 1) {
-        const unsigned long long t = S.rowfix[warp][qrow][lane];
-        if (t != 0ull) atomicAdd(fix_l + (int64_t)((int)c.row0 + i_lo + r) * K + 1 + lane, t);
-      }
     }
     off += take;
   }
@@ -1480,19 +1315,179 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
     const double v = block_sum<VM_DENSE_THREADS>(cat, S.sm_red);
     if (tid == 0) catpart[((int64_t)l * nrt + rt) * nct + ct] = v;
   }
-  if (SIMPLE && simple_on) {
-    // rho_k X of the SIMPLE ties of this tile: their part of the next phi-shape sums (phi0); nu statistic of the SINGLE ties
+}
+
+// ---- shortcut ties: the special ties whose posterior needs no fp64 and no entry list ---------------------------------
+// (vm_ctx.simple_mode.)  One thread per special tie u of the rank, in tie order (row-major): a tie with u_px[u] = 0 is
+// not a shortcut tie and is skipped (the special-tie kernel's list mode has it).  A shortcut tie's constants are
+// X = u_px (total count of a SIMPLE tie / the count of a SINGLE tie's one report), xt = u_pxt (0 = SIMPLE; +-x^T = SINGLE,
+// sign: reported by the row / the column node) and lo_k = u_lo = log2((pr_k+EPS)/(pr_0+EPS)).  With the per-node table
+// nodetab[l,n] = (q_1..q_{K-1}, G_theta, E[log theta] log2e, active) written by k_tables, q_k = -E[theta_n] d_k:
+//   log2 rho_k/rho_0 = q_k(i) + q_k(j) + lo_k + dat_k,
+//   SIMPLE: dat_k = X (E[log lambda_k]-E[log lambda_0]) log2e
+//   SINGLE: f_k = z1_k/(z1_k+z2), z1_k = G_theta_m G_lambda_k, z2 = G_nu x^T (model.py:686-696),
+//           dat_k = x log2e [ (f_k-f_0) E[log theta_m] + f_k E[log lambda_k] - f_0 E[log lambda_0] ]
+// every term O(1..30): fp32 does not cancel (the closed form's own p+q ~ -40 would).  The tie is accounted for exactly as
+// the special-tie kernel would: fp32 posterior into rho_u32 (patch source of the dense kernel, gathered by the gamma/phi
+// passes), (posterior - closed form) into the fixed-point per-reporter corrections -- the closed form recomputed with
+// the dense sweep's operations, same bits --, rho_k X of the SIMPLE ties into fixP (their part of the next phi-shape
+// sums), sum_k dz2_k rho_k = x z2 sum_k rho_k/(z1_k+z2) of the SINGLE ties (model.py:822-825) into dev_flags[VM_FLAG_FIXNU].
+template <int K>
+__global__ void __launch_bounds__(256) k_shortcut(const __grid_constant__ vm_ctx c) {
+  __shared__ double sm_red[8];
+  constexpr int NT = NodeTab<K>::STRIDE;
+  const int nloc = (int)c.nloc, N = (int)c.N, row0 = (int)c.row0;
+  const int64_t u = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  float p0[K], nu = 0.f;
+  double d[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    p0[k] = 0.f;
+    d[k] = 0.0;
+  }
+  int lrow = 0, i = 0, j = 0, l = 0;
+  double ti = 0.0, tj = 0.0;
+  bool valid = false;
+  float X = 0.f;
+  if (u < c.U) X = c.u_px[u];
+  if (X > 0.f) {
+    lrow = c.u_lrow[u];
+    l = lrow / nloc;
+    valid = c.layer_consts[(int64_t)l * VM_LC_STRIDE(K) + VM_LC_SIMPLE(K)] != 0.0;
+  }
+  if (valid) {
+    j = c.u_col[u];
+    i = lrow - l * nloc + row0;
+    const float xt = c.u_pxt[u];
+    const float* ni = c.nodetab + ((int64_t)l * N + i) * NT;
+    const float* nj = c.nodetab + ((int64_t)l * N + j) * NT;
+    float ti_[NT], tj_[NT];
+    if (K == 2) {
+      const float4 a = *reinterpret_cast<const float4*>(ni), b = *reinterpret_cast<const float4*>(nj);
+      ti_[0] = a.x; ti_[1] = a.y; ti_[2] = a.z; ti_[3] = a.w;
+      tj_[0] = b.x; tj_[1] = b.y; tj_[2] = b.z; tj_[3] = b.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < NT; q += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(ni + q), b = *reinterpret_cast<const float4*>(nj + q);
+        ti_[q] = a.x; ti_[q + 1] = a.y; ti_[q + 2] = a.z; ti_[q + 3] = a.w;
+        tj_[q] = b.x; tj_[q + 1] = b.y; tj_[q + 2] = b.z; tj_[q + 3] = b.w;
+      }
+    }
+    ti = (double)ti_[K + 1];  // active reporter flags (1 / 0), as vm_fix_accumulate expects E[theta] > 0
+    tj = (double)tj_[K + 1];
+    const bool single = xt != 0.f, rowrep = xt > 0.f;
+    const float g = single ? (rowrep ? ti_[K - 1] : tj_[K - 1]) : 1.f;
+    const float el = single ? (rowrep ? ti_[K] : tj_[K]) : 0.f;
+    const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
+    const float ell0 = (float)(c.Elog_lambda[l * K] * VM_LOG2E);
+    const float z2 = (float)c.nu[VM_NU_G] * fabsf(xt);
+    float f[K], iden[K], gl[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      const double v = block_sum<VM_DENSE_THREADS>((double)p0acc[k], S.sm_red);
-      if (tid == 0 && v != 0.0)
-        atomicAdd(reinterpret_cast<unsigned long long*>(c.fixP) + l * K + k,
+      gl[k] = (float)c.G_lambda[l * K + k];
+      const float z1 = g * gl[k];
+      iden[k] = vm_rcp(z1 + z2);
+      f[k] = single ? z1 * iden[k] : 1.f;
+    }
+    const float t0 = z2 * g * iden[0];
+    float s = 0.f, sf = 0.f, es[K], ef[K];
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+      const float ellk = (float)(c.Elog_lambda[l * K + k] * VM_LOG2E);
+      const float dgl = (float)(c.G_lambda[l * K + k] - c.G_lambda[l * K]);
+      const float dat = single ? X * ((t0 * iden[k] * dgl) * el + (f[k] * ellk - f[0] * ell0)) : X * (float)lc[VM_LC_G(K, k)];
+      const float qk = tj_[k - 1];
+      es[k] = vm_ex2(fminf(ti_[k - 1] + qk + c.u_lo[u * (K - 1) + (k - 1)] + dat, VM_CLAMP_LOG2));
+      s += es[k];
+      // the closed form the dense sweep counts for this tie: same operations, same bits
+      ef[k] = vm_ex2(fminf(__fadd_rn(c.tab_p[(int64_t)lrow * K + k], c.tab_q[((int64_t)l * N + j) * K + k]), VM_CLAMP_LOG2));
+      sf = (k == 1) ? ef[k] : __fadd_rn(sf, ef[k]);
+    }
+    const float inv = vm_rcp(1.f + s), invf = vm_rcp(__fadd_rn(1.f, sf));
+    float rho[K];
+    rho[0] = inv;
+    float nu_t = inv * iden[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+      rho[k] = es[k] * inv;
+      nu_t += rho[k] * iden[k];
+      d[k] = (double)rho[k] - (double)__fmul_rn(ef[k], invf);
+    }
+    float* ru = c.rho_u32 + u * K;
+    if (K == 2) {
+      *reinterpret_cast<float2*>(ru) = make_float2(rho[0], rho[1]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) ru[k] = rho[k];
+    }
+    if (single) {
+      nu = X * z2 * nu_t;
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) p0[k] = rho[k] * X;
+    }
+  }
+  // per-reporter corrections (warp-collective; row contributions pre-combined by a segmented scan)
+  {
+    // the layer of a warp's ties can differ at a layer boundary: accumulate per lane group of equal layer
+    const int l0 = __shfl_sync(0xffffffffu, l, 0);
+    const unsigned same = __ballot_sync(0xffffffffu, !valid || l == l0);
+    if (same == 0xffffffffu) {
+      unsigned long long* fix_l = reinterpret_cast<unsigned long long*>(c.fixA) + (int64_t)l0 * c.M * K;
+      vm_fix_accumulate<K>(fix_l, c.ego_diag != 0, valid, lrow, i, j, ti, tj, d, 0);
+    } else {  // rare: the warp straddles two layers -- plain atomics
+      if (valid) {
+        unsigned long long* fix_l = reinterpret_cast<unsigned long long*>(c.fixA) + (int64_t)l * c.M * K;
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+          const long long q = __double2ll_rn(d[k] * VM_FIX_SCALE);
+          if (q != 0 && ti > 0.0) atomicAdd(fix_l + (int64_t)i * K + k, (unsigned long long)q);
+          if (q != 0 && tj > 0.0) atomicAdd(fix_l + (int64_t)j * K + k, (unsigned long long)q);
+        }
+      }
+    }
+  }
+  // rho_k X of the SIMPLE ties (per layer) and the nu statistic of the SINGLE ties: fixed-point atomics, one per block
+  // when the block's ties belong to one layer (ties are sorted by layer: all but at most L-1 blocks), else per thread
+  __shared__ int s_lmin[8], s_lmax[8];
+  int lmin = valid ? l : 0x7fffffff, lmax = valid ? l : -1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+    lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_lmin[threadIdx.x >> 5] = lmin;
+    s_lmax[threadIdx.x >> 5] = lmax;
+  }
+  __syncthreads();
+  lmin = s_lmin[0];
+  lmax = s_lmax[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) {
+    lmin = min(lmin, s_lmin[w]);
+    lmax = max(lmax, s_lmax[w]);
+  }
+  if (lmax < 0) return;  // no shortcut tie in this block (block-uniform)
+  const double vn = block_sum<256>((double)nu, sm_red);
+  if (threadIdx.x == 0 && vn != 0.0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(c.dev_flags) + VM_FLAG_FIXNU,
+              (unsigned long long)__double2ll_rn(vn * VM_FIXP_SCALE));
+  if (lmin == lmax) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double v = block_sum<256>((double)p0[k], sm_red);
+      if (threadIdx.x == 0 && v != 0.0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(c.fixP) + lmin * K + k,
                   (unsigned long long)__double2ll_rn(v * VM_FIXP_SCALE));
     }
-    const double vn = block_sum<VM_DENSE_THREADS>((double)nuacc, S.sm_red);
-    if (tid == 0 && vn != 0.0)
-      atomicAdd(reinterpret_cast<unsigned long long*>(c.dev_flags) + VM_FLAG_FIXNU,
-                (unsigned long long)__double2ll_rn(vn * VM_FIXP_SCALE));
+  } else if (valid) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (p0[k] != 0.f)
+        atomicAdd(reinterpret_cast<unsigned long long*>(c.fixP) + l * K + k,
+                  (unsigned long long)__double2ll_rn((double)p0[k] * VM_FIXP_SCALE));
   }
 }
 
@@ -1743,14 +1738,18 @@ __global__ void __launch_bounds__(256) k_elbo_b(const __grid_constant__ vm_ctx c
 // stage 1: grid (VM_S1_BLOCKS, L), block (bx, l) reduces its slice of layer l's per-warp partials of k_special /
 // k_init_delta: nu, cat, t2 and p0[k] -> s1[((l*VM_S1_BLOCKS + bx)*(3+K)) + slot]
 #define VM_S1_BLOCKS 64
+#define VM_F_LISTED 256  // internal: this rho update ran the special-tie kernel in list mode (see launch_special)
 __global__ void __launch_bounds__(256) k_sums_stage1(const __grid_constant__ vm_ctx c, int flags, const double* upart,
                                                      double* s1) {
   __shared__ double sm[8];
   const int l = blockIdx.y, K = (int)c.K;
   const bool elbo = flags & VM_F_ELBO, init = flags & VM_F_INIT;
   const int64_t nwl = c.n_ublk * 8, nup = c.L * nwl;
+  // a layer whose special-tie kernel ran in list mode only wrote the partials of its first n_cxblk blocks
+  const bool listed = (flags & VM_F_LISTED) && c.layer_consts[(int64_t)l * VM_LC_STRIDE(K) + VM_LC_SIMPLE(K)] != 0.0;
+  const int64_t nuse = listed ? min(nwl, c.n_cxblk * 8) : nwl;
   const int64_t per = (nwl + VM_S1_BLOCKS - 1) / VM_S1_BLOCKS;
-  const int64_t q0 = (int64_t)l * nwl + (int64_t)blockIdx.x * per, q1 = min(q0 + per, (int64_t)(l + 1) * nwl);
+  const int64_t q0 = (int64_t)l * nwl + (int64_t)blockIdx.x * per, q1 = min(q0 + per, (int64_t)l * nwl + nuse);
   double* out = s1 + ((int64_t)l * VM_S1_BLOCKS + blockIdx.x) * (3 + K);
   for (int slot = 0; slot < 3 + K; ++slot) {
     const bool used = slot >= 3 ? true : (init ? false : (slot == UP_NU ? true : elbo));
@@ -1952,12 +1951,12 @@ static bool simple_iteration(const vm_ctx* c, int flags) {
 }
 
 // dynamic shared memory of the fast dense kernel (opt-in above 48 KB; set once per process and instantiation)
-template <int K, bool ELBO, bool SIMPLE>
+template <int K, bool ELBO>
 static cudaError_t fast_setup() {
   static bool done = false;
   if (done) return cudaSuccess;
-  const cudaError_t e = cudaFuncSetAttribute(k_dense_fast<K, ELBO, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(FastSmem<K, SIMPLE>));
+  const cudaError_t e = cudaFuncSetAttribute(k_dense_fast<K, ELBO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(FastSmem<K>));
   done = (e == cudaSuccess);
   return e;
 }
@@ -1965,9 +1964,8 @@ template <int K>
 static cudaError_t fast_setup_all() {
   if constexpr (K <= 4) {  // the fast kernel is only instantiated (and eligible) for K <= 4
     cudaError_t e;
-    if ((e = fast_setup<K, true, false>()) != cudaSuccess) return e;
-    if ((e = fast_setup<K, false, true>()) != cudaSuccess) return e;
-    return fast_setup<K, false, false>();
+    if ((e = fast_setup<K, true>()) != cudaSuccess) return e;
+    return fast_setup<K, false>();
   } else {
     return cudaSuccess;
   }
@@ -1980,7 +1978,6 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, in
   const bool elbo = flags & VM_F_ELBO, store = !(flags & VM_F_NO_STORE), csr = c->r_mode == VM_R_CSR;
   double* cp = region_cat(c);
   const bool fast = dense_fast_eligible<K>(c, flags);
-  const bool simple = simple_iteration<K>(c, flags);
   if (fast) {
     const cudaError_t e = fast_setup_all<K>();
     if (e != cudaSuccess) return (int)e;
@@ -2012,9 +2009,8 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, in
 #define LF()                                                                                                             \
   do {                                                                                                                   \
     if constexpr (K <= 4) {                                                                                              \
-      if (elbo) k_dense_fast<K, true><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<K, false>), st>>>(*c, cp, rt0, rtn);       \
-      else if (simple) k_dense_fast<K, false, true><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<K, true>), st>>>(*c, cp, rt0, rtn); \
-      else k_dense_fast<K, false><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<K, false>), st>>>(*c, cp, rt0, rtn);           \
+      if (elbo) k_dense_fast<K, true><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<K>), st>>>(*c, cp, rt0, rtn);              \
+      else k_dense_fast<K, false><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<K>), st>>>(*c, cp, rt0, rtn);                  \
     }                                                                                                                    \
   } while (0)
   if (fast && !side) LF();
@@ -2050,8 +2046,12 @@ static int launch_special(const vm_ctx* c, int flags, cudaStream_t st, int chunk
 #define LS(E, M) k_special<K, E, M><<<grid, 256, 0, st>>>(*c, region_u(c), chunk)
   if (chunk < 0 && simple_iteration<K>(c, flags)) {
     if constexpr (K <= 4) {  // (simple_iteration is never true for larger K)
-      k_special<K, false, VM_R_EGO, 1><<<grid, 256, 0, st>>>(*c, region_u(c), chunk);  // layers that take the shortcut
+      // layers that take the shortcut: the special-tie kernel walks the list of the other special ties (its grid covers
+      // that list only; k_sums_stage1 reads as many partial slots) while k_shortcut evaluates the shortcut ties
+      const dim3 gridl((unsigned)(c->n_cxblk > 0 ? c->n_cxblk : 1), (unsigned)c->L);
+      k_special<K, false, VM_R_EGO, 1><<<gridl, 256, 0, st>>>(*c, region_u(c), chunk);
       k_special<K, false, VM_R_EGO, 2><<<grid, 256, 0, st>>>(*c, region_u(c), chunk);  // layers that cannot
+      k_shortcut<K><<<(unsigned)cdiv(c->U, 256), 256, 0, st>>>(*c);
     }
   } else if (c->r_mode == VM_R_EGO) {
     if (elbo) LS(true, VM_R_EGO); else LS(false, VM_R_EGO);
@@ -2224,7 +2224,10 @@ static int tu_phase_rho(const vm_ctx* c, int flags, void* stream) {
     DISPATCH_K(c->K, (k_elbo_b<K><<<VM_B_BLOCKS, 256, 0, st>>>(*c, region_b(c))));
     VM_CHECK_LAUNCH();
   }
-  k_sums_stage1<<<dim3(VM_S1_BLOCKS, (unsigned)c->L), 256, 0, st>>>(*c, flags, region_u(c), region_s1(c));
+  bool listed = false;
+  DISPATCH_K(c->K, listed = simple_iteration<K>(c, flags));
+  k_sums_stage1<<<dim3(VM_S1_BLOCKS, (unsigned)c->L), 256, 0, st>>>(*c, flags | (listed ? VM_F_LISTED : 0), region_u(c),
+                                                                    region_s1(c));
   VM_CHECK_LAUNCH();
   k_sums_reduce<<<1, 256, 0, st>>>(*c, flags, region_s1(c), region_cat(c), n_catpart(c), region_b(c),
                                    c->mutuality ? VM_B_BLOCKS : 0);

@@ -18,6 +18,9 @@ Extra, optional `fit` keywords (a superset of the reference's):
                  "fast" (draws only for the ties that need them), or "auto" (reference when L*N*N*K <= 5e7);
     device     : CUDA device (default: current);
     distributed: "auto" | True | False -- shard the ties by node-row blocks over torch.distributed ranks;
+    presharded : (sharded fits) X holds only THIS rank's entries -- every X[l,i,j,m] whose row i is in the rank's block and
+                 every reciprocal X[l,j,i,m] of those -- instead of the whole list on every rank (sharded ingestion: each
+                 rank uploads, sorts and pairs about 2/G of the entries); K must then be given;
     concurrent_realisations: "auto" | True | False -- run the `num_realisations` restarts (model.py:386-437) side by
                  side, one CUDA stream + one state per restart over the shared packed data, instead of one after the
                  other.  Same seeds, same trace, same best restart; "auto" = when an iteration is launch-bound
@@ -78,7 +81,7 @@ class VimureModel(TransformerMixin, BaseEstimator):
         warnings and ValueErrors, but X/R end up as COO arrays + a structured mask instead of sktensor objects."""
         available = ["R", "EPS", "K", "bias0", "max_iter", "alpha_lambda", "beta_lambda", "alpha_theta", "beta_theta",
                      "alpha_teta", "beta_teta", "num_realisations", "init_state", "init", "device", "distributed",
-                     "store_rho", "tile_h", "graphs", "concurrent_realisations"]
+                     "store_rho", "tile_h", "graphs", "concurrent_realisations", "presharded"]
         for p in extra_params:
             if p not in available:
                 self.logger.warning("Ignoring unrecognised parameter %s." % p)
@@ -248,6 +251,13 @@ class VimureModel(TransformerMixin, BaseEstimator):
             self._packed = P = _packing.pack(self.X.subs, self.X.vals, self.L, self.N, self.M, self.K, self.R, dev,
                                              row0=row0, nloc=nloc, tile_h=int(extra_params.get("tile_h", 128)),
                                              mutuality=self.mutuality, split_e0=split_e0)
+            if world > 1 and extra_params.get("presharded", False):
+                # the sum of all counts (nu_rte = beta + sum X, model.py:593-595) from the ranks' own rows
+                if "K" not in extra_params or extra_params["K"] is None:
+                    raise ValueError("presharded=True needs K (a rank cannot see max(X))")
+                t = torch.tensor([float(P.sumX_owned or 0.0)], dtype=torch.float64, device=dev)
+                torch.distributed.all_reduce(t)
+                self.sumX = float(t.item())
             if self.undirected:  # model.py:127-132: X must be symmetric in (i, j)
                 asym = int(not bool(torch.all(P.t["e_xT"] == P.t["e_x"])))
                 if world > 1:  # every rank raises, or none does
@@ -262,9 +272,9 @@ class VimureModel(TransformerMixin, BaseEstimator):
             priors = dict(alpha_theta=self.alpha_theta, beta_theta=self.beta_theta, alpha_lambda=self.alpha_lambda,
                           beta_lambda=self.beta_lambda, alpha_eta=self.alpha_mutuality, beta_eta=self.beta_mutuality)
             self._engine = eng = CaviEngine(P, priors, mutuality=self.mutuality, eps=self.EPS, group=group)
-            if group is None and extra_params.get("graphs", True):
+            if extra_params.get("graphs", True):
                 # one graph replay per iteration instead of ~17 launches: decisive for launch-bound sizes, and still 1.6 %
-                # at config 3 (1.377 -> 1.355 ms per iteration, B200)
+                # at config 3 (1.377 -> 1.355 ms per iteration, B200); sharded fits capture their all-reduces too
                 eng.enable_graphs()
             torch.cuda.synchronize(dev)
             self.pack_time = self.timings["pack+engine"] = time.time() - t0
