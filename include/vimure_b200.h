@@ -301,6 +301,9 @@ int vm_materialize_prior(const vm_ctx* c, void* stream);
  * out[t] = argmax_k rho[t,k] (mode 0) or rho[t,1] >= threshold (mode 1), uint8, [L*nloc*N]. */
 int vm_infer(const vm_ctx* c, int mode, double threshold, uint8_t* out, void* stream);
 
+/* rho_mean (model.py:1151-1153): out[t] = sum_k k rho[t,k], float32, [L*nloc*N]. */
+int vm_infer_mean(const vm_ctx* c, float* out, void* stream);
+
 /* `sample_inferred_model` on the dense slab (model.py:1062-1096): out[t] = argmax_k of the counts of n_trials draws from
  * Categorical(rho[t,:]) (numpy: multinomial(n_trials, rho).argmax(-1)), uint8, [L*nloc*N].  Counter-based RNG (Philox4x32-10)
  * keyed by `seed` and the GLOBAL tie id: reproducible, independent of launch geometry and of the sharding.  The stream is
@@ -321,6 +324,8 @@ typedef struct vm_synth {
   uint64_t seed;
   double eta;                /* mutuality of the reports, in [0,1) */
   const double* theta;       /* [L*M] reporter reliabilities */
+  const double* lam;         /* [L*K] average interactions per ground-truth category (lam[l,0]: no tie), or NULL for the
+                                reference generator's default 0.01, 1, 2, .. (synthetic.py:140-157) */
   const int64_t* y_key;      /* [nY] sorted keys (l*N+i)*N+j of the true ties Y (ground truth, a few per node) */
   const int32_t* y_val;      /* [nY] Y_lij >= 1 */
   int64_t nY;

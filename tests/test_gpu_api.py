@@ -109,6 +109,32 @@ def test_inferred_model_methods(fitted):
     assert post["theta"].shape == (1, 100) and post["lambda"].shape == (1, 2) and post["rho"].shape == (1, 100, 100, 2)
 
 
+def test_consumers_read_the_best_restart_whichever_slab_holds_it():
+    """rho_f is the posterior of the BEST restart (model.py:925-942): the consumers must read it whether it is the last
+    restart's slab, a device copy kept from an earlier restart (sequential restarts) or another engine's slab (restarts
+    side by side) -- all four methods against the host copy of rho_f."""
+    _cuda()
+    import vimure_b200 as vm
+    from tests.golden_util import Golden
+    from tests.test_gpu_parity import build_inputs
+
+    g = Golden("f1_over")
+    X, R = build_inputs(g)
+    for conc in (False, True):
+        model = vm.VimureModel(mutuality=True)
+        fk = dict(g.fit_kwargs)
+        fk.update(num_realisations=3, max_iter=11, concurrent_realisations=conc, seed=3)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            model.fit(X, R=R, **fk)
+        rf = model.rho_f
+        assert np.array_equal(model.get_inferred_model("rho_max"), np.argmax(rf, axis=-1))
+        np.testing.assert_allclose(model.get_inferred_model("rho_mean"), rf[..., 1], rtol=0, atol=0)
+        assert np.array_equal(model.get_inferred_model("fixed_threshold", threshold=0.3), (rf[..., 1] >= np.float32(0.3)).astype(float))
+        thr = np.float32(0.54 * model.G_exp_nu - 0.01)
+        assert np.array_equal(model.get_inferred_model("heuristic_threshold"), (rf[..., 1] >= thr).astype(int))
+
+
 def test_sample_inferred_model(fitted):
     """reference test_model.py:430-438"""
     net, models = fitted

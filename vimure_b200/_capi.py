@@ -126,6 +126,7 @@ def open_library(path):
         "vm_materialize_prior": (i, [P, vp]),
         "vm_infer": (i, [P, i, d, vp, vp]),
         "vm_sample": (i, [P, i64, ctypes.c_uint64, vp, vp]),
+        "vm_infer_mean": (i, [P, vp, vp]),
         "vm_test_special": (i, [vp, vp, vp, i64, vp]),
         "vm_synth_size": (i64, []),
         "vm_synth_ego": (i, [ctypes.POINTER(synth_class()), vp]),

@@ -344,9 +344,25 @@ class CaviEngine:
                 raise RuntimeError("the dense rho slab was not stored in the last iteration (store=False)")
         return self.rho
 
-    def infer(self, mode=0, threshold=0.5):
+    def _use_slab(self, slab):
+        """Point the consumers at `slab` (a copy of an earlier restart's posterior) instead of the engine's own; returns the
+        pointer to restore."""
+        old = self.ctx.rho
+        if slab is None:
+            self.rho_slab()
+        else:
+            self.ctx.rho = slab.data_ptr()
+        return old
+
+    def infer(self, mode=0, threshold=0.5, slab=None):
         """argmax_k rho (mode 0) or rho[...,1] >= threshold (mode 1) on the device: uint8 (L, nloc, N)."""
-        self.rho_slab()
+        old = self._use_slab(slab)
+        try:
+            return self._infer(mode, threshold)
+        finally:
+            self.ctx.rho = old
+
+    def _infer(self, mode, threshold):
         P = self.P
         out = torch.empty(P.L, P.nloc, P.N, dtype=torch.uint8, device=self.dev)
         _capi.check(self.lib.vm_infer(self._cref, int(mode), float(threshold), ctypes.c_void_p(out.data_ptr()),
@@ -354,13 +370,28 @@ class CaviEngine:
         self.n_launch += 1
         return out
 
-    def sample(self, n_trials=1, seed=0):
+    def infer_mean(self, slab=None):
+        """sum_k k rho_k (reference `rho_mean`, model.py:1151-1153) on the device: float32 (L, nloc, N)."""
+        old = self._use_slab(slab)
+        try:
+            P = self.P
+            out = torch.empty(P.L, P.nloc, P.N, dtype=torch.float32, device=self.dev)
+            _capi.check(self.lib.vm_infer_mean(self._cref, ctypes.c_void_p(out.data_ptr()), self._stream()), "vm_infer_mean")
+            self.n_launch += 1
+            return out
+        finally:
+            self.ctx.rho = old
+
+    def sample(self, n_trials=1, seed=0, slab=None):
         """argmax of the counts of `n_trials` categorical draws per tie (reference `sample_inferred_model`,
         model.py:1086-1088) on the device: uint8 (L, nloc, N).  Philox stream keyed by (seed, global tie id)."""
-        self.rho_slab()
-        P = self.P
-        out = torch.empty(P.L, P.nloc, P.N, dtype=torch.uint8, device=self.dev)
-        _capi.check(self.lib.vm_sample(self._cref, int(n_trials), ctypes.c_uint64(int(seed) & (2**64 - 1)),
-                                       ctypes.c_void_p(out.data_ptr()), self._stream()), "vm_sample")
-        self.n_launch += 1
-        return out
+        old = self._use_slab(slab)
+        try:
+            P = self.P
+            out = torch.empty(P.L, P.nloc, P.N, dtype=torch.uint8, device=self.dev)
+            _capi.check(self.lib.vm_sample(self._cref, int(n_trials), ctypes.c_uint64(int(seed) & (2**64 - 1)),
+                                           ctypes.c_void_p(out.data_ptr()), self._stream()), "vm_sample")
+            self.n_launch += 1
+            return out
+        finally:
+            self.ctx.rho = old

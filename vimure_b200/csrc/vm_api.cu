@@ -35,6 +35,26 @@ extern "C" int vm_infer(const vm_ctx* c, int mode, double threshold, uint8_t* ou
   VM_ROUTE(infer(c, mode, threshold, out, stream));
 }
 
+// ---- rho_mean on the slab (model.py:1151-1153): sum_k k rho_k, 4 bytes per tie back instead of an fp64 copy of rho -----
+__global__ void __launch_bounds__(256) k_infer_mean(const float* __restrict__ rho, int64_t T, int K, float* __restrict__ out) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
+    const float* r = rho + t * K;
+    float s = 0.f;
+    for (int k = 1; k < K; ++k) s += (float)k * r[k];
+    out[t] = s;
+  }
+}
+extern "C" int vm_infer_mean(const vm_ctx* c, float* out, void* stream) {
+  if (!c || !out || c->K < 2 || c->K > VM_MAX_K || !c->rho) return VM_EINVAL;
+  const int64_t T = c->L * c->nloc * c->N;
+  if (T <= 0) return 0;
+  int64_t nb = (T + 255) / 256;
+  if (nb > 148 * 32) nb = 148 * 32;
+  k_infer_mean<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(c->rho, T, (int)c->K, out);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
 // ---- posterior sampling on the slab (model.py:1062-1096) ------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011), counter = (global tie id, block of 4 draws), key = seed: the stream of a tie does
 // not depend on the launch geometry nor on how the ties are sharded over ranks.
@@ -76,7 +96,8 @@ __global__ void __launch_bounds__(256) k_sample(const float* __restrict__ rho, i
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (d0 + q >= n_trials) break;
-        const float u = ((float)(xs[q] >> 8) + 0.5f) * (1.0f / 16777216.0f) * sum;  // uniform on (0, sum)
+        // uniform strictly inside (0, sum): 23 random bits + 1/2 is exact in fp32 (24 bits would round up to 1.0)
+        const float u = ((float)(xs[q] >> 9) + 0.5f) * (1.0f / 8388608.0f) * sum;
         float cum = 0.f;
         int k = 0;
         for (; k < K - 1; ++k) {

@@ -1332,61 +1332,113 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
 // passes), (posterior - closed form) into the fixed-point per-reporter corrections -- the closed form recomputed with
 // the dense sweep's operations, same bits --, rho_k X of the SIMPLE ties into fixP (their part of the next phi-shape
 // sums), sum_k dz2_k rho_k = x z2 sum_k rho_k/(z1_k+z2) of the SINGLE ties (model.py:822-825) into dev_flags[VM_FLAG_FIXNU].
+// Tiled like the dense kernel -- one CTA per (layer, row tile of tile_h rows, FULL column tile of TW columns) -- because
+// what limits a tie-ordered version is not arithmetic but scattered access: a warp of 32 consecutive special ties touches
+// 32 different column nodes (table gather + one global atomic each).  Here the node tables of the tile's TW column nodes
+// and tile_h row nodes are staged in shared memory once, the per-reporter corrections are accumulated in shared memory
+// (64-bit integer atomics) and flushed with one global atomic per touched node, and the CTA's ~tile_h*19 special ties are
+// spread over all its threads (a prefix sum over the rows' segments maps a thread to its tie).
+#define VM_SC_THREADS 256
 template <int K>
-__global__ void __launch_bounds__(256) k_shortcut(const __grid_constant__ vm_ctx c) {
-  __shared__ double sm_red[8];
-  constexpr int NT = NodeTab<K>::STRIDE;
-  const int nloc = (int)c.nloc, N = (int)c.N, row0 = (int)c.row0;
-  const int64_t u = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  float p0[K], nu = 0.f;
-  double d[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    p0[k] = 0.f;
-    d[k] = 0.0;
-  }
-  int lrow = 0, i = 0, j = 0, l = 0;
-  double ti = 0.0, tj = 0.0;
-  bool valid = false;
-  float X = 0.f;
-  if (u < c.U) X = c.u_px[u];
-  if (X > 0.f) {
-    lrow = c.u_lrow[u];
-    l = lrow / nloc;
-    valid = c.layer_consts[(int64_t)l * VM_LC_STRIDE(K) + VM_LC_SIMPLE(K)] != 0.0;
-  }
-  if (valid) {
-    j = c.u_col[u];
-    i = lrow - l * nloc + row0;
-    const float xt = c.u_pxt[u];
-    const float* ni = c.nodetab + ((int64_t)l * N + i) * NT;
-    const float* nj = c.nodetab + ((int64_t)l * N + j) * NT;
-    float ti_[NT], tj_[NT];
-    if (K == 2) {
-      const float4 a = *reinterpret_cast<const float4*>(ni), b = *reinterpret_cast<const float4*>(nj);
-      ti_[0] = a.x; ti_[1] = a.y; ti_[2] = a.z; ti_[3] = a.w;
-      tj_[0] = b.x; tj_[1] = b.y; tj_[2] = b.z; tj_[3] = b.w;
-    } else {
-#pragma unroll
-      for (int q = 0; q < NT; q += 4) {
-        const float4 a = *reinterpret_cast<const float4*>(ni + q), b = *reinterpret_cast<const float4*>(nj + q);
-        ti_[q] = a.x; ti_[q + 1] = a.y; ti_[q + 2] = a.z; ti_[q + 3] = a.w;
-        tj_[q] = b.x; tj_[q + 1] = b.y; tj_[q + 2] = b.z; tj_[q + 3] = b.w;
-      }
+__global__ void __launch_bounds__(VM_SC_THREADS) k_shortcut(const __grid_constant__ vm_ctx c) {
+  constexpr int NT = NodeTab<K>::STRIDE, TW = DenseCfg<K>::TW, TH = VM_FAST_MAX_TILE_H;
+  __shared__ __align__(16) float nt_col[TW * NT];
+  __shared__ __align__(16) float nt_row[TH * NT];
+  __shared__ float s_tabp[TH][K - 1];
+  __shared__ unsigned long long colfix[TW][K - 1], rowfix[TH][K - 1];
+  __shared__ int s_tp0[TH], s_off[TH + 1];
+  __shared__ float s_lam[3 * K + 1 + K];  // G_lambda_k | G_lambda_k - G_lambda_0 | E[log lambda_k] log2e | G_nu | g_k
+  __shared__ double sm_red[VM_SC_THREADS / 32];
+  const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
+  const int ct = blockIdx.x;
+  const int l = blockIdx.y / nrt, rt = blockIdx.y - l * nrt;
+  const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
+  if (lc[VM_LC_SIMPLE(K)] == 0.0) return;  // the special-tie kernel has this layer in full
+  const int tid = threadIdx.x;
+  const int jt = ct * TW, i_lo = rt * (int)c.tile_h;
+  const int nrows = min((int)c.tile_h, nloc - i_lo);
+  // ---- special-tie ranges of the tile's row segments, and their exclusive prefix sum
+  if (tid < TH) {
+    int a = 0, n = 0;
+    if (tid < nrows) {
+      const int64_t lrow = (int64_t)l * nloc + i_lo + tid;
+      a = __ldg(&c.utile_ptr[lrow * nct + ct]);
+      n = __ldg(&c.utile_ptr[lrow * nct + ct + 1]) - a;
     }
-    ti = (double)ti_[K + 1];  // active reporter flags (1 / 0), as vm_fix_accumulate expects E[theta] > 0
-    tj = (double)tj_[K + 1];
+    s_tp0[tid] = a;
+    s_off[tid + 1] = n;
+  }
+  if (tid == 0) s_off[0] = 0;
+  __syncthreads();
+  if (tid < 32) {  // TH = 128 counts: 4 per lane, warp scan
+    int v[4], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      v[q] = s_off[1 + 4 * tid + q];
+      sum += v[q];
+    }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (tid >= o) inc += t;
+    }
+    int run = inc - sum;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      run += v[q];
+      s_off[1 + 4 * tid + q] = run;
+    }
+  }
+  // ---- node tables of the tile, per-layer constants, cleared accumulators
+  for (int t = tid; t < TW * NT / 4; t += VM_SC_THREADS)
+    reinterpret_cast<float4*>(nt_col)[t] = __ldg(reinterpret_cast<const float4*>(c.nodetab + ((int64_t)l * N + jt) * NT) + t);
+  for (int t = tid; t < nrows * NT / 4; t += VM_SC_THREADS)
+    reinterpret_cast<float4*>(nt_row)[t] =
+        __ldg(reinterpret_cast<const float4*>(c.nodetab + ((int64_t)l * N + (int)c.row0 + i_lo) * NT) + t);
+  for (int t = tid; t < nrows * (K - 1); t += VM_SC_THREADS) {
+    const int r = t / (K - 1), k = t - r * (K - 1) + 1;
+    s_tabp[r][k - 1] = __ldg(&c.tab_p[((int64_t)l * nloc + i_lo + r) * K + k]);
+  }
+  for (int t = tid; t < TW * (K - 1); t += VM_SC_THREADS) (&colfix[0][0])[t] = 0ull;
+  for (int t = tid; t < TH * (K - 1); t += VM_SC_THREADS) (&rowfix[0][0])[t] = 0ull;
+  if (tid < K) {
+    const double g0 = c.G_lambda[l * K], gkk = c.G_lambda[l * K + tid];
+    s_lam[tid] = (float)gkk;
+    s_lam[K + tid] = (float)(gkk - g0);
+    s_lam[2 * K + tid] = (float)(c.Elog_lambda[l * K + tid] * VM_LOG2E);
+    s_lam[3 * K + 1 + tid] = (float)lc[VM_LC_G(K, tid)];
+    if (tid == 0) s_lam[3 * K] = (float)c.nu[VM_NU_G];
+  }
+  __syncthreads();
+  const int total = s_off[TH];
+  float p0[K], nu = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) p0[k] = 0.f;
+  for (int e = tid; e < total; e += VM_SC_THREADS) {
+    // row segment of entry e: the last r with s_off[r] <= e
+    int lo = 0, hi = TH;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_off[mid] <= e) lo = mid;
+      else hi = mid;
+    }
+    const int r = lo;
+    const int64_t u = (int64_t)s_tp0[r] + (e - s_off[r]);
+    const float X = c.u_px[u];
+    if (!(X > 0.f)) continue;  // not a shortcut tie
+    const int cj = c.u_col[u] - jt;
+    const float xt = c.u_pxt[u];
+    const float* ni = nt_row + r * NT;
+    const float* nj = nt_col + cj * NT;
     const bool single = xt != 0.f, rowrep = xt > 0.f;
-    const float g = single ? (rowrep ? ti_[K - 1] : tj_[K - 1]) : 1.f;
-    const float el = single ? (rowrep ? ti_[K] : tj_[K]) : 0.f;
-    const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
-    const float ell0 = (float)(c.Elog_lambda[l * K] * VM_LOG2E);
-    const float z2 = (float)c.nu[VM_NU_G] * fabsf(xt);
-    float f[K], iden[K], gl[K];
+    const float g = single ? (rowrep ? ni[K - 1] : nj[K - 1]) : 1.f;
+    const float el = single ? (rowrep ? ni[K] : nj[K]) : 0.f;
+    const float z2 = s_lam[3 * K] * fabsf(xt);
+    float f[K], iden[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      gl[k] = (float)c.G_lambda[l * K + k];
-      const float z1 = g * gl[k];
+      const float z1 = g * s_lam[k];
       iden[k] = vm_rcp(z1 + z2);
       f[k] = single ? z1 * iden[k] : 1.f;
     }
@@ -1394,25 +1446,29 @@ __global__ void __launch_bounds__(256) k_shortcut(const __grid_constant__ vm_ctx
     float s = 0.f, sf = 0.f, es[K], ef[K];
 #pragma unroll
     for (int k = 1; k < K; ++k) {
-      const float ellk = (float)(c.Elog_lambda[l * K + k] * VM_LOG2E);
-      const float dgl = (float)(c.G_lambda[l * K + k] - c.G_lambda[l * K]);
-      const float dat = single ? X * ((t0 * iden[k] * dgl) * el + (f[k] * ellk - f[0] * ell0)) : X * (float)lc[VM_LC_G(K, k)];
-      const float qk = tj_[k - 1];
-      es[k] = vm_ex2(fminf(ti_[k - 1] + qk + c.u_lo[u * (K - 1) + (k - 1)] + dat, VM_CLAMP_LOG2));
+      const float dat = single ? X * ((t0 * iden[k] * s_lam[K + k]) * el + (f[k] * s_lam[2 * K + k] - f[0] * s_lam[2 * K]))
+                               : X * s_lam[3 * K + 1 + k];
+      const float qk = nj[k - 1];
+      es[k] = vm_ex2(fminf(ni[k - 1] + qk + c.u_lo[u * (K - 1) + (k - 1)] + dat, VM_CLAMP_LOG2));
       s += es[k];
-      // the closed form the dense sweep counts for this tie: same operations, same bits
-      ef[k] = vm_ex2(fminf(__fadd_rn(c.tab_p[(int64_t)lrow * K + k], c.tab_q[((int64_t)l * N + j) * K + k]), VM_CLAMP_LOG2));
+      // the closed form the dense sweep counts for this tie: same operations, same bits (qk == tab_q[l,j,k])
+      ef[k] = vm_ex2(fminf(__fadd_rn(s_tabp[r][k - 1], qk), VM_CLAMP_LOG2));
       sf = (k == 1) ? ef[k] : __fadd_rn(sf, ef[k]);
     }
     const float inv = vm_rcp(1.f + s), invf = vm_rcp(__fadd_rn(1.f, sf));
     float rho[K];
     rho[0] = inv;
     float nu_t = inv * iden[0];
+    const bool act_i = ni[K + 1] != 0.f, act_j = nj[K + 1] != 0.f;
 #pragma unroll
     for (int k = 1; k < K; ++k) {
       rho[k] = es[k] * inv;
       nu_t += rho[k] * iden[k];
-      d[k] = (double)rho[k] - (double)__fmul_rn(ef[k], invf);
+      const long long q = __double2ll_rn(((double)rho[k] - (double)__fmul_rn(ef[k], invf)) * VM_FIX_SCALE);
+      if (q != 0) {
+        if (act_j) atomicAdd(&colfix[cj][k - 1], (unsigned long long)q);
+        if (act_i) atomicAdd(&rowfix[r][k - 1], (unsigned long long)q);
+      }
     }
     float* ru = c.rho_u32 + u * K;
     if (K == 2) {
@@ -1422,72 +1478,34 @@ __global__ void __launch_bounds__(256) k_shortcut(const __grid_constant__ vm_ctx
       for (int k = 0; k < K; ++k) ru[k] = rho[k];
     }
     if (single) {
-      nu = X * z2 * nu_t;
+      nu += X * z2 * nu_t;
     } else {
 #pragma unroll
-      for (int k = 0; k < K; ++k) p0[k] = rho[k] * X;
+      for (int k = 0; k < K; ++k) p0[k] += rho[k] * X;
     }
-  }
-  // per-reporter corrections (warp-collective; row contributions pre-combined by a segmented scan)
-  {
-    // the layer of a warp's ties can differ at a layer boundary: accumulate per lane group of equal layer
-    const int l0 = __shfl_sync(0xffffffffu, l, 0);
-    const unsigned same = __ballot_sync(0xffffffffu, !valid || l == l0);
-    if (same == 0xffffffffu) {
-      unsigned long long* fix_l = reinterpret_cast<unsigned long long*>(c.fixA) + (int64_t)l0 * c.M * K;
-      vm_fix_accumulate<K>(fix_l, c.ego_diag != 0, valid, lrow, i, j, ti, tj, d, 0);
-    } else {  // rare: the warp straddles two layers -- plain atomics
-      if (valid) {
-        unsigned long long* fix_l = reinterpret_cast<unsigned long long*>(c.fixA) + (int64_t)l * c.M * K;
-#pragma unroll
-        for (int k = 1; k < K; ++k) {
-          const long long q = __double2ll_rn(d[k] * VM_FIX_SCALE);
-          if (q != 0 && ti > 0.0) atomicAdd(fix_l + (int64_t)i * K + k, (unsigned long long)q);
-          if (q != 0 && tj > 0.0) atomicAdd(fix_l + (int64_t)j * K + k, (unsigned long long)q);
-        }
-      }
-    }
-  }
-  // rho_k X of the SIMPLE ties (per layer) and the nu statistic of the SINGLE ties: fixed-point atomics, one per block
-  // when the block's ties belong to one layer (ties are sorted by layer: all but at most L-1 blocks), else per thread
-  __shared__ int s_lmin[8], s_lmax[8];
-  int lmin = valid ? l : 0x7fffffff, lmax = valid ? l : -1;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
-    lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-  }
-  if ((threadIdx.x & 31) == 0) {
-    s_lmin[threadIdx.x >> 5] = lmin;
-    s_lmax[threadIdx.x >> 5] = lmax;
   }
   __syncthreads();
-  lmin = s_lmin[0];
-  lmax = s_lmax[0];
-#pragma unroll
-  for (int w = 1; w < 8; ++w) {
-    lmin = min(lmin, s_lmin[w]);
-    lmax = max(lmax, s_lmax[w]);
+  // ---- flush: one global atomic per touched node and category
+  unsigned long long* fix_l = reinterpret_cast<unsigned long long*>(c.fixA) + (int64_t)l * c.M * K;
+  for (int t = tid; t < TW * (K - 1); t += VM_SC_THREADS) {
+    const unsigned long long v = (&colfix[0][0])[t];
+    if (v != 0ull) atomicAdd(fix_l + (int64_t)(jt + t / (K - 1)) * K + 1 + t % (K - 1), v);
   }
-  if (lmax < 0) return;  // no shortcut tie in this block (block-uniform)
-  const double vn = block_sum<256>((double)nu, sm_red);
-  if (threadIdx.x == 0 && vn != 0.0)
+  for (int t = tid; t < nrows * (K - 1); t += VM_SC_THREADS) {
+    const unsigned long long v = (&rowfix[0][0])[t];
+    if (v != 0ull) atomicAdd(fix_l + (int64_t)((int)c.row0 + i_lo + t / (K - 1)) * K + 1 + t % (K - 1), v);
+  }
+  // rho_k X of the SIMPLE ties (their part of the next phi-shape sums) and the nu statistic of the SINGLE ties
+  const double vn = block_sum<VM_SC_THREADS>((double)nu, sm_red);
+  if (tid == 0 && vn != 0.0)
     atomicAdd(reinterpret_cast<unsigned long long*>(c.dev_flags) + VM_FLAG_FIXNU,
               (unsigned long long)__double2ll_rn(vn * VM_FIXP_SCALE));
-  if (lmin == lmax) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const double v = block_sum<256>((double)p0[k], sm_red);
-      if (threadIdx.x == 0 && v != 0.0)
-        atomicAdd(reinterpret_cast<unsigned long long*>(c.fixP) + lmin * K + k,
-                  (unsigned long long)__double2ll_rn(v * VM_FIXP_SCALE));
-    }
-  } else if (valid) {
-#pragma unroll
-    for (int k = 0; k < K; ++k)
-      if (p0[k] != 0.f)
-        atomicAdd(reinterpret_cast<unsigned long long*>(c.fixP) + l * K + k,
-                  (unsigned long long)__double2ll_rn((double)p0[k] * VM_FIXP_SCALE));
+  for (int k = 0; k < K; ++k) {
+    const double v = block_sum<VM_SC_THREADS>((double)p0[k], sm_red);
+    if (tid == 0 && v != 0.0)
+      atomicAdd(reinterpret_cast<unsigned long long*>(c.fixP) + l * K + k,
+                (unsigned long long)__double2ll_rn(v * VM_FIXP_SCALE));
   }
 }
 
@@ -2051,7 +2069,8 @@ static int launch_special(const vm_ctx* c, int flags, cudaStream_t st, int chunk
       const dim3 gridl((unsigned)(c->n_cxblk > 0 ? c->n_cxblk : 1), (unsigned)c->L);
       k_special<K, false, VM_R_EGO, 1><<<gridl, 256, 0, st>>>(*c, region_u(c), chunk);
       k_special<K, false, VM_R_EGO, 2><<<grid, 256, 0, st>>>(*c, region_u(c), chunk);  // layers that cannot
-      k_shortcut<K><<<(unsigned)cdiv(c->U, 256), 256, 0, st>>>(*c);
+      if (c->N / DenseCfg<K>::TW > 0)
+        k_shortcut<K><<<dim3((unsigned)(c->N / DenseCfg<K>::TW), (unsigned)(c->L * c->nrt)), VM_SC_THREADS, 0, st>>>(*c);
     }
   } else if (c->r_mode == VM_R_EGO) {
     if (elbo) LS(true, VM_R_EGO); else LS(false, VM_R_EGO);

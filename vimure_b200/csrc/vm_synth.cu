@@ -66,6 +66,13 @@ __device__ __forceinline__ int y_lookup(const int64_t* __restrict__ yk, const in
   return (lo < nY && yk[lo] == key) ? yv[lo] : 0;
 }
 
+// average interactions of a tie whose ground truth is category y: the caller's table, or the reference generator's
+// default (0.01 for "no tie", y itself otherwise; synthetic.py:140-157)
+__device__ __forceinline__ double lam_of(const vm_synth& s, int l, int y) {
+  if (s.lam) return s.lam[(int64_t)l * s.K + (y < (int)s.K ? y : (int)s.K - 1)];
+  return y > 0 ? (double)y : 0.01;
+}
+
 struct Emit {
   const vm_synth s;
   __device__ __forceinline__ void operator()(int l, int i, int j, int m, int x) const {
@@ -88,7 +95,7 @@ __device__ __forceinline__ bool base_pair(const vm_synth& s, int l, int m, int n
                                           bool& maybe) {
   const uint2 key = make_uint2((uint32_t)s.seed ^ 0x243F6A88u, (uint32_t)(s.seed >> 32) + (uint32_t)l * 0x9E3779B9u);
   const uint4 r = philox4x32(make_uint4((uint32_t)m, (uint32_t)n, 0u, 0x5eedu), key);
-  const double eta = s.eta, mu = th * 0.01, mm = mu / (1.0 - eta);
+  const double eta = s.eta, mu = th * lam_of(s, l, 0), mm = mu / (1.0 - eta);
   const double a = -expm1(-mm), b = exp(-mm) * (-expm1(-mu));  // P(first > 0), P(first = 0, second > 0)
   const double u0 = u01(r.x);
   maybe = u0 < a + b;
@@ -111,7 +118,7 @@ __global__ void __launch_bounds__(256) k_synth_base(const __grid_constant__ vm_s
     const int j = (int)(t - lrow * s.N), l = (int)(lrow / s.nloc), i = (int)(lrow - (int64_t)l * s.nloc + s.row0);
     if (i == j) {
       if (i >= s.M) continue;
-      const double th = s.theta[(int64_t)l * s.M + i], mu = th * 0.01, mm = mu / (1.0 - s.eta);
+      const double th = s.theta[(int64_t)l * s.M + i], mu = th * lam_of(s, l, 0), mm = mu / (1.0 - s.eta);
       const uint2 key = make_uint2((uint32_t)s.seed ^ 0x243F6A88u, (uint32_t)(s.seed >> 32) + (uint32_t)l * 0x9E3779B9u);
       const uint4 r = philox4x32(make_uint4((uint32_t)i, (uint32_t)i, 2u, 0x5eedu), key);
       const int y = poisson_inv(mm, u01(r.x), false);
@@ -153,8 +160,8 @@ __global__ void __launch_bounds__(256) k_synth_edges(const __grid_constant__ vm_
     const bool mine = (m >= s.row0 && m < s.row0 + s.nloc) || (n >= s.row0 && n < s.row0 + s.nloc);
     if (!mine) continue;
     const double th = s.theta[(int64_t)l * s.M + m], eta = s.eta;
-    const double lam_mn = side == 0 ? (double)yab : (yba > 0 ? (double)yba : 0.01);
-    const double lam_nm = side == 0 ? (yba > 0 ? (double)yba : 0.01) : (double)yab;
+    const double lam_mn = lam_of(s, l, side == 0 ? yab : yba);
+    const double lam_nm = lam_of(s, l, side == 0 ? yba : yab);
     const uint2 pk = make_uint2((uint32_t)s.seed ^ 0x243F6A88u, (uint32_t)(s.seed >> 32) + (uint32_t)l * 0x9E3779B9u);
     const uint4 r = philox4x32(make_uint4((uint32_t)m, (uint32_t)n, 1u, 0x5eedu), pk);
     const bool coin = (r.w & 1u) != 0;  // first direction is m->n

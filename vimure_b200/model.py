@@ -40,7 +40,7 @@ from . import _packing, masks
 from ._engine import CaviEngine
 from ._log import setup_logging
 from .sptensor import is_sparse_like, sptensor
-from .utils import apply_rho_threshold, match_arg
+from .utils import get_optimal_threshold, match_arg
 
 INF = 1e10
 DEFAULT_EPS = 1e-12
@@ -686,12 +686,25 @@ class VimureModel(TransformerMixin, BaseEstimator):
         return sptensor((l, j, i, m), self.X.vals, shape=self.X.shape)
 
     # ------------------------------------------------------------------ inferred model (model.py:1062-1214)
+    def _consume(self, what, *args):
+        """Run a posterior consumer (`infer`, `infer_mean`, `sample` of the engine) on the device slab that IS rho_f --
+        the best restart's own when the restarts ran side by side, the last restart's, or the device copy kept when an
+        earlier restart won -- and assemble the (L, N, N) result on the host: 1 byte (4 for rho_mean) per tie crosses
+        PCIe instead of an fp64 copy of rho.  On a sharded fit every rank consumes its row block and the blocks are
+        all-gathered (collective: every rank must call)."""
+        eng = getattr(self, "_engine_f", None) or self._engine
+        slab = None if (getattr(self, "_engine_f", None) is not None or self._rho_f_dev is None) else self._rho_f_dev
+        out = getattr(eng, what)(*args, slab=slab)
+        if self._world > 1:
+            parts = [torch.empty((self.L, shard_rows(self.N, self._world, r)[1], self.N), dtype=out.dtype, device=out.device)
+                     for r in range(self._world)]
+            torch.distributed.all_gather(parts, out.contiguous())
+            out = torch.cat(parts, dim=1)
+        return out.cpu().numpy()
+
     def _engine_of_rho_f(self):
-        """The engine whose device slab IS rho_f (the best restart's own when the restarts ran side by side, else the only /
-        last one unless an earlier restart won and rho_f is a copy), or None."""
-        if self._world != 1:
-            return None
-        return getattr(self, "_engine_f", None) or (self._engine if self._rho_f_dev is None else None)
+        """The engine whose consumers read rho_f (see `_consume`; pass `slab=self._rho_f_dev` when that is not None)."""
+        return getattr(self, "_engine_f", None) or self._engine
 
     def sample_inferred_model(self, N=1, seed=None, rng="auto"):
         """Sample Y trials from the rho distribution (reference model.py:1062-1096): a list of N arrays (L, N, N), each the
@@ -705,15 +718,10 @@ class VimureModel(TransformerMixin, BaseEstimator):
             seed = self.seed
         if rng not in ("auto", "numpy", "device"):
             raise ValueError("rng must be 'auto', 'numpy' or 'device'")
-        eng_f = self._engine_of_rho_f()
         if rng == "auto":
-            big = float(self.L) * self.N * self.N * self.K > AUTO_REFERENCE_INIT_LIMIT
-            rng = "device" if (big and eng_f is not None) else "numpy"
+            rng = "device" if float(self.L) * self.N * self.N * self.K > AUTO_REFERENCE_INIT_LIMIT else "numpy"
         if rng == "device":
-            if eng_f is None:
-                raise RuntimeError("rng='device' needs rho_f on this rank's device (single-rank fit whose best restart's "
-                                   "slab is still resident)")
-            return [eng_f.sample(N, int(seed) + i).cpu().numpy().astype("int") for i in range(0, N)]
+            return [self._consume("sample", N, int(seed) + i).astype("int") for i in range(0, N)]
 
         def sampleY(seed):
             pnrg = np.random.default_rng(seed)
@@ -724,7 +732,9 @@ class VimureModel(TransformerMixin, BaseEstimator):
         return [sampleY(seed + i) for i in range(0, N)]
 
     def get_inferred_model(self, method="rho_max", threshold=None):
-        """Estimate Y from rho_f: rho_max | rho_mean | fixed_threshold | heuristic_threshold (model.py:1099-1188)."""
+        """Estimate Y from rho_f: rho_max | rho_mean | fixed_threshold | heuristic_threshold (model.py:1099-1188).
+        Every method runs on the device slab (float32 storage: a posterior that sits within ~1e-7 of a threshold, or two
+        categories that tie to that precision, can come out differently from a float64 evaluation)."""
         OPTIONS = ["rho_max", "rho_mean", "fixed_threshold", "heuristic_threshold"]
         try:
             method = match_arg(method, OPTIONS)[0]
@@ -737,24 +747,16 @@ class VimureModel(TransformerMixin, BaseEstimator):
             warnings.warn(msg, UserWarning)
             method = "rho_max"
 
-        eng_f = self._engine_of_rho_f()
-        single = eng_f is not None
         if method == "rho_max":
-            if single:  # argmax on the device, 1 byte per tie back
-                return eng_f.infer(0).cpu().numpy().astype("int")
-            return np.argmax(self.rho_f, axis=-1).astype("int")
-        if method == "rho_mean":
-            return np.dot(self.rho_f, range(0, self.K))
+            return self._consume("infer", 0, 0.5).astype("int")
+        if method == "rho_mean":  # np.dot(rho_f, range(K)), model.py:1151-1153
+            return self._consume("infer_mean").astype(np.float64)
         if method == "fixed_threshold":
             if (threshold is None) or (threshold > 1) or (threshold < 0):
                 raise ValueError('For method="fixed_threshold", you must set the threshold to a value in [0,1].')
-            if single:
-                return eng_f.infer(1, threshold).cpu().numpy().astype(np.float64)
-            Y = np.copy(self.rho_f[:, :, :, 1])
-            Y[Y < threshold] = 0
-            Y[Y >= threshold] = 1
-            return Y
-        return apply_rho_threshold(self).astype("int")
+            return self._consume("infer", 1, float(threshold)).astype(np.float64)
+        # heuristic_threshold: 0.54 * G_exp_nu - 0.01 (utils.py:200-204; reads G_exp_nu, not G_exp_nu_f)
+        return self._consume("infer", 1, float(get_optimal_threshold(self))).astype("int")
 
     def get_posterior_estimates(self):
         """Posterior estimates nu, theta, lambda, rho (reference model.py:1191-1214)."""
