@@ -310,6 +310,51 @@ int vm_infer_mean(const vm_ctx* c, float* out, void* stream);
  * not numpy's (the reference draws with numpy.random.default_rng(seed)). */
 int vm_sample(const vm_ctx* c, int64_t n_trials, uint64_t seed, uint8_t* out, void* stream);
 
+/* ---- data packing (replaces the data preparation of `__check_fit_params`, model.py:147-176, and utils.py:73-84) --------
+ * From the COO list of reports (device arrays) to every packed array `vm_ctx` points to, for one node-row block and a
+ * structured reporter mask (VM_R_EGO / VM_R_ALL; a general COO mask is packed by the host-side packer): entries outside
+ * the block's needs are dropped, ONE radix sort by (l,i,j,m) puts the reports in tie order, a binary search pairs each
+ * with its reciprocal X[l,j,i,m], head flags + prefix sums give the special ties (+ the diagonal ties of an ego mask),
+ * their dense-tile pointers, classes (shortcut / not), the E0/E1 split, the reporter-sorted copies and chunk tables of
+ * the gamma pass and the transposed-position list of the ELBO.  No host synchronisation inside; the caller allocates
+ * every output by the upper bounds below and reads `counts` (device int64[16]) once the stream has drained:
+ *   counts[0..8] = U, I, I1, IT, n_cx, n_gchunk, max special ties per layer, max E1 entries per layer, max cx per layer
+ *   counts[9] != 0: duplicate entries; counts[10] != 0: subscripts outside the shape;
+ *   counts[11] = sum of the counts of the owned entries; counts[12] = b_all (integer).
+ * Capacities: cap_e >= n_in; cap_u >= n_in + L*nloc (ego) ; cap_g >= n_in/256 + L*M + 1. */
+typedef struct vm_pack_args {
+  int64_t L, N, M, K, row0, nloc, tile_h;
+  int64_t r_mode, ego_diag;  /* VM_R_EGO / VM_R_ALL; EGO: the mask contains the (m,m) ties */
+  int64_t mutuality, split_e0;
+  int64_t simple, single;    /* classify SIMPLE / SINGLE shortcut ties (see vm_ctx.simple_mode) */
+  int64_t n_in;              /* reports given */
+  const int32_t* x_l; const int32_t* x_i; const int32_t* x_j; const int32_t* x_m; const int32_t* x_v;
+  const uint8_t* rep;        /* EGO: [L*M] reporter is active */
+  int64_t cap_e, cap_u, cap_g;
+  int32_t* e_u; int32_t* e_m; float* e_x; float* e_xT; uint8_t* e_flags;
+  int32_t* f_u; int32_t* f_m; float* f_x; float* f_xT;
+  int32_t* g_u; float* g_x; float* g_xT;
+  int32_t* u_lrow; int32_t* u_col; int32_t* u_cnt; int32_t* u_m0;
+  float* u_x0; float* u_xT0; float* u_x0sum; float* u_px; float* u_pxt;
+  int64_t* u_ptr;            /* [cap_u+1] */
+  uint8_t* u_has_x; uint8_t* u_reported;
+  int64_t* u_gflat;          /* [cap_u] global flat id (l*N+i)*N+j of the tie (for injecting a prior keyed by tie) */
+  int32_t* utile_ptr;        /* [L*nloc*nct+1] */
+  int32_t* cx_idx; int64_t* cx_ptr; int32_t* cx_lrow; int32_t* cx_col; int32_t* cx_cnt; int32_t* cx_m0;
+  float* cx_x0; float* cx_xT0; float* cx_x0sum;
+  int64_t* lay_eptr;         /* [L+1] */
+  double* g0;                /* [L*M] */
+  int64_t* g_chunk_ptr;      /* [cap_g+1] */
+  int32_t* g_chunk_lm;       /* [cap_g] */
+  int64_t* g_lm_cptr;        /* [L*M+1] */
+  int32_t* t_u; int32_t* t_lrow; int32_t* t_col; float* t_x;
+  int64_t* counts;           /* [16] device */
+  void* workspace; int64_t workspace_bytes;
+} vm_pack_args;
+int64_t vm_pack_size(void);
+int64_t vm_pack_workspace_bytes(const vm_pack_args* p);
+int vm_pack(const vm_pack_args* p, void* stream);
+
 /* ---- device-side synthetic reports (the "next" row f2 of SURVEY.md section 8) ----------------------------------------
  * Samples the observed network X of the reference's `_build_X` under the self-reporter (ego) mask
  * (synthetic.py:138-209; mask synthetic.py:1184-1204) for ONE node-row block [row0, row0+nloc), sparsely, with a

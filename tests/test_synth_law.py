@@ -111,3 +111,41 @@ def test_device_generator_shards_agree_with_the_whole():
             ks = key(s)
             os_ = np.argsort(ks)
             assert np.array_equal(ks[os_], k_all[own]) and np.array_equal(v.cpu().numpy()[os_], v_all[own])
+
+
+@pytest.mark.gpu
+def test_posterior_synthetic_network_from_a_fitted_model():
+    """`PosteriorSyntheticNetwork` (reference synthetic.py:964-1177): Y from rho_f, reports from the posterior Gammas."""
+    import warnings
+
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import vimure_b200 as vm
+    import vimure_b200.synthetic as syn
+
+    net = syn.Multitensor(N=120, L=2, K=2, C=2, avg_degree=8, eta=0.3, seed=3).build_X(mutuality=0.3, seed=4)
+    model = vm.VimureModel(mutuality=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model.fit(net.X, R=net.R, K=2, seed=5, max_iter=21)
+    ps = syn.PosteriorSyntheticNetwork(model, seed_Y=11).build_Y()
+    # numpy stream for a small problem: exactly the reference's draw
+    pv = model.rho_f / model.rho_f.sum(axis=-1, keepdims=True)
+    ref_Y = np.random.default_rng(11).multinomial(n=1, pvals=pv, size=(2, 120, 120)).argmax(axis=-1)
+    assert np.array_equal(ps.Y.toarray(), ref_Y)
+    ps.build_X(seed_X=7)
+    prng = np.random.RandomState(7)
+    np.testing.assert_allclose(ps.theta, prng.gamma(shape=model.gamma_shp_f, scale=1.0 / model.gamma_rte_f, size=(2, 120)))
+    assert ps.X.shape == (2, 120, 120, 120) and len(ps.X.vals) > 0 and ps.X.vals.min() >= 1
+    l, i, j, m = ps.X.subs
+    assert np.all((m == i) | (m == j))  # self-reporter mask
+    # reporters see their true ties far more often than their non-ties
+    Yd = ps.Y.toarray() > 0
+    hit = Yd[l, i, j].mean()
+    assert hit > 5 * Yd.mean()
+    assert ps.X_union.shape == (2, 120, 120) and len(ps.X_intersection.vals) <= len(ps.X_union.vals)
+    # the device stream for Y agrees in law: same marginal frequency of ties
+    psd = syn.PosteriorSyntheticNetwork(model, seed_Y=11).build_Y(rng="device")
+    assert abs(len(psd.Y_vals) - len(ps.Y_vals)) < 6 * np.sqrt(len(ps.Y_vals)) + 10

@@ -86,23 +86,26 @@ __global__ void __launch_bounds__(256) k_gamma_partial(const __grid_constant__ v
   for (int k = 0; k < K; ++k) Gl[k] = c.G_lambda[l * K + k];
   double acc = 0.0;
   const int64_t p1 = c.g_chunk_ptr[chunk + 1];
-  // a chunk holds <= 256 entries = 8 per lane: two rounds of 4 independent gathers
-  for (int64_t pb = c.g_chunk_ptr[chunk] + lane; pb < p1; pb += 128) {
-    int64_t u[4];
-    float x[4], xT[4];
+  // a chunk holds <= 256 entries = 8 per lane: rounds of NQ independent gathers.  NQ = 1 for K > 8: with 4 entries in
+  // flight nvcc 12.9 generated a kernel for K = 12 that faulted ("misaligned address" with every access naturally
+  // aligned: a clobbered return address of the fp64 reciprocal's out-of-line slow path) -- see also vm_rcp64.
+  constexpr int NQ = (K <= 8) ? 4 : 1;
+  for (int64_t pb = c.g_chunk_ptr[chunk] + lane; pb < p1; pb += 32 * NQ) {
+    int64_t u[NQ];
+    float x[NQ], xT[NQ];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const int64_t p = pb + 32 * q;
       const bool ok = p < p1;
       u[q] = ok ? (int64_t)c.g_u[p] : 0;
       x[q] = ok ? c.g_x[p] : 0.f;
       xT[q] = ok ? c.g_xT[p] : 0.f;
     }
-    float r[4][K];  // the fp32 posterior of the tie (8 bytes at K=2: half the gather of the fp64 copy)
+    float r[NQ][K];  // the fp32 posterior of the tie (8 bytes at K=2: half the gather of the fp64 copy)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) vm_load_rho32<K>(c.rho_u32 + u[q] * K, r[q]);
+    for (int q = 0; q < NQ; ++q) vm_load_rho32<K>(c.rho_u32 + u[q] * K, r[q]);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       double dz1[K], dz2[K];
       vm_alloc<K>(mut, (double)x[q], (double)xT[q], Gth, Gl, Gnu, dz1, dz2);  // x == 0 for padding lanes
 #pragma unroll
@@ -214,12 +217,13 @@ __global__ void __launch_bounds__(256) k_phi_partial(const __grid_constant__ vm_
     Gl[k] = c.G_lambda[l * K + k];
     acc[k] = 0.0;
   }
-  for (int64_t eb = s0 + threadIdx.x; eb < s1; eb += 1024) {
-    int64_t u[4];
-    int m[4];
-    float x[4], xT[4];
+  constexpr int NQ = (K <= 8) ? 4 : 1;  // (see k_gamma_partial)
+  for (int64_t eb = s0 + threadIdx.x; eb < s1; eb += 256 * NQ) {
+    int64_t u[NQ];
+    int m[NQ];
+    float x[NQ], xT[NQ];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const int64_t e = eb + 256 * q;
       const bool ok = e < s1;
       u[q] = ok ? (int64_t)c.f_u[e] : 0;
@@ -227,15 +231,15 @@ __global__ void __launch_bounds__(256) k_phi_partial(const __grid_constant__ vm_
       x[q] = ok ? c.f_x[e] : 0.f;
       xT[q] = ok ? c.f_xT[e] : 0.f;
     }
-    float r[4][K];
-    double Gth[4];
+    float r[NQ][K];
+    double Gth[NQ];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       Gth[q] = c.G_theta[(int64_t)l * c.M + m[q]];
       vm_load_rho32<K>(c.rho_u32 + u[q] * K, r[q]);
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       double dz1[K], dz2[K];
       vm_alloc<K>(mut, (double)x[q], (double)xT[q], Gth[q], Gl, Gnu, dz1, dz2);  // x == 0 for padding
 #pragma unroll

@@ -221,52 +221,128 @@ class SparseSyntheticNetwork:
         with `emit_transposed`, the reciprocal entries X[l,j,i,m] whose row the block does not own (so that the shard can
         be paired without an exchange).  Every rank that evaluates an entry gets the same value, whatever its block.
         Also sets self.theta, self.R, self.mutuality (not self.X: use `sptensor(tuple(subs.cpu()), vals.cpu(), ...)`)."""
-        import ctypes
-
-        import torch
-
-        from . import _capi
-
-        N, M, L = self.N, self.M, self.L
-        nloc = N - row0 if nloc is None else int(nloc)
         sd = self.seed if seed is None else seed
         eta = float(mutuality)
         if eta < 0 or eta >= 1:
             raise ValueError("The mutuality parameter has to be in [0, 1)!")
         if theta is None:
-            theta = np.random.RandomState(sd).gamma(shape=sh_theta, scale=sc_theta, size=(L, M))
+            theta = np.random.RandomState(sd).gamma(shape=sh_theta, scale=sc_theta, size=(self.L, self.M))
         self.theta = theta
-        dev = torch.device(device)
-        if dev.type != "cuda":
-            raise RuntimeError("build_X_device needs a CUDA device (host counterpart: build_X)")
-        lib = _capi.load()
-        ykey = (self.Y_subs[0] * N + self.Y_subs[1]) * N + self.Y_subs[2]
-        o = np.argsort(ykey, kind="stable")
-        yk = torch.from_numpy(np.ascontiguousarray(ykey[o])).to(dev)
-        yv = torch.from_numpy(np.ascontiguousarray(self.Y_vals[o]).astype(np.int32)).to(dev)
-        th = torch.from_numpy(np.ascontiguousarray(theta, dtype=np.float64)).to(dev)
-        counter = torch.zeros(1, dtype=torch.int64, device=dev)
-        S = _capi.synth_class()()
-        S.L, S.N, S.M, S.K, S.row0, S.nloc = L, N, M, self.K, int(row0), nloc
-        S.emit_transposed = int(bool(emit_transposed))
-        S.seed = int(sd) & (2**64 - 1)
-        S.eta = eta
-        S.theta, S.y_key, S.y_val, S.nY = th.data_ptr(), yk.data_ptr(), yv.data_ptr(), int(yk.numel())
-        S.counter = counter.data_ptr()
-        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        # pass 1 counts (cap = 0: nothing is stored), pass 2 fills arrays of exactly that size
-        S.cap = 0
-        _capi.check(lib.vm_synth_ego(ctypes.byref(S), stream), "vm_synth_ego (count)")
-        n = int(counter.item())
-        out = torch.empty((5, max(n, 1)), dtype=torch.int32, device=dev)
-        S.cap = n
-        S.o_l, S.o_i, S.o_j, S.o_m, S.o_x = (out[d].data_ptr() for d in range(5))
-        _capi.check(lib.vm_synth_ego(ctypes.byref(S), stream), "vm_synth_ego (fill)")
-        if int(counter.item()) != n:
-            raise RuntimeError("vm_synth_ego: the two passes disagree (%d vs %d entries)" % (int(counter.item()), n))
-        self.R = EgoMask(L, N, M, diag=True)
+        subs, vals = device_reports(self.L, self.N, self.M, self.K, self.Y_subs, self.Y_vals, theta, eta, sd, device=device,
+                                    row0=row0, nloc=nloc, emit_transposed=emit_transposed)
+        self.R = EgoMask(self.L, self.N, self.M, diag=True)
         self.mutuality = eta
-        return out[:4, :n], out[4, :n]
+        return subs, vals
+
+
+def device_reports(L, N, M, K, Y_subs, Y_vals, theta, eta, seed, lam=None, device="cuda", row0=0, nloc=None,
+                   emit_transposed=False):
+    """Reports X under the self-reporter mask for a given ground truth Y (COO), reliabilities theta (L, M), mutuality eta
+    and, optionally, a table lam (L, K) of average interactions per ground-truth category (default: 0.01, 1, 2, ..) --
+    sampled on the device by `vm_synth_ego` (include/vimure_b200.h).  Returns int32 device tensors (subs (4, n), vals (n,))."""
+    import ctypes
+
+    import torch
+
+    from . import _capi
+
+    nloc = N - row0 if nloc is None else int(nloc)
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("device_reports needs a CUDA device (host counterpart: SparseSyntheticNetwork.build_X)")
+    lib = _capi.load()
+    Y_subs = np.asarray(Y_subs).astype(np.int64)
+    ykey = (Y_subs[0] * N + Y_subs[1]) * N + Y_subs[2]
+    o = np.argsort(ykey, kind="stable")
+    yk = torch.from_numpy(np.ascontiguousarray(ykey[o])).to(dev)
+    yv = torch.from_numpy(np.ascontiguousarray(np.asarray(Y_vals)[o]).astype(np.int32)).to(dev)
+    th = torch.from_numpy(np.ascontiguousarray(theta, dtype=np.float64)).to(dev)
+    lam_t = None if lam is None else torch.from_numpy(np.ascontiguousarray(lam, dtype=np.float64).reshape(L, K)).to(dev)
+    counter = torch.zeros(1, dtype=torch.int64, device=dev)
+    S = _capi.synth_class()()
+    S.L, S.N, S.M, S.K, S.row0, S.nloc = int(L), int(N), int(M), int(K), int(row0), nloc
+    S.emit_transposed = int(bool(emit_transposed))
+    S.seed = int(seed) & (2**64 - 1)
+    S.eta = float(eta)
+    S.theta, S.y_key, S.y_val, S.nY = th.data_ptr(), yk.data_ptr(), yv.data_ptr(), int(yk.numel())
+    S.lam = None if lam_t is None else lam_t.data_ptr()
+    S.counter = counter.data_ptr()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    # pass 1 counts (cap = 0: nothing is stored), pass 2 fills arrays of exactly that size
+    S.cap = 0
+    _capi.check(lib.vm_synth_ego(ctypes.byref(S), stream), "vm_synth_ego (count)")
+    n = int(counter.item())
+    out = torch.empty((5, max(n, 1)), dtype=torch.int32, device=dev)
+    S.cap = n
+    S.o_l, S.o_i, S.o_j, S.o_m, S.o_x = (out[d].data_ptr() for d in range(5))
+    _capi.check(lib.vm_synth_ego(ctypes.byref(S), stream), "vm_synth_ego (fill)")
+    if int(counter.item()) != n:
+        raise RuntimeError("vm_synth_ego: the two passes disagree (%d vs %d entries)" % (int(counter.item()), n))
+    return out[:4, :n], out[4, :n]
+
+
+class PosteriorSyntheticNetwork:
+    """Generates data (Y, X) from the posterior estimates of a fitted model: the counterpart of the reference's
+    `vimure.synthetic.PosteriorSyntheticNetwork` (synthetic.py:964-1177) for the self-reporter mask, without an fp64 host
+    copy of rho and without dense (L,N,N,M) arrays.
+
+    build_Y : Y_lij ~ Categorical(rho_f[l,i,j,:]) (one draw; `model.sample_inferred_model(N=1, seed=seed_Y)`: numpy's
+              stream like the reference for small problems, the device kernel for large ones).
+    build_X : theta ~ Gamma(gamma_shp_f, 1/gamma_rte_f), lambda ~ Gamma(phi_shp_f, 1/phi_rte_f), eta ~ Gamma(nu_shp_f,
+              1/nu_rte_f) drawn with RandomState(seed_X) in the reference's order (synthetic.py:1040-1042); a tie of
+              category k >= 1 gets lambda[l,k], every other tie lambda[0,0] (synthetic.py:1044-1048); the reports follow
+              `_build_X`'s law (synthetic.py:1063-1098), sampled by the device generator.  Also the union / intersection
+              baselines (synthetic.py:1139-1172)."""
+
+    def __init__(self, model, seed_Y):
+        self.model, self.seed_Y = model, seed_Y
+        self.theta_shp, self.theta_rte = model.gamma_shp_f, model.gamma_rte_f
+        self.lambda_shp, self.lambda_rte = model.phi_shp_f, model.phi_rte_f
+        self.mutuality_shp, self.mutuality_rte = model.nu_shp_f, model.nu_rte_f
+        self.L, self.N, self.K = model.L, model.N, model.K
+        self.M = self.theta_shp.shape[1]
+
+    def build_Y(self, rng="auto"):
+        Y = np.asarray(self.model.sample_inferred_model(N=1, seed=self.seed_Y, rng=rng)[0])
+        Y = np.minimum(Y, self.K - 1)
+        subs = np.nonzero(Y)
+        self.Y_subs = np.stack(subs).astype(np.int64)
+        self.Y_vals = Y[subs].astype(np.int64)
+        self.Y = sptensor(tuple(self.Y_subs), self.Y_vals, shape=(self.L, self.N, self.N))
+        return self
+
+    def build_X(self, Rinput=None, flag_self_reporter=True, cutoff_X=False, Q=None, seed_X=None, device="cuda"):
+        if Rinput is not None or not flag_self_reporter:
+            raise NotImplementedError("vimure_b200.PosteriorSyntheticNetwork samples under the self-reporter mask only")
+        for nm in ("theta_rte", "lambda_rte", "mutuality_rte"):
+            if np.any(np.asarray(getattr(self, nm)) == 0):
+                raise ValueError(nm + " has some zero entries!")
+        if seed_X is None:
+            seed_X = 90
+        self.seed_X = seed_X
+        prng = np.random.RandomState(seed_X)
+        theta = prng.gamma(shape=self.theta_shp, scale=1.0 / self.theta_rte, size=(self.L, self.M))
+        lambda_k = prng.gamma(shape=self.lambda_shp, scale=1.0 / self.lambda_rte, size=(self.L, self.K))
+        mutuality = prng.gamma(shape=self.mutuality_shp, scale=1.0 / self.mutuality_rte, size=1)[0]
+        if not (0.0 <= mutuality < 1.0):
+            raise ValueError("the drawn mutuality (%g) is outside [0, 1)" % mutuality)
+        lam = np.array(lambda_k, dtype=np.float64)
+        lam[:, 0] = lambda_k[0, 0]  # every tie without a positive category gets lambda_k[0, 0] (synthetic.py:1044)
+        subs, vals = device_reports(self.L, self.N, self.M, self.K, self.Y_subs, self.Y_vals, theta, mutuality, seed_X, lam=lam,
+                                    device=device)
+        subs, vals = subs.cpu().numpy().astype(np.int64), vals.cpu().numpy().astype(np.int64)
+        if cutoff_X:
+            vals = np.minimum(vals, (self.K if Q is None else Q) - 1)
+        self.X = sptensor(tuple(subs), vals, shape=(self.L, self.N, self.N, self.M))
+        self.R = EgoMask(self.L, self.N, self.M, diag=True)
+        self.theta, self.lambda_k, self.mutuality = theta, lambda_k, mutuality
+        # baselines (synthetic.py:1139-1172): ties reported by anybody / by exactly two reports
+        ties, cnt = np.unique(subs[:3].T, axis=0, return_counts=True)
+        shape3 = (self.L, self.N, self.N)
+        self.X_union = sptensor(tuple(ties.T), np.ones(len(ties), dtype=np.int8), shape=shape3)
+        inter = ties[cnt == 2]
+        self.X_intersection = sptensor(tuple(inter.T), np.ones(len(inter), dtype=np.int8), shape=shape3)
+        return self
 
 
 def StandardSBM(N=100, M=None, L=1, K=2, C=2, avg_degree=2.0, structure="assortative", seed=10):
