@@ -60,3 +60,42 @@ print("slab max diff", np.abs(a["slab"] - b["slab"]).max())
 print("phi0", a["phi0"], b["phi0"], "fixP", a["fixP"] / 2.0**30)
 nt = a["nodetab"].reshape(N, 4)
 print("nodetab[:3]", nt[:3], "act sum", nt[:, 3].sum())
+
+# ---- several full iterations, single engine: shortcut vs fp64 path
+print("---- multi-iteration")
+engs = {}
+for mode in ("short", "fp64"):
+    if mode == "fp64":
+        os.environ["VM_NO_SIMPLE"] = "1"
+    P = _packing.pack(net.X.subs, net.X.vals, L, N, N, K, net.R, "cuda", tile_h=32)
+    os.environ.pop("VM_NO_SIMPLE", None)
+    eng = CaviEngine(P, PRI, mutuality=True, eps=1e-12)
+    rs = np.random.RandomState(3).random_sample
+    st = dict(gamma_shp=0.1 * rs((L, N)) + 0.1, phi_shp=10.0 * rs((L, K)) + 10.0, gamma_rte=0.1 * rs((L, N)) + 0.1,
+              phi_rte=10.0 * rs((L, K)) + 10.0, nu_shp=0.5 * rs(1)[0] + 0.5)
+    keep = (P.t["u_has_x"] & P.t["u_reported"]).cpu().numpy()
+    pr_u = np.zeros((P.U, K))
+    pr_u[:, 0] = 1.0
+    pr = 1 + 0.01 * rs((int(keep.sum()), K))
+    pr_u[keep] = pr / pr.sum(axis=1)[:, None]
+    eng.set_state(st["gamma_shp"], st["gamma_rte"], st["phi_shp"], st["phi_rte"], st["nu_shp"],
+                  1.0 + float(net.X.vals.sum()), pr_u, 1e-12)
+    engs[mode] = eng
+for it in range(4):
+    out = {}
+    for mode, eng in engs.items():
+        eng.iterate(1)
+        torch.cuda.synchronize()
+        out[mode] = (eng.params(), eng.red3.cpu().numpy().copy(), eng.fixA.cpu().numpy().copy(), eng.dev_flags.cpu().numpy().copy(),
+                     eng.layer_consts.cpu().numpy().copy())
+    pa, pb = out["short"][0], out["fp64"][0]
+    msg = []
+    for k in ("gamma_shp", "gamma_rte", "phi_shp", "phi_rte", "nu_shp"):
+        x, y = np.asarray(pa[k]), np.asarray(pb[k])
+        msg.append("%s %.2e" % (k, float(np.max(np.abs(x - y) / np.abs(y)))))
+    A0, A1 = out["short"][1][:N * K].reshape(N, K), out["fp64"][1][:N * K].reshape(N, K)
+    badA = np.nonzero(np.abs(A0 - A1).max(axis=1) > 1e-6 * np.abs(A1).max(axis=1))[0]
+    print("it", it, " ".join(msg), "| A bad reporters", len(badA), badA[:8], "extras", out["short"][1][N * K:], out["fp64"][1][N * K:],
+          "flags", out["short"][3][:2], "simple flag", out["short"][4][2 * K + 4])
+    if len(badA):
+        print("   A short", A0[badA[:3]], "A fp64", A1[badA[:3]])

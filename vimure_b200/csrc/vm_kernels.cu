@@ -1447,22 +1447,32 @@ __global__ void __launch_bounds__(VM_SC_THREADS) k_shortcut(const __grid_constan
       f[k] = single ? z1 * iden[k] : 1.f;
     }
     const float t0 = z2 * g * iden[0];
-    float s = 0.f, sf = 0.f, es[K], ef[K];
+    // log2-odds against k = 0, then a softmax with the maximum subtracted: for K >= 3 the odds of two categories can both
+    // be astronomically large (a tie with a count of 20: 2^140) and only their RATIO matters -- clamping them (as the
+    // closed form may, its odds being ~2^-40) would flatten it
+    float a[K], amax = 0.f, sf = 0.f, ef[K];
 #pragma unroll
     for (int k = 1; k < K; ++k) {
       const float dat = single ? X * ((t0 * iden[k] * s_lam[K + k]) * el + (f[k] * s_lam[2 * K + k] - f[0] * s_lam[2 * K]))
                                : X * s_lam[3 * K + 1 + k];
       const float qk = nj[k - 1];
-      es[k] = vm_ex2(fminf(ni[k - 1] + qk + c.u_lo[u * (K - 1) + (k - 1)] + dat, VM_CLAMP_LOG2));
-      s += es[k];
+      a[k] = ni[k - 1] + qk + c.u_lo[u * (K - 1) + (k - 1)] + dat;
+      amax = fmaxf(amax, a[k]);
       // the closed form the dense sweep counts for this tie: same operations, same bits (qk == tab_q[l,j,k])
       ef[k] = vm_ex2(fminf(__fadd_rn(s_tabp[r][k - 1], qk), VM_CLAMP_LOG2));
       sf = (k == 1) ? ef[k] : __fadd_rn(sf, ef[k]);
     }
-    const float inv = vm_rcp(1.f + s), invf = vm_rcp(__fadd_rn(1.f, sf));
+    float es[K], s = vm_ex2(-amax);
+    es[0] = s;
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+      es[k] = vm_ex2(a[k] - amax);
+      s += es[k];
+    }
+    const float inv = vm_rcp(s), invf = vm_rcp(__fadd_rn(1.f, sf));
     float rho[K];
-    rho[0] = inv;
-    float nu_t = inv * iden[0];
+    rho[0] = es[0] * inv;
+    float nu_t = rho[0] * iden[0];
     const bool act_i = ni[K + 1] != 0.f, act_j = nj[K + 1] != 0.f;
 #pragma unroll
     for (int k = 1; k < K; ++k) {
