@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VM_ABI_VERSION 12
+#define VM_ABI_VERSION 13
 
 /* reporter-mask structure (how R[l,i,j,m] is represented) */
 #define VM_R_EGO 0 /* reporter m == node m reports row m and column m (vimure synthetic.py:1184-1204, _io.py:229-242) */
@@ -117,8 +117,6 @@ typedef struct vm_ctx {
   const float* u_x0;        /* [U]   the special-tie kernel needs no dependent load for single-entry ties */
   const float* u_xT0;       /* [U] */
   const int32_t* utile_ptr; /* [L*nloc*nct+1] first special tie of each (lrow, column tile) */
-  const int64_t* ucol_ptr;  /* [L*N+1] EGO: special ties grouped by (l, col) */
-  const int32_t* ucol_perm; /* [U] */
 
   /* ---- shortcut ties: special ties whose posterior needs neither fp64 nor the entry list ----
      Ego mask, K <= 4, off the diagonal, in a full column tile, and either
@@ -157,7 +155,9 @@ typedef struct vm_ctx {
   const float* u_px;        /* [U] X of a shortcut tie (sum of its x; the one report's x for a SINGLE tie), 0 = no shortcut */
   const float* u_pxt;       /* [U] 0 for a SIMPLE tie; SINGLE: +x^T if the entry's reporter is the row node, -x^T if it is
                                the column node */
-  const float* u_lo;        /* [U*(K-1)] lo_k = log2((pr_k+EPS)/(pr_0+EPS)), k >= 1 (constant over a fit) */
+  const float* u_rec;       /* [U*RS] one record per special tie for the shortcut kernel, RS = 4 floats at K = 2, 8 at K = 3, 4:
+                               (col as a float, u_px, u_pxt, lo_1..lo_{K-1}, padding), lo_k = log2((pr_k+EPS)/(pr_0+EPS))
+                               -- constant over a fit (built by the host from u_col / u_px / u_pxt and the prior) */
   float* nodetab;           /* [L*N*stride] per node: q_1..q_{K-1} (= -E[theta] d_k), G_theta, E[log theta] log2e, active;
                                stride = 4 floats at K = 2, 8 at K = 3, 4 (written by k_tables) */
   const double* simple_consts; /* [3] over the shortcut ties: min log(pr_0+EPS); max X; max x^T */
@@ -332,6 +332,7 @@ typedef struct vm_pack_args {
   const uint8_t* rep;        /* EGO: [L*M] reporter is active */
   int64_t cap_e, cap_u, cap_g;
   int32_t* e_u; int32_t* e_m; float* e_x; float* e_xT; uint8_t* e_flags;
+  int32_t* e_src;            /* [cap_e] position of the owned entry in the caller's list */
   int32_t* f_u; int32_t* f_m; float* f_x; float* f_xT;
   int32_t* g_u; float* g_x; float* g_xT;
   int32_t* u_lrow; int32_t* u_col; int32_t* u_cnt; int32_t* u_m0;

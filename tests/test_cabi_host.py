@@ -167,10 +167,6 @@ def test_packing_invariants(name, world):
             assert np.all(lm1[gp[cp[c]:cp[c + 1]]] == clm[c])
             assert 0 < cp[c + 1] - cp[c] <= _packing.GAMMA_CHUNK
         assert np.array_equal(t["g_u"], t["f_u"][gp])
-        # column grouping
-        cperm, cptr = t["ucol_perm"], t["ucol_ptr"]
-        ck = (t["u_lrow"] // nloc).astype(np.int64) * g.N + t["u_col"]
-        assert np.all(np.diff(ck[cperm]) >= 0) and cptr[-1] == P.U
     assert tot_I == len(g.X_vals)
     if g.mutuality:
         l, i, j, m = g.X_subs

@@ -357,4 +357,6 @@ def test_simple_special_ties_sharded_rows():
             if fl:
                 np.testing.assert_allclose(e.elbo(), one.elbo(), rtol=1e-8)
     slab = torch.cat([e.rho_slab() for e in engs], dim=1)
-    np.testing.assert_allclose(slab.cpu().numpy(), one.rho_slab().cpu().numpy(), rtol=1e-6, atol=1e-30)
+    # (the shards' parameters differ from the single rank's by reduction order, ~1e-8; a shortcut tie's fp32 posterior then
+    # differs by a few ulp)
+    np.testing.assert_allclose(slab.cpu().numpy(), one.rho_slab().cpu().numpy(), rtol=5e-6, atol=1e-30)

@@ -52,6 +52,20 @@ def _parse_header():
 
 
 _synth_cls = None
+_pack_cls = None
+
+
+def pack_class():
+    """ctypes mirror of `vm_pack_args` (device-side packer), generated from the header."""
+    global _pack_cls
+    if _pack_cls is None:
+        fields = _parse_struct(open(HEADER).read(), "vm_pack_args")
+
+        class VmPackArgs(ctypes.Structure):
+            _fields_ = fields
+
+        _pack_cls = VmPackArgs
+    return _pack_cls
 
 
 def synth_class():
@@ -128,6 +142,9 @@ def open_library(path):
         "vm_sample": (i, [P, i64, ctypes.c_uint64, vp, vp]),
         "vm_infer_mean": (i, [P, vp, vp]),
         "vm_test_special": (i, [vp, vp, vp, i64, vp]),
+        "vm_pack_size": (i64, []),
+        "vm_pack_workspace_bytes": (i64, [ctypes.POINTER(pack_class())]),
+        "vm_pack": (i, [ctypes.POINTER(pack_class()), vp]),
         "vm_synth_size": (i64, []),
         "vm_synth_ego": (i, [ctypes.POINTER(synth_class()), vp]),
     }
@@ -138,6 +155,8 @@ def open_library(path):
     if lib.vm_ctx_size() != ctypes.sizeof(Ctx):
         raise RuntimeError("vm_ctx layout mismatch: library %d bytes, python mirror %d bytes (stale build?)"
                            % (lib.vm_ctx_size(), ctypes.sizeof(Ctx)))
+    if lib.vm_pack_size() != ctypes.sizeof(pack_class()):
+        raise RuntimeError("vm_pack_args layout mismatch between header and library (stale build?)")
     if lib.vm_synth_size() != ctypes.sizeof(synth_class()):
         raise RuntimeError("vm_synth layout mismatch between header and library (stale build?)")
     if lib.vm_abi_version() != consts()["VM_ABI_VERSION"]:

@@ -15,7 +15,7 @@ from . import _capi
 
 
 def _packing_const():
-    from ._packing import SPECIAL_TIES_PER_BLOCK
+    from ._pack_native import SPECIAL_TIES_PER_BLOCK
 
     return SPECIAL_TIES_PER_BLOCK
 
@@ -77,7 +77,7 @@ class CaviEngine:
         self.phi0 = z(L * K)
         # simple special ties (see include/vimure_b200.h): patch source of the fast dense kernel, their phi0 part
         self.simple_mode = bool(getattr(P, "simple_ok", False)) and not overlap
-        self.u_lo = torch.zeros(max(U, 1), K - 1, **f32)
+        self.u_rec = torch.zeros(max(U, 1) if self.simple_mode else 1, 4 if K == 2 else 8, **f32)
         stride = 4 if K == 2 else (8 if K <= 6 else K + 2)
         self.nodetab = torch.zeros(L * N * stride if self.simple_mode else 4, **f32)
         self.fixP = torch.zeros(L * K, dtype=torch.int64, device=dev)
@@ -135,7 +135,7 @@ class CaviEngine:
             self._keep.append(t)
             return t.data_ptr() if t.numel() else self._dummy.data_ptr()
 
-        for name in ("u_lrow", "u_col", "u_ptr", "u_cnt", "u_m0", "u_x0", "u_xT0", "utile_ptr", "ucol_ptr", "ucol_perm", "e_u", "e_m", "e_x", "e_xT",
+        for name in ("u_lrow", "u_col", "u_ptr", "u_cnt", "u_m0", "u_x0", "u_xT0", "utile_ptr", "e_u", "e_m", "e_x", "e_xT",
                      "e_flags", "f_u", "f_m", "f_x", "f_xT", "lay_eptr", "g0", "u_x0sum", "sp_chunk_blk", "g_chunk_ptr", "g_chunk_lm", "g_u", "g_x", "g_xT", "g_lm_cptr", "t_u", "t_lrow",
                      "t_col", "t_x", "rep", "r_ptr", "r_m", "r_val", "c_ptr", "c_tie", "cx_idx", "cx_ptr", "cx_lrow", "cx_col", "cx_cnt",
                      "cx_m0", "cx_x0", "cx_xT0", "cx_x0sum", "u_px", "u_pxt"):
@@ -144,7 +144,7 @@ class CaviEngine:
                      "phi_shp", "phi_rte", "nu", "G_theta", "E_theta", "Elog_theta", "G_lambda", "E_lambda",
                      "Elog_lambda", "GE_theta", "rho_u", "rho_u32", "delta_u", "rho", "layer_consts", "tab_p", "tab_q",
                      "rowpart", "colpart", "er_node", "colsum", "dev_flags", "fixA", "fixG", "phi0", "blkpart", "red1", "red2", "red3",
-                     "elbo_out", "u_lo", "nodetab", "fixP", "simple_consts", "cx_logpr", "gfpart"):
+                     "elbo_out", "u_rec", "nodetab", "fixP", "simple_consts", "cx_logpr", "gfpart"):
             setattr(c, name, ptr(getattr(self, name)))
         c.A = self.red3.data_ptr()  # A aliases the (all-reduced) statistics vector
         c.ev_fork, c.ev_join = self._ev_fork.cuda_event, self._ev_join.cuda_event
@@ -202,7 +202,12 @@ class CaviEngine:
                 lp = self.u_logpr
                 if P.n_cx:
                     torch.index_select(lp, 0, P.t["cx_idx"].to(torch.int64), out=self.cx_logpr)
-                self.u_lo.copy_(((lp[:, 1:] - lp[:, :1]) * 1.4426950408889634).to(torch.float32))
+                # per-tie record of the shortcut kernel: (col, X, +-x^T, lo_1..lo_{K-1})
+                rec = self.u_rec
+                rec[:, 0] = P.t["u_col"].to(torch.float32)  # exact below 2^24 nodes
+                rec[:, 1] = P.t["u_px"]
+                rec[:, 2] = P.t["u_pxt"]
+                rec[:, 3:2 + K] = ((lp[:, 1:] - lp[:, :1]) * 1.4426950408889634).to(torch.float32)
                 big = torch.full_like(lp[:, 0], 1e300)
                 self.simple_consts[0] = torch.where(sm, lp[:, 0], big).min().clamp(max=0.0)
                 self.simple_consts[1] = P.t["u_px"].max().to(torch.float64)

@@ -15,66 +15,28 @@ import numpy as np
 import torch
 
 
-def dense_tile_w(K):
-    """Column-tile width of the dense kernel (a K-dependent constant of the CUDA library)."""
-    from . import _capi
-
-    w = int(_capi.load().vm_dense_tile_w(int(K)))
-    if w <= 0:
-        raise ValueError("vimure_b200 supports 2 <= K <= 32 = VM_MAX_K (got K=%d)" % K)
-    return w
-
-GAMMA_CHUNK = 256
-PHI_CHUNK = 4096
-SPECIAL_TIES_PER_BLOCK = 1024  # == VM_SPECIAL_TIES_PER_BLOCK of include/vimure_b200.h
-NCHUNK = 4  # == VM_NCHUNK
-
-
-def _i32(t):
-    return t.to(torch.int32).contiguous()
-
-
-class _Trace:
-    """VM_PACK_TRACE=1: print the wall time of the packer's stages (each closed by a device synchronisation)."""
-
-    def __init__(self, dev):
-        import os
-        import time
-
-        self.on = os.environ.get("VM_PACK_TRACE") == "1"
-        self.dev, self.time = dev, time
-        if self.on:
-            self._sync()
-            self.t = time.time()
-
-    def _sync(self):
-        if self.dev.type == "cuda":
-            torch.cuda.synchronize(self.dev)
-
-    def __call__(self, label):
-        if self.on:
-            self._sync()
-            now = self.time.time()
-            print("pack: %-24s %7.2f ms" % (label, (now - self.t) * 1e3), flush=True)
-            self.t = now
-
-
-class Packed:
-    """Plain container of the packed tensors + dimensions."""
-
-    def __init__(self):
-        self.t = {}
-
-    def __getattr__(self, k):
-        t = self.__dict__.get("t", {})
-        if k in t:
-            return t[k]
-        raise AttributeError(k)
+from ._pack_native import (GAMMA_CHUNK, NCHUNK, PHI_CHUNK, SPECIAL_TIES_PER_BLOCK, Packed, _Trace, _i32, _overlap_chunks,  # noqa: F401
+                           dense_tile_w, pack_device)
 
 
 def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64, mutuality=True, split_e0=True,
          simple=None, single=None):
-    """Build the packed layout.
+    """Build the packed layout: on a CUDA device and for a structured mask through the library's own packer (`vm_pack`
+    behind the C ABI, csrc/vm_pack.cu); otherwise (CPU tests, general COO masks, VM_PY_PACKER=1) with the torch index
+    ops of `pack_torch`, which doubles as the executable specification of the layout."""
+    import os
+
+    dev = torch.device(device)
+    if dev.type == "cuda" and mask.kind in ("ego", "all") and os.environ.get("VM_PY_PACKER") != "1":
+        return pack_device(X_subs, X_vals, L, N, M, K, mask, dev, row0=row0, nloc=nloc, tile_h=tile_h, mutuality=mutuality,
+                           split_e0=split_e0, simple=simple, single=single)
+    return pack_torch(X_subs, X_vals, L, N, M, K, mask, device, row0=row0, nloc=nloc, tile_h=tile_h, mutuality=mutuality,
+                      split_e0=split_e0, simple=simple, single=single)
+
+
+def pack_torch(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64, mutuality=True, split_e0=True,
+               simple=None, single=None):
+    """Build the packed layout with torch index ops (any device).
 
     X_subs : (4, I) integer array-like (l, i, j, m);  X_vals : (I,) counts;  mask : masks.ReporterMask.
     mutuality / split_e0 : the gamma and phi passes only visit the entries with a reciprocal report (x^T > 0); for the
@@ -222,29 +184,10 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
     bounds = (rows[:, None] * N + torch.arange(P.nct, device=dev, dtype=torch.int64)[None, :] * TILE_W).flatten()
     bounds = torch.cat([bounds, bounds.new_tensor([L * nloc * N])])
     P.t["utile_ptr"] = _i32(torch.searchsorted(ukeys, bounds))
-    # special ties grouped by (layer, column)   [ego statistics]
-    ck = u_l * N + u_col
-    ck_sorted, cperm = torch.sort(ck, stable=True)
-    P.t["ucol_perm"] = _i32(cperm)
-    P.t["ucol_ptr"] = torch.searchsorted(ck_sorted, torch.arange(L * N + 1, device=dev, dtype=torch.int64)).contiguous()
     n_ul = (P.t["utile_ptr"][:: nloc * P.nct][1:] - P.t["utile_ptr"][:: nloc * P.nct][:-1]) if U else None
     max_ul = int(n_ul.max()) if U else 0
     P.n_ublk = max(1, (max_ul + SPECIAL_TIES_PER_BLOCK - 1) // SPECIAL_TIES_PER_BLOCK)
-    # row chunks for overlapping the special-tie kernel with the dense kernel (see vm_ctx.n_chunks): dense chunk c covers
-    # row tiles [rt_end[c-1], rt_end[c]); it may start once the special-tie blocks below sp_chunk_blk[l][c+1] are done
-    rt_end = [min(P.nrt, -(-P.nrt * (q + 1) // NCHUNK)) for q in range(NCHUNK)]
-    P.rt_end = rt_end
-    row_end = [min(nloc, e * P.tile_h) for e in rt_end]
-    lidx = torch.arange(L, device=dev, dtype=torch.int64)
-    u0_l = P.t["utile_ptr"][(lidx * nloc) * P.nct].to(torch.int64)
-    blk = [torch.zeros(L, dtype=torch.int64, device=dev)]
-    for q in range(NCHUNK):
-        u_end = P.t["utile_ptr"][(lidx * nloc + row_end[q]) * P.nct].to(torch.int64)
-        blk.append((u_end - u0_l + SPECIAL_TIES_PER_BLOCK - 1) // SPECIAL_TIES_PER_BLOCK)
-    blk = torch.stack(blk, dim=1)  # [L, NCHUNK+1]
-    blk = torch.cummax(blk, dim=1)[0]
-    P.t["sp_chunk_blk"] = blk.contiguous().flatten()
-    P.sp_grid = [int(v) for v in (blk[:, 1:] - blk[:, :-1]).max(dim=0)[0].cpu()]
+    _overlap_chunks(P, L, nloc, dev)
 
     _mark("tile/col pointers")
     # ---- layer ranges and reporter chunks of the entries
@@ -285,7 +228,7 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
     # or the column node).  On iterations without ELBO the fast dense kernel evaluates them and the special-tie kernel walks
     # `cx_idx`, the others, through compacted copies of their per-tie arrays.
     P.simple_ok = bool(simple and mask.kind == "ego" and K <= 4 and (N * K) % 4 == 0 and N >= TILE_W and P.tile_h <= 128
-                       and (split_e0 or not mutuality) and U > 0)
+                       and (split_e0 or not mutuality) and U > 0 and N < (1 << 24))
     u_simple = torch.zeros(U, dtype=torch.bool, device=dev)
     u_single = torch.zeros(U, dtype=torch.bool, device=dev)
     if P.simple_ok:

@@ -1342,15 +1342,27 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
 // and tile_h row nodes are staged in shared memory once, the per-reporter corrections are accumulated in shared memory
 // (64-bit integer atomics) and flushed with one global atomic per touched node, and the CTA's ~tile_h*19 special ties are
 // spread over all its threads (a prefix sum over the rows' segments maps a thread to its tie).
+// The kernel is latency-bound (per tie: one record load, ~150 dependent fp32 instructions, two shared-memory atomics, one
+// store), so every thread keeps VM_SC_UNR ties in flight: their records (one 16/32-byte load each: column, X, +-x^T, lo_k
+// packed per tie in `u_rec`) are requested together before any is evaluated, and the tie -> row-segment map is a byte
+// table in shared memory filled once per CTA instead of a binary search per tie.
 #define VM_SC_THREADS 256
+#define VM_SC_MAXE 6144  // ties of a tile whose row comes from the byte table (the rest falls back to a binary search)
+template <int K>
+struct ScCfg {
+  static constexpr int RS = (K == 2) ? 4 : 8;   // floats per tie record: col, X, +-x^T, lo_1..lo_{K-1}, padding
+  static constexpr int UNR = (K == 2) ? 4 : 2;  // ties in flight per thread
+};
+
 template <int K>
 __global__ void __launch_bounds__(VM_SC_THREADS) k_shortcut(const __grid_constant__ vm_ctx c) {
-  constexpr int NT = NodeTab<K>::STRIDE, TW = DenseCfg<K>::TW, TH = VM_FAST_MAX_TILE_H;
+  constexpr int NT = NodeTab<K>::STRIDE, TW = DenseCfg<K>::TW, TH = VM_FAST_MAX_TILE_H, RS = ScCfg<K>::RS, UNR = ScCfg<K>::UNR;
   __shared__ __align__(16) float nt_col[TW * NT];
   __shared__ __align__(16) float nt_row[TH * NT];
   __shared__ float s_tabp[TH][K - 1];
   __shared__ unsigned long long colfix[TW][K - 1], rowfix[TH][K - 1];
   __shared__ int s_tp0[TH], s_off[TH + 1];
+  __shared__ unsigned char s_row[VM_SC_MAXE];
   __shared__ float s_lam[3 * K + 1 + K];  // G_lambda_k | G_lambda_k - G_lambda_0 | E[log lambda_k] log2e | G_nu | g_k
   __shared__ double sm_red[VM_SC_THREADS / 32];
   const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
@@ -1373,6 +1385,26 @@ __global__ void __launch_bounds__(VM_SC_THREADS) k_shortcut(const __grid_constan
     s_off[tid + 1] = n;
   }
   if (tid == 0) s_off[0] = 0;
+  // ---- node tables of the tile, per-layer constants, cleared accumulators (independent of the scan: issued first)
+  for (int t = tid; t < TW * NT / 4; t += VM_SC_THREADS)
+    reinterpret_cast<float4*>(nt_col)[t] = __ldg(reinterpret_cast<const float4*>(c.nodetab + ((int64_t)l * N + jt) * NT) + t);
+  for (int t = tid; t < nrows * NT / 4; t += VM_SC_THREADS)
+    reinterpret_cast<float4*>(nt_row)[t] =
+        __ldg(reinterpret_cast<const float4*>(c.nodetab + ((int64_t)l * N + (int)c.row0 + i_lo) * NT) + t);
+  for (int t = tid; t < nrows * (K - 1); t += VM_SC_THREADS) {
+    const int r = t / (K - 1), k = t - r * (K - 1) + 1;
+    s_tabp[r][k - 1] = __ldg(&c.tab_p[((int64_t)l * nloc + i_lo + r) * K + k]);
+  }
+  for (int t = tid; t < TW * (K - 1); t += VM_SC_THREADS) (&colfix[0][0])[t] = 0ull;
+  for (int t = tid; t < TH * (K - 1); t += VM_SC_THREADS) (&rowfix[0][0])[t] = 0ull;
+  if (tid < K) {
+    const double g0 = c.G_lambda[l * K], gkk = c.G_lambda[l * K + tid];
+    s_lam[tid] = (float)gkk;
+    s_lam[K + tid] = (float)(gkk - g0);
+    s_lam[2 * K + tid] = (float)(c.Elog_lambda[l * K + tid] * VM_LOG2E);
+    s_lam[3 * K + 1 + tid] = (float)lc[VM_LC_G(K, tid)];
+    if (tid == 0) s_lam[3 * K] = (float)c.nu[VM_NU_G];
+  }
   __syncthreads();
   if (tid < 32) {  // TH = 128 counts: 4 per lane, warp scan
     int v[4], sum = 0;
@@ -1394,108 +1426,118 @@ __global__ void __launch_bounds__(VM_SC_THREADS) k_shortcut(const __grid_constan
       s_off[1 + 4 * tid + q] = run;
     }
   }
-  // ---- node tables of the tile, per-layer constants, cleared accumulators
-  for (int t = tid; t < TW * NT / 4; t += VM_SC_THREADS)
-    reinterpret_cast<float4*>(nt_col)[t] = __ldg(reinterpret_cast<const float4*>(c.nodetab + ((int64_t)l * N + jt) * NT) + t);
-  for (int t = tid; t < nrows * NT / 4; t += VM_SC_THREADS)
-    reinterpret_cast<float4*>(nt_row)[t] =
-        __ldg(reinterpret_cast<const float4*>(c.nodetab + ((int64_t)l * N + (int)c.row0 + i_lo) * NT) + t);
-  for (int t = tid; t < nrows * (K - 1); t += VM_SC_THREADS) {
-    const int r = t / (K - 1), k = t - r * (K - 1) + 1;
-    s_tabp[r][k - 1] = __ldg(&c.tab_p[((int64_t)l * nloc + i_lo + r) * K + k]);
-  }
-  for (int t = tid; t < TW * (K - 1); t += VM_SC_THREADS) (&colfix[0][0])[t] = 0ull;
-  for (int t = tid; t < TH * (K - 1); t += VM_SC_THREADS) (&rowfix[0][0])[t] = 0ull;
-  if (tid < K) {
-    const double g0 = c.G_lambda[l * K], gkk = c.G_lambda[l * K + tid];
-    s_lam[tid] = (float)gkk;
-    s_lam[K + tid] = (float)(gkk - g0);
-    s_lam[2 * K + tid] = (float)(c.Elog_lambda[l * K + tid] * VM_LOG2E);
-    s_lam[3 * K + 1 + tid] = (float)lc[VM_LC_G(K, tid)];
-    if (tid == 0) s_lam[3 * K] = (float)c.nu[VM_NU_G];
-  }
   __syncthreads();
   const int total = s_off[TH];
+  if (tid < TH) {  // tie -> row segment byte table
+    const int e1 = min(s_off[tid + 1], VM_SC_MAXE);
+    for (int e = s_off[tid]; e < e1; ++e) s_row[e] = (unsigned char)tid;
+  }
+  __syncthreads();
   float p0[K], nu = 0.f;
 #pragma unroll
   for (int k = 0; k < K; ++k) p0[k] = 0.f;
-  for (int e = tid; e < total; e += VM_SC_THREADS) {
-    // row segment of entry e: the last r with s_off[r] <= e
-    int lo = 0, hi = TH;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (s_off[mid] <= e) lo = mid;
-      else hi = mid;
-    }
-    const int r = lo;
-    const int64_t u = (int64_t)s_tp0[r] + (e - s_off[r]);
-    const float X = c.u_px[u];
-    if (!(X > 0.f)) continue;  // not a shortcut tie
-    const int cj = c.u_col[u] - jt;
-    const float xt = c.u_pxt[u];
-    const float* ni = nt_row + r * NT;
-    const float* nj = nt_col + cj * NT;
-    const bool single = xt != 0.f, rowrep = xt > 0.f;
-    const float g = single ? (rowrep ? ni[K - 1] : nj[K - 1]) : 1.f;
-    const float el = single ? (rowrep ? ni[K] : nj[K]) : 0.f;
-    const float z2 = s_lam[3 * K] * fabsf(xt);
-    float f[K], iden[K];
+  for (int e0 = tid; e0 < total; e0 += VM_SC_THREADS * UNR) {
+    int rr[UNR];
+    int64_t uu[UNR];
+    float rec[UNR][RS];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const float z1 = g * s_lam[k];
-      iden[k] = vm_rcp(z1 + z2);
-      f[k] = single ? z1 * iden[k] : 1.f;
-    }
-    const float t0 = z2 * g * iden[0];
-    // log2-odds against k = 0, then a softmax with the maximum subtracted: for K >= 3 the odds of two categories can both
-    // be astronomically large (a tie with a count of 20: 2^140) and only their RATIO matters -- clamping them (as the
-    // closed form may, its odds being ~2^-40) would flatten it
-    float a[K], amax = 0.f, sf = 0.f, ef[K];
+    for (int q = 0; q < UNR; ++q) {
+      const int e = e0 + q * VM_SC_THREADS;
+      int r = 0;
+      if (e < total) {
+        if (e < VM_SC_MAXE) {
+          r = s_row[e];
+        } else {  // the last r with s_off[r] <= e
+          int lo = 0, hi = TH;
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= e) lo = mid;
+            else hi = mid;
+          }
+          r = lo;
+        }
+      }
+      rr[q] = r;
+      uu[q] = (int64_t)s_tp0[r] + (e - s_off[r]);
 #pragma unroll
-    for (int k = 1; k < K; ++k) {
-      const float dat = single ? X * ((t0 * iden[k] * s_lam[K + k]) * el + (f[k] * s_lam[2 * K + k] - f[0] * s_lam[2 * K]))
-                               : X * s_lam[3 * K + 1 + k];
-      const float qk = nj[k - 1];
-      a[k] = ni[k - 1] + qk + c.u_lo[u * (K - 1) + (k - 1)] + dat;
-      amax = fmaxf(amax, a[k]);
-      // the closed form the dense sweep counts for this tie: same operations, same bits (qk == tab_q[l,j,k])
-      ef[k] = vm_ex2(fminf(__fadd_rn(s_tabp[r][k - 1], qk), VM_CLAMP_LOG2));
-      sf = (k == 1) ? ef[k] : __fadd_rn(sf, ef[k]);
-    }
-    float es[K], s = vm_ex2(-amax);
-    es[0] = s;
-#pragma unroll
-    for (int k = 1; k < K; ++k) {
-      es[k] = vm_ex2(a[k] - amax);
-      s += es[k];
-    }
-    const float inv = vm_rcp(s), invf = vm_rcp(__fadd_rn(1.f, sf));
-    float rho[K];
-    rho[0] = es[0] * inv;
-    float nu_t = rho[0] * iden[0];
-    const bool act_i = ni[K + 1] != 0.f, act_j = nj[K + 1] != 0.f;
-#pragma unroll
-    for (int k = 1; k < K; ++k) {
-      rho[k] = es[k] * inv;
-      nu_t += rho[k] * iden[k];
-      const long long q = __double2ll_rn(((double)rho[k] - (double)__fmul_rn(ef[k], invf)) * VM_FIX_SCALE);
-      if (q != 0) {
-        if (act_j) atomicAdd(&colfix[cj][k - 1], (unsigned long long)q);
-        if (act_i) atomicAdd(&rowfix[r][k - 1], (unsigned long long)q);
+      for (int v = 0; v < RS; v += 4) {
+        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < total) t4 = __ldg(reinterpret_cast<const float4*>(c.u_rec + uu[q] * RS + v));
+        rec[q][v] = t4.x; rec[q][v + 1] = t4.y; rec[q][v + 2] = t4.z; rec[q][v + 3] = t4.w;
       }
     }
-    float* ru = c.rho_u32 + u * K;
-    if (K == 2) {
-      *reinterpret_cast<float2*>(ru) = make_float2(rho[0], rho[1]);
-    } else {
 #pragma unroll
-      for (int k = 0; k < K; ++k) ru[k] = rho[k];
-    }
-    if (single) {
-      nu += X * z2 * nu_t;
-    } else {
+    for (int q = 0; q < UNR; ++q) {
+      const float X = rec[q][1];
+      if (!(X > 0.f)) continue;  // not a shortcut tie (or past the end)
+      const int r = rr[q];
+      const int64_t u = uu[q];
+      const int cj = (int)rec[q][0] - jt;
+      const float xt = rec[q][2];
+      const float* ni = nt_row + r * NT;
+      const float* nj = nt_col + cj * NT;
+      const bool single = xt != 0.f, rowrep = xt > 0.f;
+      const float g = single ? (rowrep ? ni[K - 1] : nj[K - 1]) : 1.f;
+      const float el = single ? (rowrep ? ni[K] : nj[K]) : 0.f;
+      const float z2 = s_lam[3 * K] * fabsf(xt);
+      float f[K], iden[K];
 #pragma unroll
-      for (int k = 0; k < K; ++k) p0[k] += rho[k] * X;
+      for (int k = 0; k < K; ++k) {
+        const float z1 = g * s_lam[k];
+        iden[k] = vm_rcp(z1 + z2);
+        f[k] = single ? z1 * iden[k] : 1.f;
+      }
+      const float t0 = z2 * g * iden[0];
+      // log2-odds against k = 0, then a softmax with the maximum subtracted: for K >= 3 the odds of two categories can
+      // both be astronomically large (a tie with a count of 20: 2^140) and only their RATIO matters -- clamping them (as
+      // the closed form may, its odds being ~2^-40) would flatten it
+      float a[K], amax = 0.f, sf = 0.f, ef[K];
+#pragma unroll
+      for (int k = 1; k < K; ++k) {
+        const float dat = single ? X * ((t0 * iden[k] * s_lam[K + k]) * el + (f[k] * s_lam[2 * K + k] - f[0] * s_lam[2 * K]))
+                                 : X * s_lam[3 * K + 1 + k];
+        const float qk = nj[k - 1];
+        a[k] = ni[k - 1] + qk + rec[q][2 + k] + dat;
+        amax = fmaxf(amax, a[k]);
+        // the closed form the dense sweep counts for this tie: same operations, same bits (qk == tab_q[l,j,k])
+        ef[k] = vm_ex2(fminf(__fadd_rn(s_tabp[r][k - 1], qk), VM_CLAMP_LOG2));
+        sf = (k == 1) ? ef[k] : __fadd_rn(sf, ef[k]);
+      }
+      float es[K], s = vm_ex2(-amax);
+      es[0] = s;
+#pragma unroll
+      for (int k = 1; k < K; ++k) {
+        es[k] = vm_ex2(a[k] - amax);
+        s += es[k];
+      }
+      const float inv = vm_rcp(s), invf = vm_rcp(__fadd_rn(1.f, sf));
+      float rho[K];
+      rho[0] = es[0] * inv;
+      float nu_t = rho[0] * iden[0];
+      const bool act_i = ni[K + 1] != 0.f, act_j = nj[K + 1] != 0.f;
+#pragma unroll
+      for (int k = 1; k < K; ++k) {
+        rho[k] = es[k] * inv;
+        nu_t += rho[k] * iden[k];
+        const long long fq = __double2ll_rn(((double)rho[k] - (double)__fmul_rn(ef[k], invf)) * VM_FIX_SCALE);
+        if (fq != 0) {
+          if (act_j) atomicAdd(&colfix[cj][k - 1], (unsigned long long)fq);
+          if (act_i) atomicAdd(&rowfix[r][k - 1], (unsigned long long)fq);
+        }
+      }
+      float* ru = c.rho_u32 + u * K;
+      if (K == 2) {
+        *reinterpret_cast<float2*>(ru) = make_float2(rho[0], rho[1]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) ru[k] = rho[k];
+      }
+      if (single) {
+        nu += X * z2 * nu_t;
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) p0[k] += rho[k] * X;
+      }
     }
   }
   __syncthreads();

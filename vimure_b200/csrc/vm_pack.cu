@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(PT) k_pack_entries(const vm_pack_args p, Work 
   if (w.own[q]) {
     const int64_t o = w.own_pos[q];
     p.e_m[o] = (int32_t)m;
+    p.e_src[o] = (int32_t)e;
     p.e_x[o] = x;
     p.e_xT[o] = xT;
     p.e_flags[o] = mask_mult(p, l, i, j, m) > 0 ? 1 : 0;
