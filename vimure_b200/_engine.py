@@ -207,7 +207,7 @@ class CaviEngine:
                 rec[:, 0] = P.t["u_col"].to(torch.float32)  # exact below 2^24 nodes
                 rec[:, 1] = P.t["u_px"]
                 rec[:, 2] = P.t["u_pxt"]
-                rec[:, 3:2 + K] = ((lp[:, 1:] - lp[:, :1]) * 1.4426950408889634).to(torch.float32)
+                rec[:, 3:2 + P.K] = ((lp[:, 1:] - lp[:, :1]) * 1.4426950408889634).to(torch.float32)
                 big = torch.full_like(lp[:, 0], 1e300)
                 self.simple_consts[0] = torch.where(sm, lp[:, 0], big).min().clamp(max=0.0)
                 self.simple_consts[1] = P.t["u_px"].max().to(torch.float64)
