@@ -260,8 +260,10 @@ class CaviEngine:
         waits for the host between the phases; VM_DIST_GRAPHS=0 keeps the sharded path on eager launches."""
         import os
 
-        if self.group is not None and os.environ.get("VM_DIST_GRAPHS", "1") == "0":
-            return False
+        if self.group is not None:
+            # only NCCL collectives are stream operations that a graph can hold (gloo reduces on the host)
+            if os.environ.get("VM_DIST_GRAPHS", "1") == "0" or torch.distributed.get_backend() != "nccl":
+                return False
         if self._graphs is None:
             self._graphs = {}
         return self._graphs is not None

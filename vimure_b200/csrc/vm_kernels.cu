@@ -1346,6 +1346,14 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
 // store), so every thread keeps VM_SC_UNR ties in flight: their records (one 16/32-byte load each: column, X, +-x^T, lo_k
 // packed per tie in `u_rec`) are requested together before any is evaluated, and the tie -> row-segment map is a byte
 // table in shared memory filled once per CTA instead of a binary search per tie.
+// 64-bit add into a (lo, hi) pair of shared 32-bit words with two native atomics (modular arithmetic: exact)
+__device__ __forceinline__ void vm_smem_add64(unsigned int* w, long long v) {
+  const unsigned int lo = (unsigned int)(unsigned long long)v, hi = (unsigned int)((unsigned long long)v >> 32);
+  const unsigned int old = atomicAdd(&w[0], lo);
+  const unsigned int carry = (old + lo < old) ? 1u : 0u;
+  if (hi + carry != 0u) atomicAdd(&w[1], hi + carry);
+}
+
 #define VM_SC_THREADS 256
 #define VM_SC_MAXE 6144  // ties of a tile whose row comes from the byte table (the rest falls back to a binary search)
 template <int K>
@@ -1360,7 +1368,10 @@ __global__ void __launch_bounds__(VM_SC_THREADS) k_shortcut(const __grid_constan
   __shared__ __align__(16) float nt_col[TW * NT];
   __shared__ __align__(16) float nt_row[TH * NT];
   __shared__ float s_tabp[TH][K - 1];
-  __shared__ unsigned long long colfix[TW][K - 1], rowfix[TH][K - 1];
+  // 64-bit fixed-point accumulators as (lo, hi) pairs of 32-bit words: a 64-bit shared-memory atomic add is a
+  // compare-and-swap spin loop (ATOMS.CAST.SPIN.64), slow under the contention of a row's ~19 ties; two native 32-bit
+  // adds with the carry taken from the returned old value are exact and cheap
+  __shared__ unsigned int colfix[TW][K - 1][2], rowfix[TH][K - 1][2];
   __shared__ int s_tp0[TH], s_off[TH + 1];
   __shared__ unsigned char s_row[VM_SC_MAXE];
   __shared__ float s_lam[3 * K + 1 + K];  // G_lambda_k | G_lambda_k - G_lambda_0 | E[log lambda_k] log2e | G_nu | g_k
@@ -1395,8 +1406,8 @@ __global__ void __launch_bounds__(VM_SC_THREADS) k_shortcut(const __grid_constan
     const int r = t / (K - 1), k = t - r * (K - 1) + 1;
     s_tabp[r][k - 1] = __ldg(&c.tab_p[((int64_t)l * nloc + i_lo + r) * K + k]);
   }
-  for (int t = tid; t < TW * (K - 1); t += VM_SC_THREADS) (&colfix[0][0])[t] = 0ull;
-  for (int t = tid; t < TH * (K - 1); t += VM_SC_THREADS) (&rowfix[0][0])[t] = 0ull;
+  for (int t = tid; t < TW * (K - 1) * 2; t += VM_SC_THREADS) (&colfix[0][0][0])[t] = 0u;
+  for (int t = tid; t < TH * (K - 1) * 2; t += VM_SC_THREADS) (&rowfix[0][0][0])[t] = 0u;
   if (tid < K) {
     const double g0 = c.G_lambda[l * K], gkk = c.G_lambda[l * K + tid];
     s_lam[tid] = (float)gkk;
@@ -1521,8 +1532,8 @@ __global__ void __launch_bounds__(VM_SC_THREADS) k_shortcut(const __grid_constan
         nu_t += rho[k] * iden[k];
         const long long fq = __double2ll_rn(((double)rho[k] - (double)__fmul_rn(ef[k], invf)) * VM_FIX_SCALE);
         if (fq != 0) {
-          if (act_j) atomicAdd(&colfix[cj][k - 1], (unsigned long long)fq);
-          if (act_i) atomicAdd(&rowfix[r][k - 1], (unsigned long long)fq);
+          if (act_j) vm_smem_add64(colfix[cj][k - 1], fq);
+          if (act_i) vm_smem_add64(rowfix[r][k - 1], fq);
         }
       }
       float* ru = c.rho_u32 + u * K;
@@ -1544,11 +1555,13 @@ __global__ void __launch_bounds__(VM_SC_THREADS) k_shortcut(const __grid_constan
   // ---- flush: one global atomic per touched node and category
   unsigned long long* fix_l = reinterpret_cast<unsigned long long*>(c.fixA) + (int64_t)l * c.M * K;
   for (int t = tid; t < TW * (K - 1); t += VM_SC_THREADS) {
-    const unsigned long long v = (&colfix[0][0])[t];
+    const unsigned int* w = &colfix[0][0][0] + 2 * t;
+    const unsigned long long v = ((unsigned long long)w[1] << 32) | w[0];
     if (v != 0ull) atomicAdd(fix_l + (int64_t)(jt + t / (K - 1)) * K + 1 + t % (K - 1), v);
   }
   for (int t = tid; t < nrows * (K - 1); t += VM_SC_THREADS) {
-    const unsigned long long v = (&rowfix[0][0])[t];
+    const unsigned int* w = &rowfix[0][0][0] + 2 * t;
+    const unsigned long long v = ((unsigned long long)w[1] << 32) | w[0];
     if (v != 0ull) atomicAdd(fix_l + (int64_t)((int)c.row0 + i_lo + t / (K - 1)) * K + 1 + t % (K - 1), v);
   }
   // rho_k X of the SIMPLE ties (their part of the next phi-shape sums) and the nu statistic of the SINGLE ties

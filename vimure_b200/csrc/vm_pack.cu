@@ -62,23 +62,35 @@ struct Work {
 enum { C_U = 0, C_I, C_I1, C_IT, C_NCX, C_NGCHUNK, C_MAXUL, C_MAXLAY, C_MAXCXL, C_DUP, C_OOB, C_SUMX, C_BALL, C_NNEED, C_NE };
 
 // ---- 1. keys: (l,i,j,m) of the entries a row-block shard needs (own rows, or reciprocal of an own row) ------------
+__device__ __forceinline__ void warp_add_counter(int64_t* counter, long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v != 0) atomicAdd(reinterpret_cast<unsigned long long*>(counter), (unsigned long long)v);
+}
+
 __global__ void __launch_bounds__(PT) k_pack_keys(const vm_pack_args p, Work w, int64_t sentinel) {
-  const int64_t e = (int64_t)blockIdx.x * PT + threadIdx.x;
-  if (e >= p.n_in) return;
-  const int64_t l = p.x_l[e], i = p.x_i[e], j = p.x_j[e], m = p.x_m[e];
+  const int64_t e = (int64_t)blockIdx.x * PT + threadIdx.x;  // (no early return: the warp reductions need every lane)
   int64_t key = sentinel;  // L*N*N*M: sorts behind every valid key
-  if (l < 0 || l >= p.L || i < 0 || i >= p.N || j < 0 || j >= p.N || m < 0 || m >= p.M) {
-    p.counts[C_OOB] = 1;
-  } else {
-    const bool own = i >= p.row0 && i < p.row0 + p.nloc, ownT = j >= p.row0 && j < p.row0 + p.nloc;
-    if (own || ownT) {
-      key = ((l * p.N + i) * p.N + j) * p.M + m;
-      atomicAdd(reinterpret_cast<unsigned long long*>(p.counts) + C_NNEED, 1ull);
-      if (own) atomicAdd(reinterpret_cast<unsigned long long*>(p.counts) + C_SUMX, (unsigned long long)(long long)p.x_v[e]);
+  int need = 0;
+  long long xsum = 0;
+  if (e < p.n_in) {
+    const int64_t l = p.x_l[e], i = p.x_i[e], j = p.x_j[e], m = p.x_m[e];
+    if (l < 0 || l >= p.L || i < 0 || i >= p.N || j < 0 || j >= p.N || m < 0 || m >= p.M) {
+      p.counts[C_OOB] = 1;
+    } else {
+      const bool own = i >= p.row0 && i < p.row0 + p.nloc, ownT = j >= p.row0 && j < p.row0 + p.nloc;
+      if (own || ownT) {
+        key = ((l * p.N + i) * p.N + j) * p.M + m;
+        need = 1;
+        if (own) xsum = p.x_v[e];
+      }
     }
+    w.key[e] = key;
+    w.idx[e] = (int32_t)e;
   }
-  w.key[e] = key;
-  w.idx[e] = (int32_t)e;
+  // one atomic per warp and counter (a single address hit by every thread serialises)
+  warp_add_counter(p.counts + C_NNEED, (long long)need);
+  warp_add_counter(p.counts + C_SUMX, xsum);
 }
 
 // reporter mask multiplicity of (l,i,j,m) for the structured masks
@@ -115,38 +127,42 @@ __global__ void __launch_bounds__(PT) k_pack_pair(const vm_pack_args p, Work w) 
 
 // ---- 3. owned entries in tie order: e_m, e_x, e_xT, e_flags, tie keys, E1 flags, g0, transposed list ----------------
 __global__ void __launch_bounds__(PT) k_pack_entries(const vm_pack_args p, Work w) {
-  const int64_t q = (int64_t)blockIdx.x * PT + threadIdx.x;
-  if (q >= p.n_in) return;
+  const int64_t q = (int64_t)blockIdx.x * PT + threadIdx.x;  // (no early return: the warp reduction needs every lane)
   const int64_t n_need = p.counts[C_NNEED];
-  if (q == p.n_in - 1) {  // totals of the two compactions
-    p.counts[C_I] = w.own_pos[q] + w.own[q];
-    p.counts[C_IT] = w.tr_pos[q] + w.tr[q];
+  long long ball = 0;
+  if (q < p.n_in) {
+    if (q == p.n_in - 1) {  // totals of the two compactions
+      p.counts[C_I] = w.own_pos[q] + w.own[q];
+      p.counts[C_IT] = w.tr_pos[q] + w.tr[q];
+    }
+    if (q < n_need) {
+      const int64_t e = w.idx2[q];
+      const int64_t l = p.x_l[e], i = p.x_i[e], j = p.x_j[e], m = p.x_m[e];
+      const float x = (float)p.x_v[e], xT = w.xT[q];
+      if (w.own[q]) {
+        const int64_t o = w.own_pos[q];
+        p.e_m[o] = (int32_t)m;
+        p.e_src[o] = (int32_t)e;
+        p.e_x[o] = x;
+        p.e_xT[o] = xT;
+        p.e_flags[o] = mask_mult(p, l, i, j, m) > 0 ? 1 : 0;
+        w.tkey[o] = (l * p.nloc + (i - p.row0)) * p.N + j;
+        // E1 = the entries the gamma / phi passes visit (reciprocal report present); E0 = constant allocation dz1 = x
+        const int is1 = !p.split_e0 ? 1 : (p.mutuality ? (xT != 0.f ? 1 : 0) : 0);
+        w.e1[o] = is1;
+        if (!is1) atomicAdd(reinterpret_cast<unsigned long long*>(w.g0i) + l * p.M + m, (unsigned long long)(long long)p.x_v[e]);
+      }
+      if (w.tr[q]) {
+        const int64_t t = w.tr_pos[q];
+        p.t_lrow[t] = (int32_t)(l * p.nloc + (j - p.row0));
+        p.t_col[t] = (int32_t)i;
+        const int mult = mask_mult(p, l, j, i, m);
+        p.t_x[t] = x * (float)mult;
+        ball = (long long)p.x_v[e] * mult;
+      }
+    }
   }
-  if (q >= n_need) return;
-  const int64_t e = w.idx2[q];
-  const int64_t l = p.x_l[e], i = p.x_i[e], j = p.x_j[e], m = p.x_m[e];
-  const float x = (float)p.x_v[e], xT = w.xT[q];
-  if (w.own[q]) {
-    const int64_t o = w.own_pos[q];
-    p.e_m[o] = (int32_t)m;
-    p.e_src[o] = (int32_t)e;
-    p.e_x[o] = x;
-    p.e_xT[o] = xT;
-    p.e_flags[o] = mask_mult(p, l, i, j, m) > 0 ? 1 : 0;
-    w.tkey[o] = (l * p.nloc + (i - p.row0)) * p.N + j;
-    // E1 = the entries the gamma / phi passes visit (reciprocal report present); E0 = constant Poisson allocation dz1 = x
-    const int is1 = !p.split_e0 ? 1 : (p.mutuality ? (xT != 0.f ? 1 : 0) : 0);
-    w.e1[o] = is1;
-    if (!is1) atomicAdd(reinterpret_cast<unsigned long long*>(w.g0i) + l * p.M + m, (unsigned long long)(long long)p.x_v[e]);
-  }
-  if (w.tr[q]) {
-    const int64_t t = w.tr_pos[q];
-    p.t_lrow[t] = (int32_t)(l * p.nloc + (j - p.row0));
-    p.t_col[t] = (int32_t)i;
-    const int mult = mask_mult(p, l, j, i, m);
-    p.t_x[t] = x * (float)mult;
-    atomicAdd(reinterpret_cast<unsigned long long*>(p.counts) + C_BALL, (unsigned long long)((long long)p.x_v[e] * mult));
-  }
+  warp_add_counter(p.counts + C_BALL, ball);
 }
 
 // head flags of the owned entries (first entry of its tie)

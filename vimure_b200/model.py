@@ -621,11 +621,7 @@ class VimureModel(TransformerMixin, BaseEstimator):
     def _gather_rho(self, slab):
         """Device slab (L, nloc, N, K) float32 -> full host array (L, N, N, K) float64."""
         if self._world > 1:
-            parts = [torch.empty_like(slab) if shard_rows(self.N, self._world, r)[1] == slab.shape[1] else
-                     torch.empty(self.L, shard_rows(self.N, self._world, r)[1], self.N, self.K, dtype=slab.dtype,
-                                 device=slab.device) for r in range(self._world)]
-            torch.distributed.all_gather(parts, slab.contiguous())
-            slab = torch.cat(parts, dim=1)
+            slab = self._all_gather_rows(slab)
         return slab.cpu().numpy().astype(np.float64)
 
     @property
@@ -696,11 +692,22 @@ class VimureModel(TransformerMixin, BaseEstimator):
         slab = None if (getattr(self, "_engine_f", None) is not None or self._rho_f_dev is None) else self._rho_f_dev
         out = getattr(eng, what)(*args, slab=slab)
         if self._world > 1:
-            parts = [torch.empty((self.L, shard_rows(self.N, self._world, r)[1], self.N), dtype=out.dtype, device=out.device)
-                     for r in range(self._world)]
-            torch.distributed.all_gather(parts, out.contiguous())
-            out = torch.cat(parts, dim=1)
+            out = self._all_gather_rows(out)
         return out.cpu().numpy()
+
+    def _all_gather_rows(self, t):
+        """Concatenate the ranks' row blocks (dim 1) of a per-tie tensor; every rank gets the whole (collective).  NCCL
+        gathers device tensors; gloo (CPU tests, ranks sharing one GPU) gathers on the host."""
+        host = torch.distributed.get_backend() != "nccl"
+        if host:
+            t = t.cpu()
+        shape = list(t.shape)
+        parts = []
+        for r in range(self._world):
+            shape[1] = shard_rows(self.N, self._world, r)[1]
+            parts.append(torch.empty(shape, dtype=t.dtype, device=t.device))
+        torch.distributed.all_gather(parts, t.contiguous())
+        return torch.cat(parts, dim=1)
 
     def _engine_of_rho_f(self):
         """The engine whose consumers read rho_f (see `_consume`; pass `slab=self._rho_f_dev` when that is not None)."""
