@@ -178,7 +178,7 @@ def _cpu_worker(idx, n_nodes, L, K, iters, barrier, out):
                     o.default_pr_rho(ties, pr))
         o.iterate()  # warm-up
         if barrier is not None:
-            barrier.wait(timeout=900)  # all replicas start their timed iterations together
+            barrier.wait(timeout=300)  # all replicas start their timed iterations together
         t0 = time.time()
         for it in range(iters):
             o.iterate()
@@ -202,37 +202,82 @@ def cpu_oracle_throughput_all_cores(n_nodes, L, K, iters=3, procs=0):
     replicas of the bounded sample run CONCURRENTLY (so that they compete for memory bandwidth as a parallel
     implementation would); throughput = procs * iters * ties / slowest replica.  Returns (ties/s, s/iter, nnz, procs)."""
     import multiprocessing as mp
+    import queue as _queue
 
-    procs = procs or max(1, min(os.cpu_count() or 1, 64))
+    if not procs:
+        # the cores this process may run on (a cgroup / cpuset can be narrower than os.cpu_count()), at most 64, and no
+        # more replicas than the host memory holds (a replica of the N=2048 sample peaks at 1.5 GB; scaled by N^2)
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except Exception:  # noqa: BLE001
+            ncpu = os.cpu_count() or 1
+        per_replica = 1.6e9 * (n_nodes / 2048.0) ** 2 * L
+        try:
+            import psutil
+
+            avail = float(psutil.virtual_memory().available)
+        except Exception:  # noqa: BLE001
+            avail = 32e9
+        procs = max(1, min(ncpu, 64, int(0.6 * avail / per_replica)))
     ties = float(L) * n_nodes * n_nodes
-    if procs == 1:
-        r = _cpu_worker(0, n_nodes, L, K, iters, None, None)
-        if r[3] is not None:
-            raise RuntimeError("CPU sample failed: %s" % r[3])
-        return iters * ties / r[1], r[1] / iters, r[2], 1
-    ctx = mp.get_context("spawn")  # never fork a process that may hold a CUDA context
-    barrier, out = ctx.Barrier(procs), ctx.Queue()
-    saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS")}
-    for k in saved:
-        os.environ[k] = "1"
-    try:
-        ps = [ctx.Process(target=_cpu_worker, args=(i, n_nodes, L, K, iters, barrier, out), daemon=True) for i in range(procs)]
-        for p_ in ps:
-            p_.start()
-    finally:
-        for k, v in saved.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
-    res = [out.get(timeout=1200) for _ in ps]
-    for p_ in ps:
-        p_.join(timeout=60)
-    bad = [r for r in res if r[3] is not None]
-    if bad:
-        raise RuntimeError("CPU replica failed: %s" % bad[0][3])
-    slowest = max(r[1] for r in res)
-    return procs * iters * ties / slowest, slowest / iters, res[0][2], procs
+
+    def attempt(procs):
+        if procs == 1:
+            r = _cpu_worker(0, n_nodes, L, K, iters, None, None)
+            if r[3] is not None:
+                raise RuntimeError("CPU sample failed: %s" % r[3])
+            return iters * ties / r[1], r[1] / iters, r[2], 1
+        ctx = mp.get_context("spawn")  # never fork a process that may hold a CUDA context
+        barrier, out = ctx.Barrier(procs), ctx.Queue()
+        saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS")}
+        for k in saved:
+            os.environ[k] = "1"
+        try:
+            ps = [ctx.Process(target=_cpu_worker, args=(i, n_nodes, L, K, iters, barrier, out), daemon=True)
+                  for i in range(procs)]
+            for p_ in ps:
+                p_.start()
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        # collect the results; a replica that died without reporting (e.g. killed for memory) would leave the others at
+        # their barrier: notice it, release them and fail this attempt instead of waiting
+        res, deadline = [], time.time() + 600
+        try:
+            while len(res) < procs:
+                try:
+                    res.append(out.get(timeout=1.0))
+                    continue
+                except _queue.Empty:
+                    pass
+                dead = [p_ for p_ in ps if p_.exitcode not in (None, 0)]
+                if dead or time.time() > deadline:
+                    try:
+                        barrier.abort()
+                    except Exception:  # noqa: BLE001
+                        pass
+                    raise RuntimeError("CPU replica died (exit code %s) or timed out" % (dead[0].exitcode if dead else "-"))
+        finally:
+            for p_ in ps:
+                p_.join(timeout=5)
+                if p_.is_alive():
+                    p_.terminate()  # (exact processes this function started)
+        bad = [r for r in res if r[3] is not None]
+        if bad:
+            raise RuntimeError("CPU replica failed: %s" % bad[0][3])
+        slowest = max(r[1] for r in res)
+        return procs * iters * ties / slowest, slowest / iters, res[0][2], procs
+
+    while True:
+        try:
+            return attempt(procs)
+        except RuntimeError:
+            if procs == 1:
+                raise
+            procs = max(1, procs // 4)  # fewer replicas (memory), finally one in-process
 
 
 def cpu_baseline_record(n_nodes, L, K, iters, procs):

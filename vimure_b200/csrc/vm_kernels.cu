@@ -576,6 +576,9 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
     s_El[threadIdx.x] = c.E_lambda[l * K + threadIdx.x];
   }
   __syncthreads();
+  // LIST = 2 is launched with a small grid whose blocks stride over the layer's block indices (on most fits no layer is
+  // its to do: thousands of blocks that only return cost 15 us per iteration at config 3)
+  do {
   double nu_acc = 0.0, cat_acc = 0.0, t2_acc = 0.0;
   double dsum[K], p0[K];
 #pragma unroll
@@ -844,6 +847,7 @@ __global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) 
       if (lane == 0) part[(UP_DELTA + k) * nup + b] = v;
     }
   }
+  } while (LIST == 2 && (blk += (int)gridDim.x) < (int)c.n_ublk);
 }
 
 // ---- the per-tie dense kernel: every owned tie, closed form, fp32 slab write + statistics partials -------------
@@ -1142,7 +1146,7 @@ struct FastSmem {
   double sm_red[8];
 };
 
-template <int K, bool ELBO>
+template <int K, bool ELBO, bool PATCH = true>
 __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_MINBLK2 : 2) k_dense_fast(const __grid_constant__ vm_ctx c, double* catpart, int rt0, int rtn) {
   constexpr int NCH = DenseCfg<K>::NCH, TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32, CAPW = FastCfg<K>::CAPW;
   extern __shared__ __align__(16) unsigned char vm_fast_smem[];
@@ -1171,12 +1175,14 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
     const int64_t lrow = (int64_t)l * nloc + i_lo + r;
 #pragma unroll
     for (int k = 1; k < K; ++k) S.ps[k - 1][r] = __ldg(&c.tab_p[lrow * K + k]);
-    S.tp0[r] = __ldg(&c.utile_ptr[lrow * nct + ct]);
-    S.tp1[r] = __ldg(&c.utile_ptr[lrow * nct + ct + 1]);
+    if (PATCH) {
+      S.tp0[r] = __ldg(&c.utile_ptr[lrow * nct + ct]);
+      S.tp1[r] = __ldg(&c.utile_ptr[lrow * nct + ct + 1]);
+    }
   }
   __syncthreads();
   // ---- phase 1: stage the patch data of this warp's rows asynchronously
-  {
+  if (PATCH) {
     int off = 0;
     for (int r = warp; r < nrows; r += NW) {
       const int ua = S.tp0[r], n = S.tp1[r] - ua;
@@ -1263,6 +1269,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
 #pragma unroll
     for (int k = 1; k < K; ++k) prev[k] = rowacc[k];
     // ---- patch the special ties of this row segment (after the row's own stores)
+    if (!PATCH) continue;
     if (!waited) {
       vm_cp_async_wait_all();
       waited = true;
@@ -1321,6 +1328,252 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
   }
 }
 
+// ---- TMA variant of the fast dense kernel ---------------------------------------------------------------------------
+// Same tiling, arithmetic and partials as k_dense_fast.  What differs is how a row segment reaches HBM: the warp writes
+// its TW ties into a per-warp shared-memory stage in the slab's own layout (conflict-free 128-bit shared stores),
+// overwrites the special ties of the segment IN SHARED MEMORY, and one lane hands the whole segment (TW*K*4 bytes: 4 KB at
+// K = 2) to the TMA engine with ONE bulk store (cp.async.bulk.global.shared::cta).  The slab then only ever sees full,
+// contiguous writes: k_dense_fast's scattered 4-byte patch stores (two per special tie: 3e7 partial-sector L2 writes per
+// launch at config 3, +30 % write requests) cost it 0.11 ms of its 0.60 ms (measured: the same kernel without them takes
+// 0.497 ms, profiles/r2_dense_experiments.txt).  Two stages per warp: the next row is computed while the engine still reads
+// the previous one (cp.async.bulk.wait_group.read 1 before a stage is refilled).  The patch data of the NEXT row of the
+// warp are requested (one special tie per lane, registers) before the current row is swept, so their latency -- several
+// microseconds under a saturated store stream -- is covered by a whole row of work.
+__device__ __forceinline__ void vm_bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void vm_bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void vm_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void vm_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+#define VM_TMA_NBUF 2
+template <int K>
+struct TmaSmem {
+  static constexpr int TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32, TH = VM_FAST_MAX_TILE_H;
+  float rowbuf[NW][VM_TMA_NBUF][TW * K];  // row-segment stages (slab layout), 128-byte aligned (first member)
+  float qs[K - 1][TW];                    // column terms of the log2-odds
+  float colbuf[K - 1][TW];                // cross-warp column sums
+  float ps[K - 1][TH];                    // row terms
+  int tp0[TH], tp1[TH];                   // special-tie range of every row segment
+  double sm_red[8];
+};
+
+// the lane's 4 ties of chunk `ch` into the stage, in the slab's layout (16-byte shared stores, conflict-free)
+template <int K>
+__device__ __forceinline__ void vm_stage_chunk(float* sb_chunk, int lane, const float* o) {
+  float4* d4 = reinterpret_cast<float4*>(sb_chunk);
+  if (K == 2) {
+    d4[lane] = make_float4(o[0], o[1], o[2], o[3]);
+    d4[32 + lane] = make_float4(o[4], o[5], o[6], o[7]);
+  } else if (K == 4) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) d4[32 * t + lane] = make_float4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
+  } else {  // natural {4i..4i+3}: 4K contiguous floats per lane
+#pragma unroll
+    for (int v = 0; v < K; ++v) d4[K * lane + v] = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+  }
+}
+
+#ifndef VM_TMA_PD
+#define VM_TMA_PD 2  // rows of prefetch distance of the patch entries
+#endif
+template <int K, bool ELBO, int PD = VM_TMA_PD>
+__global__ void __launch_bounds__(VM_DENSE_THREADS, (K == 2 || K == 4) ? 3 : 2) k_dense_tma(const __grid_constant__ vm_ctx c, double* catpart, int rt0, int rtn, int xmode) {
+  constexpr int NCH = DenseCfg<K>::NCH, TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32;
+  extern __shared__ __align__(128) unsigned char vm_tma_smem[];
+  TmaSmem<K>& S = *reinterpret_cast<TmaSmem<K>*>(vm_tma_smem);
+  const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
+  const int ct = blockIdx.x;
+  const int l = blockIdx.y / rtn, rt = rt0 + (blockIdx.y - l * rtn);  // row tiles [rt0, rt0+rtn) of every layer
+  if (!vm_fast_tile<K>(c, l, ct)) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int jt = ct * TW;
+  const int i_lo = rt * (int)c.tile_h;
+  const int nrows = min((int)c.tile_h, nloc - i_lo);
+  const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
+  const float lp0 = (float)lc[VM_LC_LP0(K)], lpk = (float)lc[VM_LC_LPK(K)], epsf = (float)c.eps;
+  double cat = 0.0;
+  const float* patch_src = c.rho_u32;
+  // ---- phase 0: tables of the tile, once per CTA
+  for (int idx = tid; idx < TW; idx += VM_DENSE_THREADS) {
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+      S.qs[k - 1][idx] = __ldg(&c.tab_q[((int64_t)l * N + jt + idx) * K + k]);
+      S.colbuf[k - 1][idx] = 0.f;
+    }
+  }
+  for (int r = tid; r < nrows; r += VM_DENSE_THREADS) {
+    const int64_t lrow = (int64_t)l * nloc + i_lo + r;
+#pragma unroll
+    for (int k = 1; k < K; ++k) S.ps[k - 1][r] = __ldg(&c.tab_p[lrow * K + k]);
+    if (xmode != 1) {
+      S.tp0[r] = __ldg(&c.utile_ptr[lrow * nct + ct]);
+      S.tp1[r] = __ldg(&c.utile_ptr[lrow * nct + ct + 1]);
+    } else {
+      S.tp0[r] = S.tp1[r] = 0;
+    }
+  }
+  __syncthreads();
+  float colacc[NCH][K - 1][4];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+    for (int k = 0; k < K - 1; ++k)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) colacc[ch][k][t] = 0.f;
+  // patch entries of this lane (special tie tp0[row] + lane) for the next PD rows of the warp, fetched PD rows ahead
+  int pq_col[PD];
+  float pq_v[PD][K];
+  auto fetch = [&](int row, int& col, float* v) {
+    col = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = 0.f;
+    if (row < nrows && xmode != 2) {
+      const int ua = S.tp0[row], n = S.tp1[row] - ua;
+      if (lane < n) {
+        col = __ldg(&c.u_col[ua + lane]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = __ldg(&patch_src[(int64_t)(ua + lane) * K + k]);
+      }
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < PD; ++d) fetch(warp + d * NW, pq_col[d], pq_v[d]);
+  float prev[K];
+  int64_t prev_idx = -1;
+#pragma unroll
+  for (int k = 1; k < K; ++k) prev[k] = 0.f;
+  int buf = 0;
+  for (int r = warp; r < nrows; r += NW) {
+    const int64_t lrow = (int64_t)l * nloc + i_lo + r;
+    // ---- request the patch entry of the row PD rows ahead
+    int pn_col;
+    float pn_v[K];
+    fetch(r + PD * NW, pn_col, pn_v);
+    float p[K];
+#pragma unroll
+    for (int k = 1; k < K; ++k) p[k] = S.ps[k - 1][r];
+    float rowacc[K];
+#pragma unroll
+    for (int k = 1; k < K; ++k) rowacc[k] = 0.f;
+    float* sb = S.rowbuf[warp][buf];
+    // the bulk store that last read this stage has finished reading it
+    if (lane == 0) vm_bulk_wait_read<VM_TMA_NBUF - 1>();
+    __syncwarp();
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      float qv[K][4];
+#pragma unroll
+      for (int k = 1; k < K; ++k) vm_load_q4<K>(&S.qs[k - 1][ch * 128], lane, qv[k]);
+      float o[4 * K];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        // identical operation order to vm_formula_rho: s = ((0 + e1) + e2) + ..., inv = rcp(1 + s)
+        float e[K], s = 0.f;
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+          e[k] = vm_ex2(fminf(__fadd_rn(p[k], qv[k][t]), VM_CLAMP_LOG2));
+          s = (k == 1) ? e[k] : __fadd_rn(s, e[k]);
+        }
+        const float inv = vm_rcp(__fadd_rn(1.f, s));
+        o[t * K] = inv;
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+          const float v = __fmul_rn(e[k], inv);
+          o[t * K + k] = v;
+          colacc[ch][k - 1][t] += v;
+          rowacc[k] += v;
+        }
+        if (ELBO) cat += (double)vm_formula_cat<K>(&o[t * K], s, false, lp0, lpk, epsf);
+      }
+      vm_stage_chunk<K>(sb + ch * 128 * K, lane, o);
+      if (ch < 5) {  // step `ch` of the previous row's reduction (same order as warp_sum: 16, 8, 4, 2, 1)
+#pragma unroll
+        for (int k = 1; k < K; ++k) prev[k] += __shfl_down_sync(0xffffffffu, prev[k], 16 >> ch);
+      }
+    }
+#pragma unroll
+    for (int st = NCH; st < 5; ++st) {
+#pragma unroll
+      for (int k = 1; k < K; ++k) prev[k] += __shfl_down_sync(0xffffffffu, prev[k], 16 >> st);
+    }
+    // ---- row partials of the previous row; this row's become `prev`
+    if (prev_idx >= 0 && lane == 0) {
+      c.rowpart[prev_idx] = 0.f;
+#pragma unroll
+      for (int k = 1; k < K; ++k) c.rowpart[prev_idx + k] = prev[k];
+    }
+    prev_idx = (lrow * nct + ct) * K;
+#pragma unroll
+    for (int k = 1; k < K; ++k) prev[k] = rowacc[k];
+    // ---- overwrite the special ties of this row segment in the stage, then hand the segment to the TMA engine
+    __syncwarp();
+    const int ua = S.tp0[r], n = (xmode == 2) ? 0 : S.tp1[r] - ua;
+    if (lane < n && (xmode != 5 || pq_col[0] < 0)) {
+      float* d = sb + (pq_col[0] - jt) * K;
+#pragma unroll
+      for (int k = 0; k < K; ++k) d[k] = pq_v[0][k];
+    }
+    for (int e = 32 + lane; e < n; e += 32) {  // more than 32 special ties in the segment (rare)
+      const int col = __ldg(&c.u_col[ua + e]);
+      float* d = sb + (col - jt) * K;
+#pragma unroll
+      for (int k = 0; k < K; ++k) d[k] = __ldg(&patch_src[(int64_t)(ua + e) * K + k]);
+    }
+    vm_fence_async_smem();
+    __syncwarp();
+    if (lane == 0) vm_bulk_store(c.rho + (lrow * N + jt) * K, sb, (uint32_t)(TW * K * sizeof(float)));
+    buf = (buf + 1 == VM_TMA_NBUF) ? 0 : buf + 1;
+#pragma unroll
+    for (int d = 0; d + 1 < PD; ++d) {
+      pq_col[d] = pq_col[d + 1];
+#pragma unroll
+      for (int k = 0; k < K; ++k) pq_v[d][k] = pq_v[d + 1][k];
+    }
+    pq_col[PD - 1] = pn_col;
+#pragma unroll
+    for (int k = 0; k < K; ++k) pq_v[PD - 1][k] = pn_v[k];
+  }
+  if (prev_idx >= 0) {  // the last row of this warp
+#pragma unroll
+    for (int k = 1; k < K; ++k) prev[k] = warp_sum(prev[k]);
+    if (lane == 0) {
+      c.rowpart[prev_idx] = 0.f;
+#pragma unroll
+      for (int k = 1; k < K; ++k) c.rowpart[prev_idx + k] = prev[k];
+    }
+  }
+  // ---- column partials: combine the 8 warps in a fixed order
+  for (int w = 0; w < NW; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+        for (int k = 1; k < K; ++k)
+#pragma unroll
+          for (int t = 0; t < 4; ++t) S.colbuf[k - 1][ch * 128 + vm_tie_of<K>(lane, t)] += colacc[ch][k - 1][t];
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < TW; idx += VM_DENSE_THREADS) {
+    float* cp = c.colpart + (((int64_t)l * nrt + rt) * N + jt + idx) * K;
+    cp[0] = 0.f;
+#pragma unroll
+    for (int k = 1; k < K; ++k) cp[k] = S.colbuf[k - 1][idx];
+  }
+  if (ELBO) {
+    const double v = block_sum<VM_DENSE_THREADS>(cat, S.sm_red);
+    if (tid == 0) catpart[((int64_t)l * nrt + rt) * nct + ct] = v;
+  }
+  if (lane == 0) vm_bulk_wait_all();  // the stages must outlive the engine's reads
+}
+
 // ---- shortcut ties: the special ties whose posterior needs no fp64 and no entry list ---------------------------------
 // (vm_ctx.simple_mode.)  One thread per special tie u of the rank, in tie order (row-major): a tie with u_px[u] = 0 is
 // not a shortcut tie and is skipped (the special-tie kernel's list mode has it).  A shortcut tie's constants are
@@ -1363,7 +1616,25 @@ struct ScCfg {
 };
 
 template <int K>
-__global__ void __launch_bounds__(VM_SC_THREADS) k_shortcut(const __grid_constant__ vm_ctx c) {
+__device__ __forceinline__ void shortcut_tile(const vm_ctx& c, int ct, int lrt);
+
+// one CTA per tile (grid = full column tiles x (layers * row tiles)), or -- `persistent` -- a fixed number of CTAs that
+// walk the tiles in the same order (so that the kernel holds only its share of every SM while another kernel runs)
+template <int K>
+__global__ void __launch_bounds__(VM_SC_THREADS) k_shortcut(const __grid_constant__ vm_ctx c, int persistent) {
+  if (!persistent) {
+    shortcut_tile<K>(c, blockIdx.x, blockIdx.y);
+    return;
+  }
+  const int nctf = (int)(c.N / DenseCfg<K>::TW), ntile = nctf * (int)(c.L * c.nrt);
+  for (int t = blockIdx.x; t < ntile; t += gridDim.x) {
+    shortcut_tile<K>(c, t % nctf, t / nctf);
+    __syncthreads();  // the tile's shared-memory tables are reused
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void shortcut_tile(const vm_ctx& c, int ct, int lrt) {
   constexpr int NT = NodeTab<K>::STRIDE, TW = DenseCfg<K>::TW, TH = VM_FAST_MAX_TILE_H, RS = ScCfg<K>::RS, UNR = ScCfg<K>::UNR;
   __shared__ __align__(16) float nt_col[TW * NT];
   __shared__ __align__(16) float nt_row[TH * NT];
@@ -1377,8 +1648,7 @@ __global__ void __launch_bounds__(VM_SC_THREADS) k_shortcut(const __grid_constan
   __shared__ float s_lam[3 * K + 1 + K];  // G_lambda_k | G_lambda_k - G_lambda_0 | E[log lambda_k] log2e | G_nu | g_k
   __shared__ double sm_red[VM_SC_THREADS / 32];
   const int N = (int)c.N, nloc = (int)c.nloc, nct = (int)c.nct, nrt = (int)c.nrt;
-  const int ct = blockIdx.x;
-  const int l = blockIdx.y / nrt, rt = blockIdx.y - l * nrt;
+  const int l = lrt / nrt, rt = lrt - l * nrt;
   const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
   if (lc[VM_LC_SIMPLE(K)] == 0.0) return;  // the special-tie kernel has this layer in full
   const int tid = threadIdx.x;
@@ -2052,6 +2322,16 @@ static cudaError_t fast_setup_all() {
   if constexpr (K <= 4) {  // the fast kernel is only instantiated (and eligible) for K <= 4
     cudaError_t e;
     if ((e = fast_setup<K, true>()) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_dense_fast<K, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(FastSmem<K>))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_dense_tma<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(TmaSmem<K>))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_dense_tma<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(TmaSmem<K>))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_dense_tma<K, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(TmaSmem<K>))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_dense_tma<K, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(TmaSmem<K>))) != cudaSuccess) return e;
     return fast_setup<K, false>();
   } else {
     return cudaSuccess;
@@ -2059,7 +2339,53 @@ static cudaError_t fast_setup_all() {
 }
 
 template <int K>
-static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, int rtn) {
+static int launch_special(const vm_ctx* c, int flags, cudaStream_t st, int chunk, int64_t gridx);
+// timing experiment (VM_X_OVERLAP=1|2): the special-tie kernels of a shortcut iteration on the aux stream, next to the
+// dense kernel instead of before it (1: launched before the dense kernel, 2: after it)
+static int vm_x_overlap() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VM_X_OVERLAP");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+static int vm_x_nopatch() {  // VM_X_NOPATCH=1: the fast dense kernel leaves the special ties unpatched (timing experiment)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VM_X_NOPATCH");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+static int vm_x_notma() {  // VM_X_NOTMA=1: the STG.128 fast dense kernel instead of the TMA one (A/B)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VM_X_NOTMA");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+static int vm_x_tma_mode() {  // VM_X_TMA_MODE: 1 = no patching at all, 3 / 4 = prefetch distance 1 / 3 (timing experiments)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VM_X_TMA_MODE");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+static int vm_x_persist() {  // VM_X_PERSIST=n: k_shortcut as n persistent CTAs
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VM_X_PERSIST");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+template <int K>
+static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, int rtn, int sparse_on_aux = 0) {
   if (rtn <= 0) return 0;
   const dim3 grid((unsigned)c->nct, (unsigned)(c->L * rtn));
   const bool elbo = flags & VM_F_ELBO, store = !(flags & VM_F_NO_STORE), csr = c->r_mode == VM_R_CSR;
@@ -2093,10 +2419,18 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, in
     cudaEventRecord(ev_fork, st);
     cudaStreamWaitEvent(aux, ev_fork, 0);
   }
+  if (side && sparse_on_aux == 1) launch_special<K>(c, flags, aux, -1, c->n_ublk);
 #define LF()                                                                                                             \
   do {                                                                                                                   \
     if constexpr (K <= 4) {                                                                                              \
-      if (elbo) k_dense_fast<K, true><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<K>), st>>>(*c, cp, rt0, rtn);              \
+      if (!vm_x_notma()) {                                                                                               \
+        const int xm = vm_x_tma_mode();                                                                                  \
+        if (elbo) k_dense_tma<K, true><<<grid, VM_DENSE_THREADS, sizeof(TmaSmem<K>), st>>>(*c, cp, rt0, rtn, 0);          \
+        else if (xm == 3) k_dense_tma<K, false, 1><<<grid, VM_DENSE_THREADS, sizeof(TmaSmem<K>), st>>>(*c, cp, rt0, rtn, 0); \
+        else if (xm == 4) k_dense_tma<K, false, 3><<<grid, VM_DENSE_THREADS, sizeof(TmaSmem<K>), st>>>(*c, cp, rt0, rtn, 0); \
+        else k_dense_tma<K, false><<<grid, VM_DENSE_THREADS, sizeof(TmaSmem<K>), st>>>(*c, cp, rt0, rtn, xm);             \
+      } else if (elbo) k_dense_fast<K, true><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<K>), st>>>(*c, cp, rt0, rtn);       \
+      else if (vm_x_nopatch()) k_dense_fast<K, false, false><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<K>), st>>>(*c, cp, rt0, rtn); \
       else k_dense_fast<K, false><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<K>), st>>>(*c, cp, rt0, rtn);                  \
     }                                                                                                                    \
   } while (0)
@@ -2114,6 +2448,7 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, in
 #undef LD
   if (side) {
     LF();
+    if (sparse_on_aux == 2) launch_special<K>(c, flags, aux, -1, c->n_ublk);
     cudaEventRecord(ev_join, aux);
     cudaStreamWaitEvent(st, ev_join, 0);
     if (own_events) {
@@ -2137,9 +2472,13 @@ static int launch_special(const vm_ctx* c, int flags, cudaStream_t st, int chunk
       // that list only; k_sums_stage1 reads as many partial slots) while k_shortcut evaluates the shortcut ties
       const dim3 gridl((unsigned)(c->n_cxblk > 0 ? c->n_cxblk : 1), (unsigned)c->L);
       k_special<K, false, VM_R_EGO, 1><<<gridl, 256, 0, st>>>(*c, region_u(c), chunk);
-      k_special<K, false, VM_R_EGO, 2><<<grid, 256, 0, st>>>(*c, region_u(c), chunk);  // layers that cannot
-      if (c->N / DenseCfg<K>::TW > 0)
-        k_shortcut<K><<<dim3((unsigned)(c->N / DenseCfg<K>::TW), (unsigned)(c->L * c->nrt)), VM_SC_THREADS, 0, st>>>(*c);
+      const dim3 grid2((unsigned)imin64(gridx, 148 * 2), (unsigned)c->L);
+      k_special<K, false, VM_R_EGO, 2><<<grid2, 256, 0, st>>>(*c, region_u(c), chunk);  // layers that cannot
+      if (c->N / DenseCfg<K>::TW > 0) {
+        const int pg = vm_x_persist();
+        if (pg > 0) k_shortcut<K><<<(unsigned)pg, VM_SC_THREADS, 0, st>>>(*c, 1);
+        else k_shortcut<K><<<dim3((unsigned)(c->N / DenseCfg<K>::TW), (unsigned)(c->L * c->nrt)), VM_SC_THREADS, 0, st>>>(*c, 0);
+      }
     }
   } else if (c->r_mode == VM_R_EGO) {
     if (elbo) LS(true, VM_R_EGO); else LS(false, VM_R_EGO);
@@ -2159,6 +2498,8 @@ static int launch_rho_kernels(const vm_ctx* c, int flags, cudaStream_t st) {
   int rc;
   cudaStream_t aux = (cudaStream_t)c->aux_stream;
   if (c->n_chunks != VM_NCHUNK || aux == nullptr || aux == st) {
+    if (vm_x_overlap() && aux != nullptr && aux != st && simple_iteration<K>(c, flags))
+      return launch_dense<K>(c, flags, st, 0, (int)c->nrt, vm_x_overlap());
     if ((rc = launch_special<K>(c, flags, st, -1, c->n_ublk))) return rc;
     return launch_dense<K>(c, flags, st, 0, (int)c->nrt);
   }

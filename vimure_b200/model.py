@@ -127,7 +127,7 @@ class VimureModel(TransformerMixin, BaseEstimator):
         self.L, self.N, self.M = int(shape[0]), int(shape[1]), int(shape[3])
         self.X = sptensor(tuple(subs), vals, shape=shape)
         self.subs_nz = self.X.subs
-        self.sumX = self.X.vals.sum()
+        self.sumX = None  # sum of all counts: from the packer (one rank) or a host sum (several), see fit
 
         # ---- K (model.py:179-196)
         if K_in is None:
@@ -251,6 +251,8 @@ class VimureModel(TransformerMixin, BaseEstimator):
             self._packed = P = _packing.pack(self.X.subs, self.X.vals, self.L, self.N, self.M, self.K, self.R, dev,
                                              row0=row0, nloc=nloc, tile_h=int(extra_params.get("tile_h", 128)),
                                              mutuality=self.mutuality, split_e0=split_e0)
+            # nu_rte = beta + sum X (model.py:593-595): the packer already summed the counts of the rows it owns
+            self.sumX = float(P.sumX) if (world == 1 and getattr(P, "sumX", None) is not None) else float(self.X.vals.sum())
             if world > 1 and extra_params.get("presharded", False):
                 # the sum of all counts (nu_rte = beta + sum X, model.py:593-595) from the ranks' own rows
                 if "K" not in extra_params or extra_params["K"] is None:
