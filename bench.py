@@ -645,7 +645,9 @@ def run_workload(args, config, N, L, K, steps, warmup, dist, world, rank, dev, d
             d2h = model.gamma_shp.nbytes * 4 + model.phi_shp.nbytes * 4 + 8 * (2 + len(model.trace))
             torch.cuda.synchronize(dev)
             wall = allmax(time.time() - t0)
-            runs.append((wall, model.pack_time, {k: round(v, 4) for k, v in model.timings.items()}, d2h))
+            tm = {k: round(v, 4) for k, v in model.timings.items()}
+            tm["batch_ms_per_iteration"] = [round(float(v) * 1e3, 3) for v in model.trace["runtime"]]
+            runs.append((wall, model.pack_time, tm, d2h))
             del model
         wall, pack_t, timings, d2h = sorted(runs, key=lambda r_: r_[0])[1]
         warm = sorted(r_[0] for r_ in runs[1:])[0]

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VM_ABI_VERSION 13
+#define VM_ABI_VERSION 14
 
 /* reporter-mask structure (how R[l,i,j,m] is represented) */
 #define VM_R_EGO 0 /* reporter m == node m reports row m and column m (vimure synthetic.py:1184-1204, _io.py:229-242) */
@@ -73,8 +73,6 @@ extern "C" {
 #ifndef VM_SPECIAL_TIES_PER_BLOCK /* (a timing variant may be built with a multiple of it: tools/ab_libs.py) */
 #define VM_SPECIAL_TIES_PER_BLOCK 1024
 #endif
-/* row chunks of the special/dense overlap */
-#define VM_NCHUNK 4
 
 typedef struct vm_ctx {
   /* ---- dimensions ---- */
@@ -93,16 +91,9 @@ typedef struct vm_ctx {
   int64_t phi_chunk;        /* entries per block in the phi pass */
   int64_t n_phichunk;       /* max over layers of ceil(entries_in_layer/phi_chunk) */
   int64_t n_ublk;           /* blocks per layer of the special-tie kernel */
-  /* row chunks for overlapping the special-tie kernel (aux stream) with the dense kernel (main stream): dense chunk c
-     covers row tiles [rt_end[c-1], rt_end[c]) of every layer and may start once special-tie blocks < sp_chunk_blk[l][c+1]
-     of every layer are done.  n_chunks = 0 or aux_stream = NULL: serial. */
-  int64_t n_chunks;         /* 0 or VM_NCHUNK */
-  int64_t rt_end0, rt_end1, rt_end2, rt_end3;      /* cumulative row-tile ends of the chunks */
-  int64_t sp_grid0, sp_grid1, sp_grid2, sp_grid3;  /* blocks per layer (max over layers) of each special-tie chunk */
   void* aux_stream;         /* cudaStream_t owned by the caller */
   void* ev_fork;            /* two cudaEvent_t (timing disabled) owned by the caller, used to fork the aux stream from and */
   void* ev_join;            /*   join it back into the main one; NULL: the library creates and destroys a pair per launch */
-  const int64_t* sp_chunk_blk; /* [L*(VM_NCHUNK+1)] first special-tie block of each chunk, per layer */
   double eps;               /* EPS, model.py:215-218 */
   double alpha_eta, beta_eta;
   double b_all;             /* sum of t_x: the eta part of the ELBO when no tie has underflowed completely */

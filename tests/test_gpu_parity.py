@@ -41,7 +41,7 @@ def build_inputs(g, structured=False):
     return X, R
 
 
-def make_engine(g, row0=0, nloc=None, structured=True, tile_h=64, overlap=None):
+def make_engine(g, row0=0, nloc=None, structured=True, tile_h=64):
     torch = _cuda()
     import vimure_b200 as vm
     from vimure_b200 import _packing
@@ -52,7 +52,7 @@ def make_engine(g, row0=0, nloc=None, structured=True, tile_h=64, overlap=None):
     P = _packing.pack(g.X_subs, g.X_vals, g.L, g.N, g.M, g.K, mask, "cuda", row0=row0, nloc=nloc, tile_h=tile_h,
                       mutuality=g.mutuality)
     eps = g.fit_kwargs.get("EPS", 1e-12)
-    eng = CaviEngine(P, g.priors(), mutuality=g.mutuality, eps=eps, overlap=overlap)
+    eng = CaviEngine(P, g.priors(), mutuality=g.mutuality, eps=eps)
     st = g.init_state()
     # prior of the special ties from the injected (l,i,j) -> values
     flat = P.t["u_gflat"].cpu().numpy()
@@ -244,19 +244,20 @@ def test_device_special_functions():
     np.testing.assert_allclose(lg.cpu().numpy(), sp.gammaln(x), rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize("name", ["gm_l2_k3", "dense_reporting", "custom_mask"])
-def test_two_stream_overlap_option_is_equivalent(name):
-    """The optional special/dense overlap on two streams (row chunks) must give the same trajectory."""
+@pytest.mark.parametrize("name", ["gm_l2_k3", "dense_reporting", "custom_mask", "sbm_n520"])
+def test_two_engines_are_bit_identical(name):
+    """Every reduction has a fixed order and the per-reporter corrections are integer atomics: two engines over the same
+    packed problem (different tile heights for the small ones) give the same bits, slab included."""
     g = Golden(name)
-    a, _ = make_engine(g, tile_h=8, overlap=False)
-    b, _ = make_engine(g, tile_h=8, overlap=True)
+    a, _ = make_engine(g, tile_h=8 if g.N < 512 else 128)
+    b, _ = make_engine(g, tile_h=8 if g.N < 512 else 128)
     for it in range(4):
-        a.iterate(1, elbo_last=True)
-        b.iterate(1, elbo_last=True)
+        a.iterate(1, elbo_last=(it % 2 == 1))
+        b.iterate(1, elbo_last=(it % 2 == 1))
         pa, pb = a.params(), b.params()
         for k in ("gamma_shp", "gamma_rte", "phi_shp", "phi_rte", "nu_shp"):
             np.testing.assert_array_equal(pa[k], pb[k])
-        assert a.elbo() == b.elbo()
+    assert a.elbo() == b.elbo()
     import torch
 
     assert torch.equal(a.rho_slab(), b.rho_slab())

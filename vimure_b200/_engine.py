@@ -21,7 +21,7 @@ def _packing_const():
 
 
 class CaviEngine:
-    def __init__(self, packed, priors, mutuality=True, eps=1e-12, group=None, may_dead=False, overlap=None):
+    def __init__(self, packed, priors, mutuality=True, eps=1e-12, group=None, may_dead=False):
         P = self.P = packed
         if not torch.cuda.is_available():
             raise RuntimeError("vimure_b200 needs a CUDA device: the CAVI kernels have no CPU fallback")
@@ -76,7 +76,7 @@ class CaviEngine:
         self.fixG = torch.zeros(L * M, dtype=torch.int64, device=dev)
         self.phi0 = z(L * K)
         # simple special ties (see include/vimure_b200.h): patch source of the fast dense kernel, their phi0 part
-        self.simple_mode = bool(getattr(P, "simple_ok", False)) and not overlap
+        self.simple_mode = bool(getattr(P, "simple_ok", False))
         self.u_rec = torch.zeros(max(U, 1) if self.simple_mode else 1, 4 if K == 2 else 8, **f32)
         stride = 4 if K == 2 else (8 if K <= 6 else K + 2)
         self.nodetab = torch.zeros(L * N * stride if self.simple_mode else 4, **f32)
@@ -110,25 +110,9 @@ class CaviEngine:
         c.simple_mode = int(self.simple_mode)
         c.n_cx = int(getattr(P, "n_cx", U))
         c.n_cxblk = int(getattr(P, "n_cxblk", P.n_ublk))
-        # special/dense overlap: worthwhile once the special-tie kernel is long enough to matter
-        self.aux_stream = None
-        if overlap is None:
-            # measured on B200 at config 3: 1.55 ms/iteration with the overlap vs 1.46 ms serial -- both kernels need the
-            # occupancy the other one takes away.  Kept as an option, off by default.
-            overlap = False
-        if overlap:
-            assert self.C["VM_NCHUNK"] == len(P.rt_end)
-            self.aux_stream = torch.cuda.Stream(device=dev, priority=-1)  # higher priority than the main stream
-            c.n_chunks = len(P.rt_end)
-            c.rt_end0, c.rt_end1, c.rt_end2, c.rt_end3 = (int(v) for v in P.rt_end)
-            c.sp_grid0, c.sp_grid1, c.sp_grid2, c.sp_grid3 = (int(v) for v in P.sp_grid)
-            c.aux_stream = self.aux_stream.cuda_stream
-        else:
-            # serial special -> dense; the aux stream only carries the general dense kernel (partial column tiles) under
-            # the fast one (see launch_dense)
-            self.aux_stream = torch.cuda.Stream(device=dev)
-            c.n_chunks = 0
-            c.aux_stream = self.aux_stream.cuda_stream
+        # the aux stream carries the general dense kernel (partial column tiles) under the fast one (see launch_dense)
+        self.aux_stream = torch.cuda.Stream(device=dev)
+        c.aux_stream = self.aux_stream.cuda_stream
         self._keep = []
 
         def ptr(t):
@@ -136,7 +120,7 @@ class CaviEngine:
             return t.data_ptr() if t.numel() else self._dummy.data_ptr()
 
         for name in ("u_lrow", "u_col", "u_ptr", "u_cnt", "u_m0", "u_x0", "u_xT0", "utile_ptr", "e_u", "e_m", "e_x", "e_xT",
-                     "e_flags", "f_u", "f_m", "f_x", "f_xT", "lay_eptr", "g0", "u_x0sum", "sp_chunk_blk", "g_chunk_ptr", "g_chunk_lm", "g_u", "g_x", "g_xT", "g_lm_cptr", "t_u", "t_lrow",
+                     "e_flags", "f_u", "f_m", "f_x", "f_xT", "lay_eptr", "g0", "u_x0sum", "g_chunk_ptr", "g_chunk_lm", "g_u", "g_x", "g_xT", "g_lm_cptr", "t_u", "t_lrow",
                      "t_col", "t_x", "rep", "r_ptr", "r_m", "r_val", "c_ptr", "c_tie", "cx_idx", "cx_ptr", "cx_lrow", "cx_col", "cx_cnt",
                      "cx_m0", "cx_x0", "cx_xT0", "cx_x0sum", "u_px", "u_pxt"):
             setattr(c, name, ptr(P.t[name]) if name in P.t else self._dummy.data_ptr())
@@ -169,12 +153,10 @@ class CaviEngine:
         csr, ego = P.r_mode == 2, P.r_mode == 0
         fast = (P.K <= 4 and store and not csr and (P.N * P.K) % 4 == 0 and P.N >= P.tile_w
                 and P.tile_h <= 128)
-        nch = self.ctx.n_chunks if self.ctx.n_chunks else 1  # special / dense are launched once per row chunk
-        n_special = sum(1 for q in range(nch) if self.P.sp_grid[q] > 0) if self.ctx.n_chunks else 1
-        n = 2 + 3 + 1 + (0 if csr else 1) + n_special + nch * ((1 if fast else 0) + 1) + (1 if ego else 0) + 1 + 2 + 1
+        n = 2 + 3 + 1 + (0 if csr else 1) + 1 + (1 if fast else 0) + 1 + (1 if ego else 0) + 1 + 2 + 1
         if elbo:
             n += 1 + (1 if self.mutuality else 0)
-        elif self.simple_mode and fast and not self.ctx.n_chunks:
+        elif self.simple_mode and fast:
             n += 2  # the special-tie kernel is launched twice (layers that take the shortcut / that cannot) + k_shortcut
         return n
 
@@ -279,6 +261,9 @@ class CaviEngine:
     def _graph(self, flags):
         g = self._graphs.get(flags)
         if g is None:
+            import time
+
+            t_cap = time.time()
             # Explicit capture_begin/capture_end on a side stream instead of the `torch.cuda.graph` context manager: that
             # one runs gc.collect() and torch.cuda.empty_cache() on entry (hundreds of ms once the caching allocator holds
             # many blocks), which a capture that allocates nothing does not need.  Capture only: nothing executes, the
@@ -302,6 +287,7 @@ class CaviEngine:
                 _capi.check(rc, "vm_iteration (capture)")
             cur.wait_stream(side)
             self._graphs[flags] = g
+            self.capture_s = getattr(self, "capture_s", 0.0) + time.time() - t_cap
         return g
 
     # single phases, for tests that emulate several ranks on one GPU

@@ -20,7 +20,6 @@ def dense_tile_w(K):
 GAMMA_CHUNK = 256
 PHI_CHUNK = 4096
 SPECIAL_TIES_PER_BLOCK = 1024  # == VM_SPECIAL_TIES_PER_BLOCK of include/vimure_b200.h
-NCHUNK = 4  # == VM_NCHUNK
 
 
 def _i32(t):
@@ -63,24 +62,6 @@ class Packed:
         if k in t:
             return t[k]
         raise AttributeError(k)
-
-
-def _overlap_chunks(P, L, nloc, dev):
-    """Row chunks for the optional special/dense overlap (vm_ctx.n_chunks): dense chunk c covers row tiles
-    [rt_end[c-1], rt_end[c]); it may start once the special-tie blocks below sp_chunk_blk[l][c+1] are done."""
-    rt_end = [min(P.nrt, -(-P.nrt * (q + 1) // NCHUNK)) for q in range(NCHUNK)]
-    P.rt_end = rt_end
-    row_end = [min(nloc, e * P.tile_h) for e in rt_end]
-    lidx = torch.arange(L, device=dev, dtype=torch.int64)
-    u0_l = P.t["utile_ptr"][(lidx * nloc) * P.nct].to(torch.int64)
-    blk = [torch.zeros(L, dtype=torch.int64, device=dev)]
-    for q in range(NCHUNK):
-        u_end = P.t["utile_ptr"][(lidx * nloc + row_end[q]) * P.nct].to(torch.int64)
-        blk.append((u_end - u0_l + SPECIAL_TIES_PER_BLOCK - 1) // SPECIAL_TIES_PER_BLOCK)
-    blk = torch.stack(blk, dim=1)  # [L, NCHUNK+1]
-    blk = torch.cummax(blk, dim=1)[0]
-    P.t["sp_chunk_blk"] = blk.contiguous().flatten()
-    P.sp_grid = [int(v) for v in (blk[:, 1:] - blk[:, :-1]).max(dim=0)[0].cpu()]
 
 
 def pack_device(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64, mutuality=True, split_e0=True,
@@ -216,7 +197,6 @@ def pack_device(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, til
     P.ego_diag = int(getattr(mask, "diag", False))
     if ego:
         P.t["rep"] = rep
-    _overlap_chunks(P, L, nloc, dev)
     _mark("finish")
     return P
 

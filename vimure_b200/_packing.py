@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 
-from ._pack_native import (GAMMA_CHUNK, NCHUNK, PHI_CHUNK, SPECIAL_TIES_PER_BLOCK, Packed, _Trace, _i32, _overlap_chunks,  # noqa: F401
+from ._pack_native import (GAMMA_CHUNK, PHI_CHUNK, SPECIAL_TIES_PER_BLOCK, Packed, _Trace, _i32,  # noqa: F401
                            dense_tile_w, pack_device)
 
 
@@ -187,7 +187,6 @@ def pack_torch(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile
     n_ul = (P.t["utile_ptr"][:: nloc * P.nct][1:] - P.t["utile_ptr"][:: nloc * P.nct][:-1]) if U else None
     max_ul = int(n_ul.max()) if U else 0
     P.n_ublk = max(1, (max_ul + SPECIAL_TIES_PER_BLOCK - 1) // SPECIAL_TIES_PER_BLOCK)
-    _overlap_chunks(P, L, nloc, dev)
 
     _mark("tile/col pointers")
     # ---- layer ranges and reporter chunks of the entries

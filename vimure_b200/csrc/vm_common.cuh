@@ -168,6 +168,7 @@ __device__ __forceinline__ void vm_formula_rho(const float* a, bool may_dead, fl
 
 // log1p for fp32: series below 0.05 (exact to ~1e-10 relative), MUFU-based above
 __device__ __forceinline__ float vm_log1p_fast(float x) {
+  if (fabsf(x) < 4e-4f) return x * (1.f - 0.5f * x);  // (the usual case: x ~ EPS; truncation x^2/3 < 6e-8 relative)
   if (fabsf(x) < 0.05f) {
     const float t = -0.16666667f;
     return x * (1.f + x * (-0.5f + x * (0.33333334f + x * (-0.25f + x * (0.2f + x * t)))));

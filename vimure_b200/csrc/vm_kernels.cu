@@ -540,19 +540,12 @@ __device__ __forceinline__ void vm_fix_accumulate(unsigned long long* fix_l, boo
 // layer).  LIST = 2 handles the other layers exactly like LIST = 0.  Each block of a (layer, block) grid does its work
 // in exactly one of the two launches and returns in the other.
 template <int K, bool ELBO, int RMODE, int LIST = 0>
-__global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) : 2)) k_special(const __grid_constant__ vm_ctx c, double* part, int chunk) {
+__global__ void __launch_bounds__(256, (K <= 2 ? (ELBO ? 3 : VM_SPECIAL_MINBLK) : 2)) k_special(const __grid_constant__ vm_ctx c, double* part) {
   __shared__ double s_Gl[K], s_Ell[K], s_El[K];
   const int l = blockIdx.y;
   const int nloc = (int)c.nloc, nct = (int)c.nct, N = (int)c.N, M = (int)c.M, row0 = (int)c.row0;
   const int u0 = c.utile_ptr[(int64_t)l * nloc * nct], u1 = c.utile_ptr[(int64_t)(l + 1) * nloc * nct];
-  // block index within the layer (chunked launches cover a sub-range of the layer's blocks)
-  int blk = blockIdx.x;
-  if (chunk >= 0) {
-    const int64_t b0 = c.sp_chunk_blk[(int64_t)l * (VM_NCHUNK + 1) + chunk];
-    const int64_t b1 = c.sp_chunk_blk[(int64_t)l * (VM_NCHUNK + 1) + chunk + 1];
-    blk += (int)b0;
-    if (blk >= b1) return;
-  }
+  int blk = blockIdx.x;  // block index within the layer
   constexpr bool elbo = ELBO;
   constexpr bool COOP = (RMODE != VM_R_EGO);
   const bool mut = c.mutuality != 0;
@@ -1146,7 +1139,7 @@ struct FastSmem {
   double sm_red[8];
 };
 
-template <int K, bool ELBO, bool PATCH = true>
+template <int K, bool ELBO>
 __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_MINBLK2 : 2) k_dense_fast(const __grid_constant__ vm_ctx c, double* catpart, int rt0, int rtn) {
   constexpr int NCH = DenseCfg<K>::NCH, TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32, CAPW = FastCfg<K>::CAPW;
   extern __shared__ __align__(16) unsigned char vm_fast_smem[];
@@ -1175,14 +1168,12 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
     const int64_t lrow = (int64_t)l * nloc + i_lo + r;
 #pragma unroll
     for (int k = 1; k < K; ++k) S.ps[k - 1][r] = __ldg(&c.tab_p[lrow * K + k]);
-    if (PATCH) {
-      S.tp0[r] = __ldg(&c.utile_ptr[lrow * nct + ct]);
-      S.tp1[r] = __ldg(&c.utile_ptr[lrow * nct + ct + 1]);
-    }
+    S.tp0[r] = __ldg(&c.utile_ptr[lrow * nct + ct]);
+    S.tp1[r] = __ldg(&c.utile_ptr[lrow * nct + ct + 1]);
   }
   __syncthreads();
   // ---- phase 1: stage the patch data of this warp's rows asynchronously
-  if (PATCH) {
+  {
     int off = 0;
     for (int r = warp; r < nrows; r += NW) {
       const int ua = S.tp0[r], n = S.tp1[r] - ua;
@@ -1269,7 +1260,6 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K <= 2 && !ELBO) ? VM_FAST_
 #pragma unroll
     for (int k = 1; k < K; ++k) prev[k] = rowacc[k];
     // ---- patch the special ties of this row segment (after the row's own stores)
-    if (!PATCH) continue;
     if (!waited) {
       vm_cp_async_wait_all();
       waited = true;
@@ -1384,7 +1374,7 @@ __device__ __forceinline__ void vm_stage_chunk(float* sb_chunk, int lane, const 
 #define VM_TMA_PD 2  // rows of prefetch distance of the patch entries
 #endif
 template <int K, bool ELBO, int PD = VM_TMA_PD>
-__global__ void __launch_bounds__(VM_DENSE_THREADS, (K == 2 || K == 4) ? 3 : 2) k_dense_tma(const __grid_constant__ vm_ctx c, double* catpart, int rt0, int rtn, int xmode) {
+__global__ void __launch_bounds__(VM_DENSE_THREADS, (K == 2 || K == 4) ? 3 : 2) k_dense_tma(const __grid_constant__ vm_ctx c, double* catpart, int rt0, int rtn) {
   constexpr int NCH = DenseCfg<K>::NCH, TW = DenseCfg<K>::TW, NW = VM_DENSE_THREADS / 32;
   extern __shared__ __align__(128) unsigned char vm_tma_smem[];
   TmaSmem<K>& S = *reinterpret_cast<TmaSmem<K>*>(vm_tma_smem);
@@ -1412,12 +1402,8 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K == 2 || K == 4) ? 3 : 2) 
     const int64_t lrow = (int64_t)l * nloc + i_lo + r;
 #pragma unroll
     for (int k = 1; k < K; ++k) S.ps[k - 1][r] = __ldg(&c.tab_p[lrow * K + k]);
-    if (xmode != 1) {
-      S.tp0[r] = __ldg(&c.utile_ptr[lrow * nct + ct]);
-      S.tp1[r] = __ldg(&c.utile_ptr[lrow * nct + ct + 1]);
-    } else {
-      S.tp0[r] = S.tp1[r] = 0;
-    }
+    S.tp0[r] = __ldg(&c.utile_ptr[lrow * nct + ct]);
+    S.tp1[r] = __ldg(&c.utile_ptr[lrow * nct + ct + 1]);
   }
   __syncthreads();
   float colacc[NCH][K - 1][4];
@@ -1434,7 +1420,7 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K == 2 || K == 4) ? 3 : 2) 
     col = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = 0.f;
-    if (row < nrows && xmode != 2) {
+    if (row < nrows) {
       const int ua = S.tp0[row], n = S.tp1[row] - ua;
       if (lane < n) {
         col = __ldg(&c.u_col[ua + lane]);
@@ -1514,8 +1500,8 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K == 2 || K == 4) ? 3 : 2) 
     for (int k = 1; k < K; ++k) prev[k] = rowacc[k];
     // ---- overwrite the special ties of this row segment in the stage, then hand the segment to the TMA engine
     __syncwarp();
-    const int ua = S.tp0[r], n = (xmode == 2) ? 0 : S.tp1[r] - ua;
-    if (lane < n && (xmode != 5 || pq_col[0] < 0)) {
+    const int ua = S.tp0[r], n = S.tp1[r] - ua;
+    if (lane < n) {
       float* d = sb + (pq_col[0] - jt) * K;
 #pragma unroll
       for (int k = 0; k < K; ++k) d[k] = pq_v[0][k];
@@ -1599,12 +1585,17 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K == 2 || K == 4) ? 3 : 2) 
 // store), so every thread keeps VM_SC_UNR ties in flight: their records (one 16/32-byte load each: column, X, +-x^T, lo_k
 // packed per tie in `u_rec`) are requested together before any is evaluated, and the tie -> row-segment map is a byte
 // table in shared memory filled once per CTA instead of a binary search per tie.
-// 64-bit add into a (lo, hi) pair of shared 32-bit words with two native atomics (modular arithmetic: exact)
-__device__ __forceinline__ void vm_smem_add64(unsigned int* w, long long v) {
-  const unsigned int lo = (unsigned int)(unsigned long long)v, hi = (unsigned int)((unsigned long long)v >> 32);
-  const unsigned int old = atomicAdd(&w[0], lo);
-  const unsigned int carry = (old + lo < old) ? 1u : 0u;
-  if (hi + carry != 0u) atomicAdd(&w[1], hi + carry);
+// A fixed-point correction fq (|fq| <= 2^44) is accumulated in shared memory as TWO 32-bit words, fq = hi * 2^22 + lo with
+// lo = the low 22 bits (unsigned) and hi = fq >> 22 (signed, |hi| <= 2^22): a node of a tile receives at most TW = 512
+// terms, so neither word can overflow (512 * 2^22 = 2^31), the two native 32-bit adds need no carry -- hence no returned
+// value to wait for: a 64-bit shared-memory atomic is a compare-and-swap spin loop (ATOMS.CAST.SPIN.64), and a carry taken
+// from the returned old value exposed the atomic's latency twice per tie and category -- and the sum is exact.
+__device__ __forceinline__ void vm_smem_add_split(unsigned int* w, long long v) {
+  atomicAdd(&w[0], (unsigned int)((unsigned long long)v & 0x3fffffull));
+  atomicAdd(&w[1], (unsigned int)(int)(v >> 22));
+}
+__device__ __forceinline__ unsigned long long vm_smem_split_value(const unsigned int* w) {
+  return (unsigned long long)((long long)(int)w[1] * 4194304ll + (long long)w[0]);
 }
 
 #define VM_SC_THREADS 256
@@ -1616,32 +1607,13 @@ struct ScCfg {
 };
 
 template <int K>
-__device__ __forceinline__ void shortcut_tile(const vm_ctx& c, int ct, int lrt);
-
-// one CTA per tile (grid = full column tiles x (layers * row tiles)), or -- `persistent` -- a fixed number of CTAs that
-// walk the tiles in the same order (so that the kernel holds only its share of every SM while another kernel runs)
-template <int K>
-__global__ void __launch_bounds__(VM_SC_THREADS) k_shortcut(const __grid_constant__ vm_ctx c, int persistent) {
-  if (!persistent) {
-    shortcut_tile<K>(c, blockIdx.x, blockIdx.y);
-    return;
-  }
-  const int nctf = (int)(c.N / DenseCfg<K>::TW), ntile = nctf * (int)(c.L * c.nrt);
-  for (int t = blockIdx.x; t < ntile; t += gridDim.x) {
-    shortcut_tile<K>(c, t % nctf, t / nctf);
-    __syncthreads();  // the tile's shared-memory tables are reused
-  }
-}
-
-template <int K>
-__device__ __forceinline__ void shortcut_tile(const vm_ctx& c, int ct, int lrt) {
+__global__ void __launch_bounds__(VM_SC_THREADS) k_shortcut(const __grid_constant__ vm_ctx c) {
+  const int ct = blockIdx.x, lrt = blockIdx.y;
   constexpr int NT = NodeTab<K>::STRIDE, TW = DenseCfg<K>::TW, TH = VM_FAST_MAX_TILE_H, RS = ScCfg<K>::RS, UNR = ScCfg<K>::UNR;
   __shared__ __align__(16) float nt_col[TW * NT];
   __shared__ __align__(16) float nt_row[TH * NT];
   __shared__ float s_tabp[TH][K - 1];
-  // 64-bit fixed-point accumulators as (lo, hi) pairs of 32-bit words: a 64-bit shared-memory atomic add is a
-  // compare-and-swap spin loop (ATOMS.CAST.SPIN.64), slow under the contention of a row's ~19 ties; two native 32-bit
-  // adds with the carry taken from the returned old value are exact and cheap
+  // fixed-point accumulators as (low 22 bits, rest) pairs of 32-bit words, see vm_smem_add_split
   __shared__ unsigned int colfix[TW][K - 1][2], rowfix[TH][K - 1][2];
   __shared__ int s_tp0[TH], s_off[TH + 1];
   __shared__ unsigned char s_row[VM_SC_MAXE];
@@ -1802,8 +1774,8 @@ __device__ __forceinline__ void shortcut_tile(const vm_ctx& c, int ct, int lrt) 
         nu_t += rho[k] * iden[k];
         const long long fq = __double2ll_rn(((double)rho[k] - (double)__fmul_rn(ef[k], invf)) * VM_FIX_SCALE);
         if (fq != 0) {
-          if (act_j) vm_smem_add64(colfix[cj][k - 1], fq);
-          if (act_i) vm_smem_add64(rowfix[r][k - 1], fq);
+          if (act_j) vm_smem_add_split(colfix[cj][k - 1], fq);
+          if (act_i) vm_smem_add_split(rowfix[r][k - 1], fq);
         }
       }
       float* ru = c.rho_u32 + u * K;
@@ -1825,13 +1797,11 @@ __device__ __forceinline__ void shortcut_tile(const vm_ctx& c, int ct, int lrt) 
   // ---- flush: one global atomic per touched node and category
   unsigned long long* fix_l = reinterpret_cast<unsigned long long*>(c.fixA) + (int64_t)l * c.M * K;
   for (int t = tid; t < TW * (K - 1); t += VM_SC_THREADS) {
-    const unsigned int* w = &colfix[0][0][0] + 2 * t;
-    const unsigned long long v = ((unsigned long long)w[1] << 32) | w[0];
+    const unsigned long long v = vm_smem_split_value(&colfix[0][0][0] + 2 * t);
     if (v != 0ull) atomicAdd(fix_l + (int64_t)(jt + t / (K - 1)) * K + 1 + t % (K - 1), v);
   }
   for (int t = tid; t < nrows * (K - 1); t += VM_SC_THREADS) {
-    const unsigned int* w = &rowfix[0][0][0] + 2 * t;
-    const unsigned long long v = ((unsigned long long)w[1] << 32) | w[0];
+    const unsigned long long v = vm_smem_split_value(&rowfix[0][0][0] + 2 * t);
     if (v != 0ull) atomicAdd(fix_l + (int64_t)((int)c.row0 + i_lo + t / (K - 1)) * K + 1 + t % (K - 1), v);
   }
   // rho_k X of the SIMPLE ties (their part of the next phi-shape sums) and the nu statistic of the SINGLE ties
@@ -2303,8 +2273,7 @@ static bool dense_fast_eligible(const vm_ctx* c, int flags) {
 // ... and do the fast dense kernel / the list mode of the special-tie kernel handle the simple special ties in it?
 template <int K>
 static bool simple_iteration(const vm_ctx* c, int flags) {
-  return c->simple_mode != 0 && c->r_mode == VM_R_EGO && !(flags & VM_F_ELBO) && c->n_chunks == 0 &&
-         dense_fast_eligible<K>(c, flags);
+  return c->simple_mode != 0 && c->r_mode == VM_R_EGO && !(flags & VM_F_ELBO) && dense_fast_eligible<K>(c, flags);
 }
 
 // dynamic shared memory of the fast dense kernel (opt-in above 48 KB; set once per process and instantiation)
@@ -2322,15 +2291,9 @@ static cudaError_t fast_setup_all() {
   if constexpr (K <= 4) {  // the fast kernel is only instantiated (and eligible) for K <= 4
     cudaError_t e;
     if ((e = fast_setup<K, true>()) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_dense_fast<K, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)sizeof(FastSmem<K>))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_dense_tma<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(TmaSmem<K>))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_dense_tma<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)sizeof(TmaSmem<K>))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_dense_tma<K, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)sizeof(TmaSmem<K>))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_dense_tma<K, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(TmaSmem<K>))) != cudaSuccess) return e;
     return fast_setup<K, false>();
   } else {
@@ -2338,54 +2301,21 @@ static cudaError_t fast_setup_all() {
   }
 }
 
-template <int K>
-static int launch_special(const vm_ctx* c, int flags, cudaStream_t st, int chunk, int64_t gridx);
-// timing experiment (VM_X_OVERLAP=1|2): the special-tie kernels of a shortcut iteration on the aux stream, next to the
-// dense kernel instead of before it (1: launched before the dense kernel, 2: after it)
-static int vm_x_overlap() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("VM_X_OVERLAP");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-
-static int vm_x_nopatch() {  // VM_X_NOPATCH=1: the fast dense kernel leaves the special ties unpatched (timing experiment)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("VM_X_NOPATCH");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-static int vm_x_notma() {  // VM_X_NOTMA=1: the STG.128 fast dense kernel instead of the TMA one (A/B)
+static bool vm_x_notma() {  // VM_X_NOTMA=1: the STG.128 fast dense kernel instead of the TMA one (A/B measurements)
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("VM_X_NOTMA");
-    v = e ? atoi(e) : 0;
+    v = (e && atoi(e)) ? 1 : 0;
   }
-  return v;
-}
-static int vm_x_tma_mode() {  // VM_X_TMA_MODE: 1 = no patching at all, 3 / 4 = prefetch distance 1 / 3 (timing experiments)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("VM_X_TMA_MODE");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-static int vm_x_persist() {  // VM_X_PERSIST=n: k_shortcut as n persistent CTAs
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("VM_X_PERSIST");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
+  return v != 0;
 }
 
+// `sums_flags` >= 0: the scalar-sum kernels that only depend on the special-tie kernels (k_elbo_b, k_sums_stage1) also go
+// to the aux stream, under the dense kernel; *sums_done tells the caller whether they were launched here.
 template <int K>
-static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, int rtn, int sparse_on_aux = 0) {
+static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, int rtn, int sums_flags = -1,
+                        bool* sums_done = nullptr) {
+  if (sums_done) *sums_done = false;
   if (rtn <= 0) return 0;
   const dim3 grid((unsigned)c->nct, (unsigned)(c->L * rtn));
   const bool elbo = flags & VM_F_ELBO, store = !(flags & VM_F_NO_STORE), csr = c->r_mode == VM_R_CSR;
@@ -2418,19 +2348,19 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, in
   if (side) {
     cudaEventRecord(ev_fork, st);
     cudaStreamWaitEvent(aux, ev_fork, 0);
+    if (sums_flags >= 0) {
+      if ((flags & VM_F_ELBO) && c->mutuality) k_elbo_b<K><<<VM_B_BLOCKS, 256, 0, aux>>>(*c, region_b(c));
+      k_sums_stage1<<<dim3(VM_S1_BLOCKS, (unsigned)c->L), 256, 0, aux>>>(*c, sums_flags, region_u(c), region_s1(c));
+      if (sums_done) *sums_done = true;
+    }
   }
-  if (side && sparse_on_aux == 1) launch_special<K>(c, flags, aux, -1, c->n_ublk);
 #define LF()                                                                                                             \
   do {                                                                                                                   \
     if constexpr (K <= 4) {                                                                                              \
       if (!vm_x_notma()) {                                                                                               \
-        const int xm = vm_x_tma_mode();                                                                                  \
-        if (elbo) k_dense_tma<K, true><<<grid, VM_DENSE_THREADS, sizeof(TmaSmem<K>), st>>>(*c, cp, rt0, rtn, 0);          \
-        else if (xm == 3) k_dense_tma<K, false, 1><<<grid, VM_DENSE_THREADS, sizeof(TmaSmem<K>), st>>>(*c, cp, rt0, rtn, 0); \
-        else if (xm == 4) k_dense_tma<K, false, 3><<<grid, VM_DENSE_THREADS, sizeof(TmaSmem<K>), st>>>(*c, cp, rt0, rtn, 0); \
-        else k_dense_tma<K, false><<<grid, VM_DENSE_THREADS, sizeof(TmaSmem<K>), st>>>(*c, cp, rt0, rtn, xm);             \
+        if (elbo) k_dense_tma<K, true><<<grid, VM_DENSE_THREADS, sizeof(TmaSmem<K>), st>>>(*c, cp, rt0, rtn);             \
+        else k_dense_tma<K, false><<<grid, VM_DENSE_THREADS, sizeof(TmaSmem<K>), st>>>(*c, cp, rt0, rtn);                 \
       } else if (elbo) k_dense_fast<K, true><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<K>), st>>>(*c, cp, rt0, rtn);       \
-      else if (vm_x_nopatch()) k_dense_fast<K, false, false><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<K>), st>>>(*c, cp, rt0, rtn); \
       else k_dense_fast<K, false><<<grid, VM_DENSE_THREADS, sizeof(FastSmem<K>), st>>>(*c, cp, rt0, rtn);                  \
     }                                                                                                                    \
   } while (0)
@@ -2448,7 +2378,6 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, in
 #undef LD
   if (side) {
     LF();
-    if (sparse_on_aux == 2) launch_special<K>(c, flags, aux, -1, c->n_ublk);
     cudaEventRecord(ev_join, aux);
     cudaStreamWaitEvent(st, ev_join, 0);
     if (own_events) {
@@ -2461,23 +2390,35 @@ static int launch_dense(const vm_ctx* c, int flags, cudaStream_t st, int rt0, in
 }
 
 template <int K>
-static int launch_special(const vm_ctx* c, int flags, cudaStream_t st, int chunk, int64_t gridx) {
+static int launch_special(const vm_ctx* c, int flags, cudaStream_t st) {
+  const int64_t gridx = c->n_ublk;
   if (gridx <= 0) return 0;
   const dim3 grid((unsigned)gridx, (unsigned)c->L);
   const bool elbo = flags & VM_F_ELBO;
-#define LS(E, M) k_special<K, E, M><<<grid, 256, 0, st>>>(*c, region_u(c), chunk)
-  if (chunk < 0 && simple_iteration<K>(c, flags)) {
+#define LS(E, M) k_special<K, E, M><<<grid, 256, 0, st>>>(*c, region_u(c))
+  if (simple_iteration<K>(c, flags)) {
     if constexpr (K <= 4) {  // (simple_iteration is never true for larger K)
       // layers that take the shortcut: the special-tie kernel walks the list of the other special ties (its grid covers
       // that list only; k_sums_stage1 reads as many partial slots) while k_shortcut evaluates the shortcut ties
+      // The list-mode launches and k_shortcut touch disjoint ties (and integer atomics): with an aux stream the former
+      // run next to the latter (-4 us per iteration at config 3)
+      cudaStream_t aux = (cudaStream_t)c->aux_stream;
+      cudaEvent_t ev_fork = (cudaEvent_t)c->ev_fork, ev_join = (cudaEvent_t)c->ev_join;
+      const bool split = aux != nullptr && aux != st && ev_fork != nullptr && ev_join != nullptr;
+      cudaStream_t sl = split ? aux : st;
+      if (split) {
+        cudaEventRecord(ev_fork, st);
+        cudaStreamWaitEvent(aux, ev_fork, 0);
+      }
       const dim3 gridl((unsigned)(c->n_cxblk > 0 ? c->n_cxblk : 1), (unsigned)c->L);
-      k_special<K, false, VM_R_EGO, 1><<<gridl, 256, 0, st>>>(*c, region_u(c), chunk);
+      k_special<K, false, VM_R_EGO, 1><<<gridl, 256, 0, sl>>>(*c, region_u(c));
       const dim3 grid2((unsigned)imin64(gridx, 148 * 2), (unsigned)c->L);
-      k_special<K, false, VM_R_EGO, 2><<<grid2, 256, 0, st>>>(*c, region_u(c), chunk);  // layers that cannot
-      if (c->N / DenseCfg<K>::TW > 0) {
-        const int pg = vm_x_persist();
-        if (pg > 0) k_shortcut<K><<<(unsigned)pg, VM_SC_THREADS, 0, st>>>(*c, 1);
-        else k_shortcut<K><<<dim3((unsigned)(c->N / DenseCfg<K>::TW), (unsigned)(c->L * c->nrt)), VM_SC_THREADS, 0, st>>>(*c, 0);
+      k_special<K, false, VM_R_EGO, 2><<<grid2, 256, 0, sl>>>(*c, region_u(c));  // layers that cannot
+      if (c->N / DenseCfg<K>::TW > 0)
+        k_shortcut<K><<<dim3((unsigned)(c->N / DenseCfg<K>::TW), (unsigned)(c->L * c->nrt)), VM_SC_THREADS, 0, st>>>(*c);
+      if (split) {
+        cudaEventRecord(ev_join, aux);
+        cudaStreamWaitEvent(st, ev_join, 0);
       }
     }
   } else if (c->r_mode == VM_R_EGO) {
@@ -2491,50 +2432,14 @@ static int launch_special(const vm_ctx* c, int flags, cudaStream_t st, int chunk
   return 0;
 }
 
-// special-tie kernel + dense kernel of one rho update.  With an aux stream and row chunks, special-tie chunk c+1
-// (latency / issue bound) runs on the aux stream while the dense kernel (HBM-write bound) of chunk c runs on the main one.
+// special-tie kernels, then the dense kernel, of one rho update.  (Running them side by side on two streams was measured
+// twice -- row chunks in round 1, a persistent shortcut kernel next to an unpatched dense kernel in round 2,
+// profiles/r2_dense_experiments.txt -- and lost both times: each wants the registers and warp slots the other holds.)
 template <int K>
-static int launch_rho_kernels(const vm_ctx* c, int flags, cudaStream_t st) {
+static int launch_rho_kernels(const vm_ctx* c, int flags, cudaStream_t st, bool* sums_done) {
   int rc;
-  cudaStream_t aux = (cudaStream_t)c->aux_stream;
-  if (c->n_chunks != VM_NCHUNK || aux == nullptr || aux == st) {
-    if (vm_x_overlap() && aux != nullptr && aux != st && simple_iteration<K>(c, flags))
-      return launch_dense<K>(c, flags, st, 0, (int)c->nrt, vm_x_overlap());
-    if ((rc = launch_special<K>(c, flags, st, -1, c->n_ublk))) return rc;
-    return launch_dense<K>(c, flags, st, 0, (int)c->nrt);
-  }
-  const int64_t rt_end[VM_NCHUNK] = {c->rt_end0, c->rt_end1, c->rt_end2, c->rt_end3};
-  const int64_t sp_grid[VM_NCHUNK] = {c->sp_grid0, c->sp_grid1, c->sp_grid2, c->sp_grid3};
-  cudaEvent_t ev_fork, ev[VM_NCHUNK];
-  cudaError_t e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
-  if (e != cudaSuccess) return (int)e;
-  for (int q = 0; q < VM_NCHUNK; ++q) {
-    e = cudaEventCreateWithFlags(&ev[q], cudaEventDisableTiming);
-    if (e != cudaSuccess) {
-      cudaEventDestroy(ev_fork);
-      for (int p = 0; p < q; ++p) cudaEventDestroy(ev[p]);
-      return (int)e;
-    }
-  }
-  // main stream: special-tie chunks back to back; aux stream (the caller gives it a HIGHER priority): dense chunk q as
-  // soon as special chunk q is done, so that dense CTAs take every slot that frees up and the special-tie kernel of the
-  // next chunk fills the rest
-  rc = 0;
-  for (int q = 0; q < VM_NCHUNK && !rc; ++q) {
-    rc = launch_special<K>(c, flags, st, q, sp_grid[q]);
-    cudaEventRecord(ev[q], st);
-  }
-  for (int q = 0; q < VM_NCHUNK; ++q) {
-    cudaStreamWaitEvent(aux, ev[q], 0);
-    if (rc) continue;
-    const int rt0 = q == 0 ? 0 : (int)rt_end[q - 1];
-    rc = launch_dense<K>(c, flags, aux, rt0, (int)rt_end[q] - rt0);
-  }
-  cudaEventRecord(ev_fork, aux);
-  cudaStreamWaitEvent(st, ev_fork, 0);  // join
-  cudaEventDestroy(ev_fork);  // destruction is deferred by the runtime until the events have completed
-  for (int q = 0; q < VM_NCHUNK; ++q) cudaEventDestroy(ev[q]);
-  return rc;
+  if ((rc = launch_special<K>(c, flags, st))) return rc;
+  return launch_dense<K>(c, flags, st, 0, (int)c->nrt, flags | (simple_iteration<K>(c, flags) ? VM_F_LISTED : 0), sums_done);
 }
 
 template <int K>
@@ -2644,20 +2549,23 @@ static int tu_phase_rho(const vm_ctx* c, int flags, void* stream) {
     DISPATCH_K(c->K, (k_tables<K><<<(unsigned)cdiv(c->L * c->N, 256), 256, 0, st>>>(*c)));
     VM_CHECK_LAUNCH();
   }
-  DISPATCH_K(c->K, rc = launch_rho_kernels<K>(c, flags, st));
+  bool sums_done = false;
+  DISPATCH_K(c->K, rc = launch_rho_kernels<K>(c, flags, st, &sums_done));
   if (rc) return rc;
   VM_CHECK_LAUNCH();
   DISPATCH_K(c->K, launch_stats<K>(c, 0, st));
   VM_CHECK_LAUNCH();
-  if ((flags & VM_F_ELBO) && c->mutuality) {
-    DISPATCH_K(c->K, (k_elbo_b<K><<<VM_B_BLOCKS, 256, 0, st>>>(*c, region_b(c))));
+  if (!sums_done) {
+    if ((flags & VM_F_ELBO) && c->mutuality) {
+      DISPATCH_K(c->K, (k_elbo_b<K><<<VM_B_BLOCKS, 256, 0, st>>>(*c, region_b(c))));
+      VM_CHECK_LAUNCH();
+    }
+    bool listed = false;
+    DISPATCH_K(c->K, listed = simple_iteration<K>(c, flags));
+    k_sums_stage1<<<dim3(VM_S1_BLOCKS, (unsigned)c->L), 256, 0, st>>>(*c, flags | (listed ? VM_F_LISTED : 0), region_u(c),
+                                                                      region_s1(c));
     VM_CHECK_LAUNCH();
   }
-  bool listed = false;
-  DISPATCH_K(c->K, listed = simple_iteration<K>(c, flags));
-  k_sums_stage1<<<dim3(VM_S1_BLOCKS, (unsigned)c->L), 256, 0, st>>>(*c, flags | (listed ? VM_F_LISTED : 0), region_u(c),
-                                                                    region_s1(c));
-  VM_CHECK_LAUNCH();
   k_sums_reduce<<<1, 256, 0, st>>>(*c, flags, region_s1(c), region_cat(c), n_catpart(c), region_b(c),
                                    c->mutuality ? VM_B_BLOCKS : 0);
   VM_CHECK_LAUNCH();

@@ -344,6 +344,7 @@ class VimureModel(TransformerMixin, BaseEstimator):
                         trace.append((r, self.seed, it - 1, elbo, runtime, reached))
                 self.n_iter_ = it - 1
                 self.timings["cavi_loop"] = self.timings.get("cavi_loop", 0.0) + time.time() - t_loop
+                self.timings["graph_capture"] = getattr(eng, "capture_s", 0.0)  # (part of cavi_loop)
                 t1 = time.time()
                 self._fetch_params()
                 if maxL < elbo:
