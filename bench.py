@@ -598,9 +598,13 @@ def run_workload(args, config, N, L, K, steps, warmup, dist, world, rank, dev, d
     except Exception:
         pass
     shortcut = bool(eng.simple_mode)
-    kname = ("k_dense_fast<K=%d,ELBO=false,SIMPLE=%s>" % (K, "true" if shortcut else "false")) if P.N >= P.tile_w and K <= 4 \
-        and P.r_mode != 2 else "k_dense<K=%d>" % K
-    roofline = {"bound": "hbm", "kernel": kname + " (+ k_dense on the aux stream for the partial last column tile)",
+    lcs = eng.layer_consts.cpu().numpy().reshape(L, 3 * K + 5)
+    all32 = bool(getattr(eng, "all32_mode", False))
+    fp32_layers = int((lcs[:, 2 * K + 4] == 1.0).sum()) if (eng.simple_mode or all32) else 0
+    fast = P.N >= P.tile_w and K <= 4 and P.r_mode != 2 and (P.N * K) % 4 == 0
+    tma = os.environ.get("VM_X_NOTMA") != "1"
+    kname = (("k_dense_tma<K=%d,ELBO=false>" if tma else "k_dense_fast<K=%d,ELBO=false>") % K) if fast else "k_dense<K=%d>" % K
+    roofline = {"bound": "hbm", "kernel": kname + (" (+ k_dense on the aux stream for the partial last column tile)" if fast else ""),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch "
                                   "(profiles/dense_traffic.json)" if traffic else None,
@@ -666,7 +670,8 @@ def run_workload(args, config, N, L, K, steps, warmup, dist, world, rank, dev, d
             "elbo_final": elbo_final, "launches": launches, "dense_ms": dense_ms, "ms_nostore": ms_nostore,
             "roofline": roofline, "roofline_step": roofline_step, "e2e": e2e, "clocks": clk.summary(), "pack_s": pack_s,
             "generate_s": sh.gen_s, "generator": sh.generator, "M": M, "slab_gb_per_gpu": alg_bytes / 1e9,
-            "shortcut_ties": shortcut, "nloc": sh.nloc}
+            "shortcut_ties": shortcut, "nloc": sh.nloc, "fp32_layers": fp32_layers,
+            "all32": all32}
 
 
 def run_ours(args):
@@ -724,7 +729,8 @@ def run_ours(args):
                        "generator": main["generator"],
                        "l2": "per-iteration output (%.1f GB slab per GPU) exceeds L2" % main["slab_gb_per_gpu"],
                        "elbo_cadence": "iter 1, every 10th, last (inside the timed region)",
-                       "shortcut_ties_in_dense_kernel": main["shortcut_ties"]},
+                       "shortcut_ties_kernel": main["shortcut_ties"], "fp32_special_tie_kernel_all_mask": main["all32"],
+                       "layers_on_the_fp32_special_tie_path": main["fp32_layers"]},
             "iter_per_s": steps / (ms * 1e-3),
             "reports_per_s": steps * ((2.0 * N - 1) * main["M"] * L if args.config != "c4" else float(N) * N * main["M"] * L) / (ms * 1e-3),
             "elbo_final": main["elbo_final"], "ms_per_step_store_rho_false": main["ms_nostore"],

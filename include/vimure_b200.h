@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VM_ABI_VERSION 14
+#define VM_ABI_VERSION 15
 
 /* reporter-mask structure (how R[l,i,j,m] is represented) */
 #define VM_R_EGO 0 /* reporter m == node m reports row m and column m (vimure synthetic.py:1184-1204, _io.py:229-242) */
@@ -151,7 +151,24 @@ typedef struct vm_ctx {
                                -- constant over a fit (built by the host from u_col / u_px / u_pxt and the prior) */
   float* nodetab;           /* [L*N*stride] per node: q_1..q_{K-1} (= -E[theta] d_k), G_theta, E[log theta] log2e, active;
                                stride = 4 floats at K = 2, 8 at K = 3, 4 (written by k_tables) */
-  const double* simple_consts; /* [3] over the shortcut ties: min log(pr_0+EPS); max X; max x^T */
+  const double* simple_consts; /* [3+K] over the shortcut ties: min log(pr_0+EPS); max X; max x^T; min log(pr_k+EPS), k < K */
+  /* ---- all-reporter mask: fp32 evaluation of EVERY special tie on iterations without ELBO (k_all32) ----
+     With the all-reporter mask S is a per-layer constant, most ties carry reports (69 % at config 4) and a tie has
+     several entries, so the work is per ENTRY: the kernel computes each entry's contribution to the log2-odds
+       log2 rho_k/rho_0 = lo_k - S_all (E[lambda_k]-E[lambda_0]) log2e + sum over the tie's entries of dat_k(entry)
+     (dat_k as for a SINGLE tie above, or x (E[log lambda_k]-E[log lambda_0]) log2e for an entry without a reciprocal
+     report) entry-parallel from a shared-memory reporter table, then one thread per tie sums its entries and normalises.
+     Same outputs and block partials as the special-tie kernel, which still runs every special tie in fp64 on ELBO
+     iterations and for layers whose VM_LC_SIMPLE guard (fp32 range, closed-form rows alive) fails.  A tie whose every
+     log-weight lies below the reference's underflow threshold is detected per tie (its log2 weight of category 0 is
+     carried along) and zeroed as the fp64 kernel does.  simple_consts then covers all special ties. */
+  int64_t all32_mode;       /* 1 = enabled (ALL mask, M <= 4096, counts and priors in fp32 range) */
+  int64_t gamma_ts;         /* 1 = the gamma pass walks the TIE-sorted entries (f_*) with per-reporter accumulators in shared
+                               memory instead of the reporter-sorted copies (g_*): with few reporters (all-reporter mask,
+                               M <= 256) every reporter's entries are spread over all ties, so the reporter-sorted pass reads
+                               a whole 32-byte sector per 8-byte posterior (7.8 GB per pass at config 4 instead of 2.6) */
+  const float* u_lo;        /* [U*K] per special tie: log2(pr_0+EPS), then lo_k = log2((pr_k+EPS)/(pr_0+EPS)), k = 1..K-1
+                               (built by the host; the first value only serves the complete-underflow check) */
   int64_t* fixP;            /* [L*K] fixed point 2^-30: sum over the simple ties of rho_k X (their part of phi0) */
 
   /* ---- X entries, sorted by tie ---- */

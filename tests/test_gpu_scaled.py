@@ -92,6 +92,67 @@ def test_config4_scaled_dense_reporting():
     _compare(eng, o, 4)
 
 
+@pytest.mark.parametrize("case", ["k2_m16", "k3_m40_nomut_layer"])
+def test_all_reporter_mask_fp32_special_ties(case, monkeypatch):
+    """All-reporter mask: on iterations without ELBO every special tie is evaluated in fp32, entry-parallel (k_all32,
+    include/vimure_b200.h: vm_ctx.all32_mode).  Against the oracle (usual tolerances, after runs of such iterations, slab
+    included) and against the same engine on the fp64 special-tie kernel (VM_NO_ALL32=1)."""
+    torch = _cuda()
+    import vimure_b200 as vm
+    import vimure_b200.synthetic as syn
+
+    if case == "k2_m16":
+        L, N, M, K, mut = 2, 300, 16, 2, 0.4
+    else:  # more reporters than a tie group's stage slice would hold per tie is not needed: several entries per tie, K = 3
+        L, N, M, K, mut = 1, 200, 40, 3, 0.5
+    y = syn.StandardSBM(N=N, M=M, L=L, K=K, C=2, avg_degree=8, seed=5)
+    X, theta = syn.dense_reporting_X(y, M=M, mutuality=mut, seed=6)
+
+    class Net:
+        pass
+
+    net = Net()
+    net.X = X
+    mask = vm.masks.AllMask(L, N, M)
+    eng, o, P = _engine_and_oracle(net, mask, {"kind": "all", "dense_input": True}, K)
+    assert eng.all32_mode
+    monkeypatch.setenv("VM_NO_ALL32", "1")
+    ref, _, _ = _engine_and_oracle(net, mask, None, K)
+    assert not ref.all32_mode
+
+    def check(tag):
+        p, q = eng.params(), ref.params()
+        for k in ("gamma_shp", "gamma_rte", "phi_shp", "phi_rte"):
+            np.testing.assert_allclose(p[k], getattr(o, k), rtol=1e-5, err_msg=f"{k} vs oracle {tag}")
+            np.testing.assert_allclose(p[k], q[k], rtol=5e-6, err_msg=f"{k} vs fp64 path {tag}")
+        np.testing.assert_allclose(p["nu_shp"], o.nu_shp, rtol=1e-5, err_msg=tag)
+        np.testing.assert_allclose(p["nu_shp"], q["nu_shp"], rtol=5e-6, err_msg=tag)
+        a = eng.rho_slab().cpu().numpy().astype(np.float64)
+        np.testing.assert_allclose(a, o.rho, rtol=2e-5, atol=1e-30, err_msg=tag)
+        np.testing.assert_allclose(a, ref.rho_slab().cpu().numpy(), rtol=2e-5, atol=1e-30, err_msg=tag)
+
+    for e in (eng, ref):
+        e.iterate(3)  # iterations without ELBO: the fp32 kernel
+    for _ in range(3):
+        o.iterate()
+    lc = eng.layer_consts.cpu().numpy().reshape(L, 3 * K + 5)
+    assert (lc[:, 2 * K + 4] == 1.0).all()  # every layer's guard holds
+    check("after 3 fp32 iterations")
+    for e in (eng, ref):
+        e.iterate(3, elbo_last=True)
+    for _ in range(3):
+        o.iterate()
+    np.testing.assert_allclose(eng.elbo(), o.elbo(), rtol=1e-6)
+    np.testing.assert_allclose(eng.elbo(), ref.elbo(), rtol=1e-7)
+    check("after an ELBO iteration")
+    for e in (eng, ref):
+        e.iterate(2)
+    for _ in range(2):
+        o.iterate()
+    check("fp32 iterations after an ELBO iteration")
+    torch.cuda.synchronize()
+
+
 def test_config5_scaled_gm_l2_k3():
     """config 5 law (Multitensor/GMReciprocity, ego-only, K=3, several layers) at N=640, L=2 (N % 4 == 0: fast kernel)."""
     import vimure_b200.synthetic as syn

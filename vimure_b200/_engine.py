@@ -81,7 +81,13 @@ class CaviEngine:
         stride = 4 if K == 2 else (8 if K <= 6 else K + 2)
         self.nodetab = torch.zeros(L * N * stride if self.simple_mode else 4, **f32)
         self.fixP = torch.zeros(L * K, dtype=torch.int64, device=dev)
-        self.simple_consts = z(3)
+        self.simple_consts = z(3 + K)
+        # all-reporter mask: every special tie in fp32 on iterations without ELBO (k_all32, see the header)
+        import os
+
+        self.all32_mode = bool(P.r_mode == 1 and M <= 4096 and U > 0 and getattr(P, "split_e0", False)
+                               and os.environ.get("VM_NO_ALL32") != "1")
+        self.u_lo = torch.zeros(max(U, 1) * K if self.all32_mode else 1, **f32)
         self.gfpart = z(L * ((M + 255) // 256) * (K + 4))
         # fork/join events of the aux stream, created once (vm_ctx.ev_fork / ev_join)
         self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
@@ -89,7 +95,10 @@ class CaviEngine:
         self._ev_join.record()
         self.cx_logpr = z(max(int(getattr(P, "n_cx", 0)), 1) if self.simple_mode else 1, K)
         assert _packing_const() == self.C["VM_SPECIAL_TIES_PER_BLOCK"]
-        n_blk = max(P.n_gchunk, L * P.n_phichunk * K,
+        # tie-sorted gamma pass (vm_ctx.gamma_ts): few reporters, counts small enough for its 2^-30 fixed point
+        self.gamma_ts = bool(P.r_mode == 1 and M <= 256 and P.I1 > 0 and os.environ.get("VM_NO_GAMMA_TS") != "1"
+                             and float(P.t["f_x"].max()) < 2.0 ** 19)
+        n_blk = max(P.n_gchunk, L * P.n_phichunk * K, (L * P.n_phichunk * M) if self.gamma_ts else 0,
                     L * P.n_ublk * 8 * (3 + 2 * K) + P.nct * L * P.nrt + 128 + 2 * 64 + L * 64 * (3 + K)) + 64
         self.blkpart = z(n_blk)
         self.red1, self.red2 = z(L * M), z(L * K)
@@ -108,6 +117,8 @@ class CaviEngine:
         c.alpha_eta, c.beta_eta = self.alpha_eta, self.beta_eta
         c.b_all = float(P.b_all)
         c.simple_mode = int(self.simple_mode)
+        c.all32_mode = int(self.all32_mode)
+        c.gamma_ts = int(self.gamma_ts)
         c.n_cx = int(getattr(P, "n_cx", U))
         c.n_cxblk = int(getattr(P, "n_cxblk", P.n_ublk))
         # the aux stream carries the general dense kernel (partial column tiles) under the fast one (see launch_dense)
@@ -128,7 +139,7 @@ class CaviEngine:
                      "phi_shp", "phi_rte", "nu", "G_theta", "E_theta", "Elog_theta", "G_lambda", "E_lambda",
                      "Elog_lambda", "GE_theta", "rho_u", "rho_u32", "delta_u", "rho", "layer_consts", "tab_p", "tab_q",
                      "rowpart", "colpart", "er_node", "colsum", "dev_flags", "fixA", "fixG", "phi0", "blkpart", "red1", "red2", "red3",
-                     "elbo_out", "u_rec", "nodetab", "fixP", "simple_consts", "cx_logpr", "gfpart"):
+                     "elbo_out", "u_rec", "nodetab", "fixP", "simple_consts", "cx_logpr", "gfpart", "u_lo"):
             setattr(c, name, ptr(getattr(self, name)))
         c.A = self.red3.data_ptr()  # A aliases the (all-reduced) statistics vector
         c.ev_fork, c.ev_join = self._ev_fork.cuda_event, self._ev_join.cuda_event
@@ -194,6 +205,20 @@ class CaviEngine:
                 self.simple_consts[0] = torch.where(sm, lp[:, 0], big).min().clamp(max=0.0)
                 self.simple_consts[1] = P.t["u_px"].max().to(torch.float64)
                 self.simple_consts[2] = P.t["u_pxt"].abs().max().to(torch.float64)
+                self.simple_consts[3:] = torch.where(sm[:, None], lp, big[:, None]).min(dim=0)[0].clamp(max=0.0)
+            if self.all32_mode:
+                lp = self.u_logpr
+                ulo = self.u_lo.view(P.U, P.K)
+                ulo[:, 0] = (lp[:, 0] * 1.4426950408889634).to(torch.float32)
+                ulo[:, 1:] = ((lp[:, 1:] - lp[:, :1]) * 1.4426950408889634).to(torch.float32)
+                # guard constants over ALL special ties: min log(pr_0+EPS); largest total count of a tie; largest x^T
+                xt = torch.zeros(P.U, dtype=torch.float32, device=self.dev)
+                if P.I:
+                    xt.index_add_(0, P.t["e_u"].to(torch.int64), P.t["e_x"])
+                self.simple_consts[0] = lp[:, 0].min().clamp(max=0.0)
+                self.simple_consts[1] = xt.max().to(torch.float64)
+                self.simple_consts[2] = (P.t["e_xT"].abs().max() if P.I else torch.zeros((), device=self.dev)).to(torch.float64)
+                self.simple_consts[3:] = lp.min(dim=0)[0].clamp(max=0.0)
         st = self._stream()
         _capi.check(self.lib.vm_refresh_cache(self._cref, st), "vm_refresh_cache")
         _capi.check(self.lib.vm_init_stats(self._cref, st), "vm_init_stats")

@@ -28,10 +28,14 @@ def pack(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64,
 
     dev = torch.device(device)
     if dev.type == "cuda" and mask.kind in ("ego", "all") and os.environ.get("VM_PY_PACKER") != "1":
-        return pack_device(X_subs, X_vals, L, N, M, K, mask, dev, row0=row0, nloc=nloc, tile_h=tile_h, mutuality=mutuality,
-                           split_e0=split_e0, simple=simple, single=single)
-    return pack_torch(X_subs, X_vals, L, N, M, K, mask, device, row0=row0, nloc=nloc, tile_h=tile_h, mutuality=mutuality,
-                      split_e0=split_e0, simple=simple, single=single)
+        P = pack_device(X_subs, X_vals, L, N, M, K, mask, dev, row0=row0, nloc=nloc, tile_h=tile_h, mutuality=mutuality,
+                        split_e0=split_e0, simple=simple, single=single)
+    else:
+        P = pack_torch(X_subs, X_vals, L, N, M, K, mask, device, row0=row0, nloc=nloc, tile_h=tile_h, mutuality=mutuality,
+                       split_e0=split_e0, simple=simple, single=single)
+    # (the fp32 paths need the E0 / E1 split's precondition: no prior so small that exp(E[log theta/lambda]) can be 0)
+    P.split_e0 = bool(split_e0 or not mutuality)
+    return P
 
 
 def pack_torch(X_subs, X_vals, L, N, M, K, mask, device, row0=0, nloc=None, tile_h=64, mutuality=True, split_e0=True,

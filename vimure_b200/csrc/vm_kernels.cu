@@ -128,6 +128,85 @@ __global__ void __launch_bounds__(256) k_gamma_reduce(const __grid_constant__ vm
   if (lane == 0) c.red1[lm] = s + c.g0[lm] + (double)c.fixG[lm] * VM_FIX_INV;
 }
 
+// Tie-sorted variant of the gamma pass (vm_ctx.gamma_ts: all-reporter mask, M <= 256).  Grid and chunking of k_phi_partial
+// (blocks of phi_chunk consecutive E1 entries of a layer, sorted by tie: the posterior gather is sequential); the
+// per-reporter sums of a block are accumulated in shared memory, per warp, in FIXED POINT (2^-30; three 20-bit limbs in
+// 32-bit words, so that plain 32-bit shared atomics neither overflow -- a warp adds at most phi_chunk/8 = 512 terms -- nor
+// depend on the order: bit-reproducible).  One partial per (block, reporter); k_gamma_reduce_ts sums them.
+template <int K>
+__global__ void __launch_bounds__(256) k_gamma_partial_ts(const __grid_constant__ vm_ctx c, double* part) {
+  extern __shared__ __align__(16) unsigned char gts_smem[];
+  const int l = blockIdx.y, M = (int)c.M, warp = threadIdx.x >> 5;
+  double* s_Gth = reinterpret_cast<double*>(gts_smem);                     // [M]
+  unsigned int* s_acc = reinterpret_cast<unsigned int*>(s_Gth + M);        // [8][M][3]
+  for (int m = threadIdx.x; m < M; m += 256) s_Gth[m] = c.G_theta[(int64_t)l * M + m];
+  for (int t = threadIdx.x; t < 8 * M * 3; t += 256) s_acc[t] = 0u;
+  __syncthreads();
+  const int64_t s0 = c.lay_eptr[l] + (int64_t)blockIdx.x * c.phi_chunk;
+  const int64_t s1 = min(s0 + c.phi_chunk, c.lay_eptr[l + 1]);
+  const bool mut = c.mutuality != 0;
+  const double Gnu = c.nu[VM_NU_G];
+  double Gl[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) Gl[k] = c.G_lambda[l * K + k];
+  unsigned int* acc = s_acc + (size_t)warp * M * 3;
+  constexpr int NQ = 4;
+  for (int64_t eb = s0 + threadIdx.x; eb < s1; eb += 256 * NQ) {
+    int64_t u[NQ];
+    int m[NQ];
+    float x[NQ], xT[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int64_t e = eb + 256 * q;
+      const bool ok = e < s1;
+      u[q] = ok ? (int64_t)c.f_u[e] : 0;
+      m[q] = ok ? c.f_m[e] : 0;
+      x[q] = ok ? c.f_x[e] : 0.f;
+      xT[q] = ok ? c.f_xT[e] : 0.f;
+    }
+    float r[NQ][K];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) vm_load_rho32<K>(c.rho_u32 + u[q] * K, r[q]);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      double dz1[K], dz2[K];
+      vm_alloc<K>(mut, (double)x[q], (double)xT[q], s_Gth[m[q]], Gl, Gnu, dz1, dz2);  // x == 0 for padding
+      double sv = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) sv += (double)r[q][k] * dz1[k];
+      const unsigned long long v = (unsigned long long)__double2ll_rn(sv * 1073741824.0);  // sv >= 0
+      if (v != 0ull) {
+        unsigned int* a = acc + m[q] * 3;
+        atomicAdd(a, (unsigned int)(v & 0xfffffull));
+        atomicAdd(a + 1, (unsigned int)((v >> 20) & 0xfffffull));
+        const unsigned int hi = (unsigned int)(v >> 40);
+        if (hi) atomicAdd(a + 2, hi);
+      }
+    }
+  }
+  __syncthreads();
+  for (int mm = threadIdx.x; mm < M; mm += 256) {
+    unsigned long long tot = 0ull;
+    for (int w = 0; w < 8; ++w) {
+      const unsigned int* a = s_acc + ((size_t)w * M + mm) * 3;
+      tot += (unsigned long long)a[0] + ((unsigned long long)a[1] << 20) + ((unsigned long long)a[2] << 40);
+    }
+    part[((int64_t)l * c.n_phichunk + blockIdx.x) * M + mm] = (double)tot * (1.0 / 1073741824.0);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_gamma_reduce_ts(const __grid_constant__ vm_ctx c, const double* part) {
+  // one warp per reporter: fixed-order sum of its block partials
+  const int lane = threadIdx.x & 31;
+  const int64_t lm = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (lm >= c.L * c.M) return;
+  const int64_t l = lm / c.M, m = lm - l * c.M;
+  double s = 0.0;
+  for (int64_t q = lane; q < c.n_phichunk; q += 32) s += part[(l * c.n_phichunk + q) * c.M + m];
+  s = warp_sum(s);
+  if (lane == 0) c.red1[lm] = s + c.g0[lm] + (double)c.fixG[lm] * VM_FIX_INV;
+}
+
 // =====================================================================================================
 // phase phi
 // =====================================================================================================
@@ -336,15 +415,21 @@ __global__ void __launch_bounds__(256) k_phi_finish(const __grid_constant__ vm_c
 #pragma unroll
     for (int k = 0; k < K; ++k) lc[VM_LC_G(K, k)] = (Ell[k] - Ell[0]) * VM_LOG2E;
     // shortcut ties (see vm_ctx.simple_mode): evaluated by the fast dense kernel only if
-    //  (i) none of them can underflow completely: the log-weight of k=0 is
-    //      >= min log(pr_0+EPS) - S_max E[lambda_0] + X_max min(0, min E[log theta] + E[log lambda_0])
-    //      (a SINGLE tie's dz1_0 lies in [0, x], so the same bound holds for it), and
+    //  (i) none of them can underflow completely: the log-weight of category k is
+    //      >= min log(pr_k+EPS) - S_max E[lambda_k] + X_max min(0, min E[log theta] + E[log lambda_k])
+    //      (every entry's dz1_k lies in [0, x]), and it is enough that ONE category stays above the threshold, and
     //  (ii) the fp32 Poisson split of the SINGLE ties stays in range: z2 = G_nu x^T and z1 = G_theta G_lambda_k
     //       within [1e-30, 1e30] at their largest / z2 at its smallest (x^T >= 1)
     bool simple_ok = false;
-    if (c.simple_mode && c.r_mode == VM_R_EGO && c.may_dead == 0 && lc[VM_LC_DEAD(K)] == 0.0) {
-      const double lw0 = c.simple_consts[0] - s_max * El[0] + c.simple_consts[1] * fmin(0.0, -nelmax + Ell[0]);
-      simple_ok = lw0 >= VM_DEAD_LN + 8.0;
+    if (((c.simple_mode && c.r_mode == VM_R_EGO) || (c.all32_mode && c.r_mode == VM_R_ALL)) && c.may_dead == 0 &&
+        lc[VM_LC_DEAD(K)] == 0.0) {
+      // (a tie is alive if ANY category's log-weight is: the bound of the most favourable category decides; the
+      // all-reporter kernel checks every tie itself -- with many reporters per tie this bound is far too pessimistic)
+      double lwb = -1e300;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        lwb = fmax(lwb, c.simple_consts[3 + k] - s_max * El[k] + c.simple_consts[1] * fmin(0.0, -nelmax + Ell[k]));
+      simple_ok = c.r_mode == VM_R_ALL || lwb >= VM_DEAD_LN + 8.0;
       if (c.mutuality) {
         const double gnu = c.nu[VM_NU_G];
         double glmax = 0.0;
@@ -1818,6 +1903,238 @@ __global__ void __launch_bounds__(VM_SC_THREADS) k_shortcut(const __grid_constan
   }
 }
 
+// ---- all-reporter mask: every special tie in fp32, entry-parallel (vm_ctx.all32_mode) ---------------------------------
+// Drop-in for k_special<K, false, VM_R_ALL> on iterations without ELBO, for the layers flagged VM_LC_SIMPLE: same grid
+// (n_ublk blocks of VM_SPECIAL_TIES_PER_BLOCK consecutive ties per layer), same per-warp block partials (nu, p0, delta),
+// same rho_u32.  The fp64 kernel is instruction-bound there (config 4: 8.9e7 special ties with 1.8 entries on average,
+// 2.2e9 warp instructions, 19 of 32 lanes active because a warp waits for its tie with the most entries: 4.1 ms,
+// profiles/ncu_r2_c4_special.txt).  Here the work is per ENTRY: for each group of 256 consecutive ties the block's threads
+// stride over the group's (contiguous) entries, each computing its entry's contribution to the log2-odds and to the nu
+// statistic from a shared-memory reporter table -- coalesced 12-byte entry reads, every lane busy -- and stage it in
+// shared memory; then one thread per tie sums its entries' staged values (fixed order), adds the prior and the S term,
+// normalises and accumulates the statistics.  Groups with more entries than the stage holds go through it in slices.
+// log2 rho_k/rho_0 = lo_k - S_all d_k + sum_e dat_k(e): every term O(1..30), fp32 does not cancel (see k_shortcut).
+#define VM_A32_CAP 128  // staged entries per slice and WARP (a warp's 32 consecutive ties have ~58 entries at config 4)
+// floats per staged entry: w_k = dz1_k (K), t_0 = dz1_0 E[log theta] and t_k = (dz1_k - dz1_0) E[log theta] (K),
+// dz2_k (K); padded to 16 bytes
+#define VM_A32_EF(K) ((3 * (K) + 3) / 4 * 4)
+template <int K>
+static inline size_t vm_all32_smem_bytes(int64_t M) {
+  return ((size_t)2 * ((M + 3) / 4 * 4) + (size_t)8 * VM_A32_CAP * VM_A32_EF(K)) * sizeof(float);
+}
+template <int K>
+__global__ void __launch_bounds__(256, (K <= 2) ? 4 : 3) k_all32(const __grid_constant__ vm_ctx c, double* part) {
+  constexpr int EF = VM_A32_EF(K);
+  extern __shared__ __align__(16) float a32_smem[];
+  const int l = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
+  const int M = (int)c.M, Mp = (M + 3) / 4 * 4;
+  float* s_G = a32_smem;        // [Mp] G_theta
+  float* s_El = s_G + Mp;       // [Mp] E[log theta] log2e
+  const int warp = tid >> 5, lane = tid & 31;
+  float* s_ent = s_El + Mp + warp * (VM_A32_CAP * EF);  // this warp's stage [VM_A32_CAP * EF]
+  const double* lc = c.layer_consts + (int64_t)l * VM_LC_STRIDE(K);
+  if (lc[VM_LC_SIMPLE(K)] == 0.0) return;  // the fp64 special-tie kernel (LIST = 2) has this layer
+  const int nloc = (int)c.nloc, nct = (int)c.nct;
+  const int u0 = c.utile_ptr[(int64_t)l * nloc * nct], u1 = c.utile_ptr[(int64_t)(l + 1) * nloc * nct];
+  const bool mut = c.mutuality != 0;
+  for (int m = tid; m < M; m += 256) {
+    const double2 ge = *reinterpret_cast<const double2*>(c.GE_theta + 2 * ((int64_t)l * M + m));
+    s_G[m] = (float)ge.x;
+    s_El[m] = (float)(ge.y * VM_LOG2E);
+  }
+  // Per-layer constants.  Those that multiply a tie's whole count -- E[log lambda_k], -S_all d_k -- stay in fp64 and are
+  // applied once per tie to fp32 sums over its entries: rounded to fp32 they would shift the log-odds of EVERY tie of
+  // the layer the same way (up to 5e-6 for a tie with 20 reports), an error that does not average out in the statistics.
+  float Gl[K], dGl[K];
+  double Ell[K], base[K];
+  const double g0 = c.G_lambda[l * K], S_all = lc[VM_LC_SALL(K)];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    Gl[k] = (float)c.G_lambda[l * K + k];
+    dGl[k] = (float)(c.G_lambda[l * K + k] - g0);
+    Ell[k] = c.Elog_lambda[l * K + k] * VM_LOG2E;
+    base[k] = -S_all * lc[VM_LC_D(K, k)];  // k = 0: the S term of the log2 WEIGHT of category 0 (dead check)
+  }
+  const float Gnu = (float)c.nu[VM_NU_G];
+  // the closed form the dense sweep counts for every tie of this layer (all-reporter mask: one value per layer)
+  double cfv[K];
+  {
+    float a[K], cf[K], epsr;
+    bool dead;
+#pragma unroll
+    for (int k = 0; k < K; ++k) a[k] = __fadd_rn(c.tab_p[((int64_t)l * nloc) * K + k], c.tab_q[((int64_t)l * c.N) * K + k]);
+    vm_formula_rho<K>(a, false, cf, epsr, dead);
+    double fk = 0.0;
+#pragma unroll
+    for (int k = 1; k < K; ++k) fk += (double)cf[k];
+#pragma unroll
+    for (int k = 0; k < K; ++k) cfv[k] = (k == 0) ? 1.0 - fk : (double)cf[k];
+  }
+  double nu_acc = 0.0, dsum[K], p0[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) dsum[k] = p0[k] = 0.0;
+  __syncthreads();
+  // Every warp is autonomous (no block barrier after the tables): it owns 128 consecutive ties of the block, 32 at a time;
+  // the entry range of the NEXT 32 ties is requested before the current ones are processed.
+  constexpr int TPW = VM_SPECIAL_TIES_PER_BLOCK / 8;  // ties per warp
+  const int wbase = u0 + blk * VM_SPECIAL_TIES_PER_BLOCK + warp * TPW;
+  int64_t n_p0 = 0, n_p1 = 0;
+  if (wbase + lane < u1) {
+    n_p0 = c.u_ptr[wbase + lane];
+    n_p1 = c.u_ptr[wbase + lane + 1];
+  }
+#pragma unroll 1
+  for (int it = 0; it < TPW / 32; ++it) {
+    const int gbase = wbase + it * 32;
+    const int ng = max(0, min(32, u1 - gbase));
+    const int64_t p0v = n_p0, p1v = n_p1;
+    if (it + 1 < TPW / 32 && gbase + 32 + lane < u1) {
+      n_p0 = c.u_ptr[gbase + 32 + lane];
+      n_p1 = c.u_ptr[gbase + 32 + lane + 1];
+    }
+    if (ng == 0) break;  // (warp-uniform; nothing follows for this warp)
+    const int64_t e0 = __shfl_sync(0xffffffffu, p0v, 0);
+    const int n_e = (int)(__shfl_sync(0xffffffffu, p1v, ng - 1) - e0);
+    const int qlo = (lane < ng) ? (int)(p0v - e0) : 0, qhi = (lane < ng) ? (int)(p1v - e0) : 0;
+    // per-tie constants of the fit, requested now, used after the entries
+    const int u = gbase + lane;
+    float lo[K], x0s = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) lo[k] = 0.f;
+    if (lane < ng) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) lo[k] = c.u_lo[(int64_t)u * K + k];
+      x0s = c.u_x0sum[u];
+    }
+    // (fp64 accumulators: a tie of this mask can have dozens of entries, and W_k is multiplied by |E[log lambda]| ~ 7)
+    double W[K], T[K], dz[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) W[k] = T[k] = dz[k] = 0.0;
+    for (int sl = 0; sl < n_e; sl += VM_A32_CAP) {
+      const int ns = min(VM_A32_CAP, n_e - sl);
+      // ---- phase 1: one lane per entry of the slice; the loads of two rounds (64 entries: more than a group's usual
+      // 58) are issued together -- the kernel is latency-bound on exactly these loads
+      for (int el0 = lane; el0 < ns; el0 += 64) {
+        int mm[2];
+        float xx[2], xt[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int el = el0 + 32 * h;
+          const bool ok = el < ns;
+          const int64_t e = e0 + sl + (ok ? el : 0);
+          mm[h] = ok ? c.e_m[e] : 0;
+          xx[h] = ok ? c.e_x[e] : 0.f;
+          xt[h] = ok ? c.e_xT[e] : 0.f;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int el = el0 + 32 * h;
+          if (el >= ns) break;
+          const int m = mm[h];
+          const float x = xx[h], xT = xt[h];
+          float o[EF];
+#pragma unroll
+          for (int q = 0; q < EF; ++q) o[q] = 0.f;
+          const float elt = s_El[m];
+          if (mut && xT != 0.f) {
+            const float g = s_G[m];
+            const float z2 = Gnu * xT;
+            float iden[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+              const float z1 = g * Gl[k];
+              iden[k] = vm_rcp(z1 + z2);
+              o[k] = x * (z1 * iden[k]);        // dz1_k = x z1_k / (z1_k + z2)
+              o[2 * K + k] = x * z2 * iden[k];  // dz2_k (model.py:693-696)
+            }
+            // dz1_k - dz1_0 = x z2 G_theta (G_lambda_k - G_lambda_0) / ((z1_k + z2)(z1_0 + z2)): the difference form
+            const float t0 = x * z2 * g * iden[0];
+            o[K] = o[0] * elt;
+#pragma unroll
+            for (int k = 1; k < K; ++k) o[K + k] = (t0 * iden[k] * dGl[k]) * elt;
+          } else {  // no reciprocal report: dz1_k = x for every k, dz2 = 0
+#pragma unroll
+            for (int k = 0; k < K; ++k) o[k] = x;
+            o[K] = x * elt;
+          }
+          float4* dst = reinterpret_cast<float4*>(s_ent + el * EF);
+#pragma unroll
+          for (int q = 0; q < EF / 4; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        }
+      }
+      __syncwarp();
+      // ---- phase 2: one lane per tie sums its entries of the slice (ascending: fixed order)
+      const int qa = max(qlo, sl), qb = min(qhi, sl + ns);
+      for (int q = qa; q < qb; ++q) {
+        const float* v = s_ent + (q - sl) * EF;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          W[k] += (double)v[k];
+          T[k] += (double)v[K + k];
+          dz[k] += (double)v[2 * K + k];
+        }
+      }
+      __syncwarp();
+    }
+    // ---- the tie: softmax with the maximum subtracted, statistics, store
+    if (lane < ng) {
+      // log2 rho_k/rho_0 = lo_k - S_all d_k + T_k + E[log lambda_k] W_k - E[log lambda_0] W_0: the K-1 sums and the
+      // subtraction of the maximum in fp64 (a few operations per tie), so that the exponent that matters reaches ex2 with
+      // full relative precision
+      const double w0 = Ell[0] * W[0];
+      double a[K], amax = 0.0;
+      a[0] = 0.0;
+#pragma unroll
+      for (int k = 1; k < K; ++k) {
+        a[k] = (double)lo[k] + base[k] + T[k] + (Ell[k] * W[k] - w0);
+        amax = fmax(amax, a[k]);
+      }
+      // the largest log2 WEIGHT of the tie: below the reference's underflow threshold the whole row stays 0 (Q3)
+      const bool dead = (double)lo[0] + base[0] + T[0] + w0 + amax < (double)VM_DEAD_LOG2;
+      float es[K], ssum = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        es[k] = vm_ex2((float)(a[k] - amax));
+        ssum += es[k];
+      }
+      const float inv = dead ? 0.f : vm_rcp(ssum);
+      if (dead) {  // (rare) as the fp64 kernel: flag it, and take its E0 entries' x out of the constant g0
+        c.dev_flags[VM_FLAG_DEAD] = 1;
+        for (int64_t e = e0 + qlo; e < e0 + qhi; ++e)
+          if (!mut || c.e_xT[e] == 0.f)
+            atomicAdd(reinterpret_cast<unsigned long long*>(c.fixG) + (int64_t)l * M + c.e_m[e],
+                      (unsigned long long)(-__double2ll_rn((double)c.e_x[e] * VM_FIX_SCALE)));
+      }
+      float rho[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        rho[k] = es[k] * inv;
+        nu_acc += (double)rho[k] * dz[k];
+        p0[k] += (double)(rho[k] * x0s);
+        dsum[k] += (double)rho[k] - cfv[k];
+      }
+      float* ru = c.rho_u32 + (int64_t)u * K;
+      if (K == 2) {
+        *reinterpret_cast<float2*>(ru) = make_float2(rho[0], rho[1]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) ru[k] = rho[k];
+      }
+    }
+  }
+  // per-WARP partials, the layout k_special writes (k_sums_stage1 / k_stats_all read them)
+  const int64_t nup = c.L * c.n_ublk * 8, b = ((int64_t)l * c.n_ublk + blk) * 8 + warp;
+  double v = warp_sum(nu_acc);
+  if (lane == 0) part[UP_NU * nup + b] = v;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    v = warp_sum(p0[k]);
+    if (lane == 0) part[(UP_P0(K) + k) * nup + b] = v;
+    v = warp_sum(dsum[k]);
+    if (lane == 0) part[(UP_DELTA + k) * nup + b] = v;
+  }
+}
+
 // ---- statistics of the new rho: A[l,m,k] = sum of rho_k over the ties reported by (l,m) ------------------------
 // column partials of the dense kernel summed over the row tiles (coalesced: consecutive threads = consecutive (m,k))
 template <int K>
@@ -2423,6 +2740,12 @@ static int launch_special(const vm_ctx* c, int flags, cudaStream_t st) {
     }
   } else if (c->r_mode == VM_R_EGO) {
     if (elbo) LS(true, VM_R_EGO); else LS(false, VM_R_EGO);
+  } else if (c->r_mode == VM_R_ALL && c->all32_mode != 0 && !elbo) {
+    // layers whose guard holds: every special tie in fp32, entry-parallel; the others: the fp64 kernel (strided grid)
+    const size_t smb = vm_all32_smem_bytes<K>(c->M);
+    k_all32<K><<<grid, 256, smb, st>>>(*c, region_u(c));
+    const dim3 grid2((unsigned)imin64(gridx, 148 * 2), (unsigned)c->L);
+    k_special<K, false, VM_R_ALL, 2><<<grid2, 256, 0, st>>>(*c, region_u(c));
   } else if (c->r_mode == VM_R_ALL) {
     if (elbo) LS(true, VM_R_ALL); else LS(false, VM_R_ALL);
   } else {
@@ -2486,6 +2809,11 @@ static int tu_init_stats(const vm_ctx* c, void* stream) {
     cudaError_t e = cudaSuccess;
     DISPATCH_K(c->K, e = fast_setup_all<K>());
     if (e != cudaSuccess) return (int)e;
+    if (c->all32_mode) {
+      DISPATCH_K(c->K, e = cudaFuncSetAttribute(k_all32<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)vm_all32_smem_bytes<K>(c->M)));
+      if (e != cudaSuccess) return (int)e;
+    }
   }
   if (c->r_mode == VM_R_EGO) {
     cudaMemsetAsync(c->fixA, 0, (size_t)(c->L * c->M * c->K) * sizeof(int64_t), st);
@@ -2517,6 +2845,14 @@ static int tu_phase_gamma(const vm_ctx* c, void* stream) {
   int rc = check_ctx(c);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (c->gamma_ts) {  // tie-sorted pass (few reporters)
+    const size_t smb = (size_t)c->M * sizeof(double) + (size_t)8 * c->M * 3 * sizeof(unsigned int);
+    DISPATCH_K(c->K, (k_gamma_partial_ts<K><<<dim3((unsigned)c->n_phichunk, (unsigned)c->L), 256, smb, st>>>(*c, c->blkpart)));
+    VM_CHECK_LAUNCH();
+    k_gamma_reduce_ts<<<(unsigned)cdiv(c->L * c->M, 8), 256, 0, st>>>(*c, c->blkpart);
+    VM_CHECK_LAUNCH();
+    return 0;
+  }
   if (c->n_gchunk > 0) {
     DISPATCH_K(c->K, (k_gamma_partial<K><<<(unsigned)cdiv(c->n_gchunk, 8), 256, 0, st>>>(*c, c->blkpart)));
     VM_CHECK_LAUNCH();
