@@ -1,4 +1,5 @@
 export VIMURE_B200_LIB=$PWD/vimure_b200/_lib/x/libx.so
-timeout 600 python -m pytest tests -m gpu -x -q -k "all_reporter or dense_reporting or config4" 2>&1 | tail -3
-python bench.py --config c4 --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --no-parity --no-c5 > gpurun_out/r3d_c4.json 2> gpurun_out/r3d_c4.err; echo "c4 rc=$?"
-python tools/show_bench.py gpurun_out/r3d_c4.json
+python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/r3j_bench.json 2> gpurun_out/r3j_bench.err; echo rc=$?
+python tools/show_bench.py gpurun_out/r3j_bench.json
+python -c "
+import json; d=json.loads(open('gpurun_out/r3j_bench.json').read().strip().splitlines()[-1]); print('parity', d['parity']['pass'], 'c5 dense', d['configs']['c5']['roofline']['kernel_ms'], d['configs']['c5']['roofline']['frac'])"
