@@ -248,7 +248,7 @@ typedef struct vm_ctx {
                                [VM_FLAG_FIXNU]: fixed point 2^-30, nu statistic of the SINGLE ties the shortcut kernel evaluated */
   int64_t* fixG;            /* [L*M] fixed-point correction of g0: -x of the E0 entries of special ties that underflowed */
   double* phi0;             /* [L*K] sum over special ties of rho_k * u_x0sum (E0 part of the next phi-shape sums) */
-  int64_t* fixA;            /* [L*M*K] EGO: per-reporter sums of (special - closed form), fixed point 2^-44, accumulated
+  int64_t* fixA;            /* [L*M*K] EGO: per-reporter sums of (special - closed form), fixed point 2^-42, accumulated
                                with integer atomics (order-independent => bit-reproducible); slot k=0 holds only the
                                residual count (live special) - (live closed form) */
   double* gfpart;           /* [L*ceil(M/256)*(K+4)] block partials of k_gamma_finish for k_phi_finish */

@@ -44,9 +44,12 @@ static inline int64_t vm_dense_tile_w_host(int64_t K) {
   if (K < 2 || K > VM_MAX_K) return VM_EINVAL;
   return K <= 2 ? DenseCfg<2>::TW : K == 3 ? DenseCfg<3>::TW : K <= 5 ? DenseCfg<4>::TW : DenseCfg<6>::TW;
 }
-// fixed-point scale of the integer-atomic per-reporter accumulators (2^44: |sum| < 1.3e5 fits, 5.7e-14 resolution)
-#define VM_FIX_SCALE 17592186044416.0
-#define VM_FIX_INV (1.0 / 17592186044416.0)
+// fixed-point scale of the integer-atomic per-reporter accumulators: 2^42, i.e. |sum| < 2^21 = 2.1e6 fits an int64 and the
+// resolution is 2.3e-13.  A reporter of an ego mask has at most 2N special ties, each contributing less than 1 in
+// magnitude, and no slab with N > 4.2e5 fits eight 180 GB GPUs (K = 2, L = 1): the sum cannot overflow at any size the
+// path can run.  (Round 1 used 2^44, which a hub with more than 5.2e5 special ties would have overflowed silently.)
+#define VM_FIX_SCALE 4398046511104.0
+#define VM_FIX_INV (1.0 / 4398046511104.0)
 
 // ------------------------------------------------------------------ special functions (fp64)
 // digamma: recurrence up to x >= 10, then the asymptotic series (truncation error < 1e-16 there).

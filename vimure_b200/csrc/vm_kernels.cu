@@ -1670,8 +1670,8 @@ __global__ void __launch_bounds__(VM_DENSE_THREADS, (K == 2 || K == 4) ? 3 : 2) 
 // store), so every thread keeps VM_SC_UNR ties in flight: their records (one 16/32-byte load each: column, X, +-x^T, lo_k
 // packed per tie in `u_rec`) are requested together before any is evaluated, and the tie -> row-segment map is a byte
 // table in shared memory filled once per CTA instead of a binary search per tie.
-// A fixed-point correction fq (|fq| <= 2^44) is accumulated in shared memory as TWO 32-bit words, fq = hi * 2^22 + lo with
-// lo = the low 22 bits (unsigned) and hi = fq >> 22 (signed, |hi| <= 2^22): a node of a tile receives at most TW = 512
+// A fixed-point correction fq (|fq| <= 2^42) is accumulated in shared memory as TWO 32-bit words, fq = hi * 2^22 + lo with
+// lo = the low 22 bits (unsigned) and hi = fq >> 22 (signed, |hi| <= 2^20): a node of a tile receives at most TW = 512
 // terms, so neither word can overflow (512 * 2^22 = 2^31), the two native 32-bit adds need no carry -- hence no returned
 // value to wait for: a 64-bit shared-memory atomic is a compare-and-swap spin loop (ATOMS.CAST.SPIN.64), and a carry taken
 // from the returned old value exposed the atomic's latency twice per tie and category -- and the sum is exact.
