@@ -1,4 +1,5 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/r3k_bench.json 2> gpurun_out/r3k_bench.err; echo rc=$?
-python tools/show_bench.py gpurun_out/r3k_bench.json
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+export VIMURE_B200_LIB=$PWD/vimure_b200/_lib/x/libx.so
+python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/r3m_bench.json 2> gpurun_out/r3m_bench.err; echo rc=$?
+python tools/show_bench.py gpurun_out/r3m_bench.json
+python -c "
+import json; d=json.loads(open('gpurun_out/r3m_bench.json').read().strip().splitlines()[-1]); print('parity', d['parity']['pass'])"
