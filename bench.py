@@ -629,9 +629,14 @@ def run_workload(args, config, N, L, K, steps, warmup, dist, world, rank, dev, d
 
         barrier()
         # this rank's entries as PINNED host buffers (int32 indices / counts), as the contract asks
-        host = torch.empty((5, sh.subs.shape[1]), dtype=torch.int32, pin_memory=True)
-        host[:4].copy_(sh.subs)
-        host[4].copy_(sh.vals)
+        # (several ranks: only the entries of the rank's OWN rows travel over PCIe; fit(presharded="rows") fetches the
+        # reciprocal entries it needs from their owners, device to device)
+        own_e = (sh.subs[1] >= sh.row0) & (sh.subs[1] < sh.row0 + sh.nloc)
+        e_subs, e_vals = (sh.subs[:, own_e], sh.vals[own_e]) if world > 1 else (sh.subs, sh.vals)
+        host = torch.empty((5, e_subs.shape[1]), dtype=torch.int32, pin_memory=True)
+        host[:4].copy_(e_subs)
+        host[4].copy_(e_vals)
+        del e_subs, e_vals, own_e
         torch.cuda.synchronize(dev)
         hn = host.numpy()
         Xh = sptensor(tuple(hn[d] for d in range(4)), hn[4], shape=(L, N, N, M))
@@ -645,7 +650,7 @@ def run_workload(args, config, N, L, K, steps, warmup, dist, world, rank, dev, d
             barrier()
             t0 = time.time()
             model.fit(Xh, R=sh.R, K=K, seed=1, max_iter=steps, init="fast", graphs=not args.no_graphs,
-                      presharded=world > 1)
+                      presharded="rows" if world > 1 else False)
             d2h = model.gamma_shp.nbytes * 4 + model.phi_shp.nbytes * 4 + 8 * (2 + len(model.trace))
             torch.cuda.synchronize(dev)
             wall = allmax(time.time() - t0)
@@ -665,7 +670,7 @@ def run_workload(args, config, N, L, K, steps, warmup, dist, world, rank, dev, d
                "what": "VimureModel.fit(X = this rank's entries as pinned host COO, R=EgoMask, max_iter=steps%s): H2D + "
                        "pack + CAVI + ELBO + D2H of gamma/phi/nu posteriors; rho stays on the device; `value` = median "
                        "of 3 consecutive complete fits, wall clock, max over ranks"
-                       % (", presharded=True" if world > 1 else "")}
+                       % (', presharded="rows"' if world > 1 else "")}
     return {"N": N, "L": L, "K": K, "ties": T, "nnz_X": nnzX, "special_ties": U_all, "ms": ms, "steps": steps, "value": value,
             "elbo_final": elbo_final, "launches": launches, "dense_ms": dense_ms, "ms_nostore": ms_nostore,
             "roofline": roofline, "roofline_step": roofline_step, "e2e": e2e, "clocks": clk.summary(), "pack_s": pack_s,

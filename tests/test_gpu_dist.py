@@ -98,6 +98,27 @@ def _worker(rank, world, port, ngpu, out):
             res["asym_raises"] = False
         except ValueError:
             res["asym_raises"] = True
+        # 5. sharded ingestion: the whole list on every rank, own rows + reciprocals (presharded=True) and own rows only
+        #    (presharded="rows": the reciprocals come from their owners in one all-to-all) give the same fit
+        from vimure_b200.model import shard_rows
+
+        g = Golden("sbm_n520")
+        X, R = build_inputs(g)
+        s, v = np.stack(X.subs), np.asarray(X.vals)
+        row0, nloc = shard_rows(g.N, world, rank)
+        own = (s[1] >= row0) & (s[1] < row0 + nloc)
+        tr = (s[2] >= row0) & (s[2] < row0 + nloc)
+        fits = {}
+        for tag, sel, ps in (("all", np.ones(len(v), bool), False), ("own+reciprocals", own | tr, True), ("rows", own, "rows")):
+            Xs = vm.sptensor.sptensor(tuple(s[:, sel]), v[sel], shape=X.shape)
+            m = vm.VimureModel(mutuality=True, convergence_tol=0.0)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                m.fit(Xs, R=R, K=g.K, seed=3, max_iter=11, init="fast", presharded=ps)
+            fits[tag] = (m.maxL, m.gamma_shp.copy(), m.phi_rte.copy(), float(m.nu_shp))
+        res["ingestion_modes_agree"] = all(
+            fits[t][0] == fits["all"][0] and np.array_equal(fits[t][1], fits["all"][1]) and
+            np.array_equal(fits[t][2], fits["all"][2]) and fits[t][3] == fits["all"][3] for t in ("own+reciprocals", "rows"))
         res["ok"] = True
     except Exception as e:  # noqa: BLE001
         import traceback
@@ -132,3 +153,4 @@ def test_two_rank_sharded_fit_matches_the_reference():
             assert w == world
             assert err <= 1e-5 and e_elbo <= 1e-6, (rank, name, err, e_elbo)
         assert res["rho_max_equal"] and res["seed_none_agree"] and res["undirected_fast_agree"] and res["asym_raises"], res
+        assert res["ingestion_modes_agree"], res

@@ -18,9 +18,11 @@ Extra, optional `fit` keywords (a superset of the reference's):
                  "fast" (draws only for the ties that need them), or "auto" (reference when L*N*N*K <= 5e7);
     device     : CUDA device (default: current);
     distributed: "auto" | True | False -- shard the ties by node-row blocks over torch.distributed ranks;
-    presharded : (sharded fits) X holds only THIS rank's entries -- every X[l,i,j,m] whose row i is in the rank's block and
-                 every reciprocal X[l,j,i,m] of those -- instead of the whole list on every rank (sharded ingestion: each
-                 rank uploads, sorts and pairs about 2/G of the entries); K must then be given;
+    presharded : (sharded fits) X holds only THIS rank's entries instead of the whole list on every rank (sharded
+                 ingestion); K must then be given.  True: every X[l,i,j,m] whose row i is in the rank's block AND every
+                 reciprocal X[l,j,i,m] of those (each rank uploads, sorts and pairs about 2/G of the entries).
+                 "rows": only the entries of the rank's own rows (1/G of the entries over PCIe); the reciprocal entries a
+                 rank needs come from the rank that owns them, device to device (one all-to-all over NVLink);
     concurrent_realisations: "auto" | True | False -- run the `num_realisations` restarts (model.py:386-437) side by
                  side, one CUDA stream + one state per restart over the shared packed data, instead of one after the
                  other.  Same seeds, same trace, same best restart; "auto" = when an iteration is launch-bound
@@ -248,12 +250,19 @@ class VimureModel(TransformerMixin, BaseEstimator):
             # small that exp(E[log theta/lambda]) can underflow to exactly 0 (then model.py:692 applies): psi(0.01) ~ -100
             split_e0 = (not self.mutuality) or (float(np.min(self.alpha_theta)) >= 0.01 and
                                                 float(np.min(self.alpha_lambda)) >= 0.01)
-            self._packed = P = _packing.pack(self.X.subs, self.X.vals, self.L, self.N, self.M, self.K, self.R, dev,
+            presharded = extra_params.get("presharded", False) if world > 1 else False
+            x_subs, x_vals = self.X.subs, self.X.vals
+            if presharded == "rows":
+                x_subs, x_vals = _exchange_reciprocals(x_subs, x_vals, self.N, world, rank, dev)
+            self._packed = P = _packing.pack(x_subs, x_vals, self.L, self.N, self.M, self.K, self.R, dev,
                                              row0=row0, nloc=nloc, tile_h=int(extra_params.get("tile_h", 128)),
                                              mutuality=self.mutuality, split_e0=split_e0)
             # nu_rte = beta + sum X (model.py:593-595): the packer already summed the counts of the rows it owns
-            self.sumX = float(P.sumX) if (world == 1 and getattr(P, "sumX", None) is not None) else float(self.X.vals.sum())
-            if world > 1 and extra_params.get("presharded", False):
+            if world == 1 and getattr(P, "sumX", None) is not None:
+                self.sumX = float(P.sumX)
+            elif not presharded:
+                self.sumX = float(self.X.vals.sum())
+            if presharded:
                 # the sum of all counts (nu_rte = beta + sum X, model.py:593-595) from the ranks' own rows
                 if "K" not in extra_params or extra_params["K"] is None:
                     raise ValueError("presharded=True needs K (a rank cannot see max(X))")
@@ -781,6 +790,37 @@ def _agree_int(v, dev, op="bcast"):
     else:
         torch.distributed.broadcast(t, src=0)
     return int(t.item())
+
+
+def _exchange_reciprocals(subs, vals, N, world, rank, dev):
+    """Sharded ingestion from the entries of a rank's OWN rows (`presharded="rows"`): the entry X[l,i,j,m] is also needed by
+    the rank that owns row j (it pairs X[l,j,i,m] with it and lists it for the eta part of the ELBO), so every rank sends
+    each of its entries to the owner of its column node -- one variable-size all-to-all, device to device -- and packs
+    its own entries followed by what it received.  Returns (4 index tensors, value tensor), int32, on `dev`."""
+    import torch.distributed as dist
+
+    cols = [torch.as_tensor(np.ascontiguousarray(np.asarray(a).astype(np.int32, copy=False))) for a in (*subs, vals)]
+    own = torch.stack([c.to(dev, non_blocking=True) for c in cols], dim=1)  # (n, 5): l, i, j, m, x
+    bounds = torch.tensor([shard_rows(N, world, r)[0] for r in range(1, world)], dtype=torch.int32, device=dev)
+    dest = torch.bucketize(own[:, 2].contiguous(), bounds, right=True)  # owner of the column node j
+    away = dest != rank
+    d_away = dest[away]
+    order = torch.argsort(d_away, stable=True)
+    send = own[away][order].contiguous()
+    n_send = torch.bincount(d_away, minlength=world).to(torch.int64)
+    if dist.get_backend() == "nccl":
+        n_recv = torch.empty_like(n_send)
+        dist.all_to_all_single(n_recv, n_send)
+        ns, nr = [int(v) for v in n_send.cpu()], [int(v) for v in n_recv.cpu()]
+        recv = torch.empty((sum(nr), 5), dtype=torch.int32, device=dev)
+        dist.all_to_all_single(recv, send, output_split_sizes=nr, input_split_sizes=ns)
+    else:  # gloo (CPU tests, ranks sharing a GPU): gather everything on the host and keep what is addressed to this rank
+        host = (send.cpu(), d_away[order].cpu())
+        parts = [None] * world
+        dist.all_gather_object(parts, host)
+        recv = torch.cat([p_[0][p_[1] == rank] for p_ in parts], dim=0).to(dev)
+    both = torch.cat([own, recv], dim=0)
+    return tuple(both[:, d].contiguous() for d in range(4)), both[:, 4].contiguous()
 
 
 def _agree_float(v, dev):
