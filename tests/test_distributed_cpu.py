@@ -120,3 +120,42 @@ def test_shard_rows_partition():
                 assert cover == list(range(N))
             else:
                 assert sum(n for _, n in cover) == N and all(cover[i][0] + cover[i][1] == cover[i + 1][0] for i in range(W - 1))
+
+
+def _exchange_worker(rank, world, port, name, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vimure_b200.model import _exchange_reciprocals, shard_rows
+
+    g = Golden(name)
+    s, v = g.X_subs, g.X_vals
+    row0, nloc = shard_rows(g.N, world, rank)
+    own = (s[1] >= row0) & (s[1] < row0 + nloc)
+    subs, vals = _exchange_reciprocals(tuple(s[:, own]), v[own], g.N, world, rank, torch.device("cpu"))
+    got = np.stack([t.numpy() for t in (*subs, vals)], axis=1)
+    np.save(out + ".%d.npy" % rank, got)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_ingestion_exchange_of_reciprocal_entries(world, tmp_path):
+    """`fit(presharded="rows")`: from the entries of its own rows every rank must end up with exactly the entries a
+    row-block shard needs -- its own rows plus every entry whose column node it owns -- each once."""
+    from vimure_b200.model import shard_rows
+
+    name = "gm_l2_k3"
+    out = str(tmp_path / "ex")
+    mp.spawn(_exchange_worker, args=(world, _free_port(), name, out), nprocs=world, join=True)
+    g = Golden(name)
+    s, v = g.X_subs, g.X_vals
+    full = np.concatenate([s.T, v[:, None]], axis=1).astype(np.int64)
+    for rank in range(world):
+        row0, nloc = shard_rows(g.N, world, rank)
+        own = (s[1] >= row0) & (s[1] < row0 + nloc)
+        tr = (s[2] >= row0) & (s[2] < row0 + nloc)
+        want = np.concatenate([full[own], full[tr & ~own]], axis=0)
+        got = np.load(out + ".%d.npy" % rank).astype(np.int64)
+        key = lambda a: a[np.lexsort(a.T[::-1])]  # noqa: E731
+        np.testing.assert_array_equal(key(got), key(want))
