@@ -211,7 +211,7 @@ def test_full_size_properties_config3():
 
 @pytest.mark.parametrize("case", ["sbm_k2", "gm_l2_k3", "nomut_k2", "subset_k4"])
 def test_simple_special_ties_in_the_dense_kernel(case, monkeypatch):
-    """On iterations without ELBO the fast dense kernel evaluates the special ties that have no reciprocal report itself
+    """On iterations without ELBO the shortcut kernel (k_shortcut) evaluates the special ties that have no reciprocal report
     (fp32, include/vimure_b200.h: vm_ctx.simple_mode) and the special-tie kernel only walks the others.  Against the
     oracle (the usual tolerances, after runs of such iterations) and against the same engine with the shortcut off."""
     torch = _cuda()
@@ -284,7 +284,7 @@ def test_simple_special_ties_in_the_dense_kernel(case, monkeypatch):
 
 
 def test_shortcut_ties_vs_fp64_path_at_config3_size():
-    """N = 20 000 (config 3): 10 iterations in which the fast dense kernel evaluates the SIMPLE and SINGLE special ties in
+    """N = 20 000 (config 3): 10 iterations in which the shortcut kernel evaluates the SIMPLE and SINGLE special ties in
     fp32 against the same 10 iterations with every special tie in fp64 (VM_NO_SIMPLE=1).  The fp32 table rounding is common
     to all ties of a node, so its effect does not average down with N: this is the size at which it has to be checked."""
     torch = _cuda()

@@ -1,13 +1,17 @@
 // vimure_b200 -- hand-written sm_100a kernels of the CAVI hot path + the extern "C" launcher layer.
 //
 // What runs where (one CAVI iteration = reference `_update_CAVI`, model.py:623-660):
-//   phase gamma : k_gamma_partial -> k_gamma_reduce                       (red1)
+//   phase gamma : k_gamma_partial (reporter-sorted) | k_gamma_partial_ts (tie-sorted, few reporters) -> k_gamma_reduce  (red1)
 //   phase phi   : k_gamma_finish -> k_phi_partial -> k_phi_reduce         (red2)
-//   phase rho   : k_phi_finish -> k_tables -> k_special<K> -> k_dense<K>  (the HBM-bound per-tie kernel)
-//                 -> k_col_reduce -> k_stats_* -> [k_elbo_b] -> k_sums_reduce   (red3)
+//   phase rho   : k_phi_finish -> k_tables
+//                 -> special ties: k_special<K> (fp64; every special tie on ELBO iterations, the non-shortcut ones otherwise)
+//                                  + k_shortcut<K> (ego mask, fp32) | k_all32<K> (all-reporter mask, fp32, entry-parallel)
+//                 -> every tie:    k_dense_tma<K> (TMA bulk stores; the HBM-bound kernel) + k_dense<K> (partial tiles,
+//                                  general masks, dead rows) on the aux stream, k_sums_stage1 / k_elbo_b next to them
+//                 -> k_col_reduce -> k_stats_* -> k_sums_reduce   (red3)
 //   phase finish: [k_elbo_partial] -> k_finish
-// All reductions are two-pass (block partials, then a fixed-order second pass): results are bit-reproducible
-// run to run. No floating-point atomics anywhere.
+// All reductions are two-pass (block partials, then a fixed-order second pass) or integer atomics on fixed-point values:
+// results are bit-reproducible run to run.  No floating-point atomics anywhere.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(256) k_phi_finish(const __grid_constant__ vm_c
     lc[VM_LC_DEAD(K)] = (c.r_mode == VM_R_CSR || lp0 - s_max * El[0] < VM_DEAD_LN + 8.0) ? 1.0 : 0.0;
 #pragma unroll
     for (int k = 0; k < K; ++k) lc[VM_LC_G(K, k)] = (Ell[k] - Ell[0]) * VM_LOG2E;
-    // shortcut ties (see vm_ctx.simple_mode): evaluated by the fast dense kernel only if
+    // shortcut ties (see vm_ctx.simple_mode): evaluated by the fp32 kernels only if
     //  (i) none of them can underflow completely: the log-weight of category k is
     //      >= min log(pr_k+EPS) - S_max E[lambda_k] + X_max min(0, min E[log theta] + E[log lambda_k])
     //      (every entry's dz1_k lies in [0, x]), and it is enough that ONE category stays above the threshold, and
@@ -2429,7 +2433,7 @@ __global__ void __launch_bounds__(256) k_sums_reduce(const __grid_constant__ vm_
   b = block_sum<256>(b, sm);
   if (threadIdx.x == 0) {
     double* ex = c.red3 + c.L * c.M * c.K;
-    // + the SINGLE ties the fast dense kernel evaluated this iteration (0 on every other iteration)
+    // + the SINGLE ties the shortcut kernel evaluated this iteration (0 on every other iteration)
     ex[VM_R3_NU] = nu + ((c.simple_mode && !(flags & VM_F_INIT)) ? (double)c.dev_flags[VM_FLAG_FIXNU] * (1.0 / VM_FIXP_SCALE) : 0.0);
     ex[VM_R3_CAT] = cat;
     ex[VM_R3_T2] = t2;
@@ -2441,7 +2445,7 @@ __global__ void __launch_bounds__(256) k_sums_reduce(const __grid_constant__ vm_
       double v = (threadIdx.x < VM_S1_BLOCKS) ? s1[((int64_t)l * VM_S1_BLOCKS + threadIdx.x) * (3 + K) + 3 + k] : 0.0;
       v = block_sum<256>(v, sm);
       if (threadIdx.x == 0) {
-        // + the simple ties the fast dense kernel evaluated this iteration (0 on every other iteration)
+        // + the simple ties the shortcut kernel evaluated this iteration (0 on every other iteration)
         if (c.simple_mode && !(flags & VM_F_INIT)) v += (double)c.fixP[l * K + k] * (1.0 / VM_FIXP_SCALE);
         c.phi0[l * K + k] = v;
       }
