@@ -162,10 +162,10 @@ typedef struct vm_ctx {
      iterations and for layers whose VM_LC_SIMPLE guard (fp32 range, closed-form rows alive) fails.  A tie whose every
      log-weight lies below the reference's underflow threshold is detected per tie (its log2 weight of category 0 is
      carried along) and zeroed as the fp64 kernel does.  simple_consts then covers all special ties. */
-  int64_t all32_mode;       /* 1 = enabled (ALL mask, M <= 4096, counts and priors in fp32 range) */
+  int64_t all32_mode;       /* 1 = enabled (ALL mask, K <= 4, M <= 4096, counts and priors in fp32 range) */
   int64_t gamma_ts;         /* 1 = the gamma pass walks the TIE-sorted entries (f_*) with per-reporter accumulators in shared
                                memory instead of the reporter-sorted copies (g_*): with few reporters (all-reporter mask,
-                               M <= 256) every reporter's entries are spread over all ties, so the reporter-sorted pass reads
+                               M <= 256, K <= 8) every reporter's entries are spread over all ties, so the reporter-sorted pass reads
                                a whole 32-byte sector per 8-byte posterior (7.8 GB per pass at config 4 instead of 2.6) */
   const float* u_lo;        /* [U*K] per special tie: log2(pr_0+EPS), then lo_k = log2((pr_k+EPS)/(pr_0+EPS)), k = 1..K-1
                                (built by the host; the first value only serves the complete-underflow check) */

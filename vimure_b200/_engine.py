@@ -85,7 +85,7 @@ class CaviEngine:
         # all-reporter mask: every special tie in fp32 on iterations without ELBO (k_all32, see the header)
         import os
 
-        self.all32_mode = bool(P.r_mode == 1 and M <= 4096 and U > 0 and getattr(P, "split_e0", False)
+        self.all32_mode = bool(P.r_mode == 1 and K <= 4 and M <= 4096 and U > 0 and getattr(P, "split_e0", False)
                                and os.environ.get("VM_NO_ALL32") != "1")
         self.u_lo = torch.zeros(max(U, 1) * K if self.all32_mode else 1, **f32)
         self.gfpart = z(L * ((M + 255) // 256) * (K + 4))
@@ -96,7 +96,7 @@ class CaviEngine:
         self.cx_logpr = z(max(int(getattr(P, "n_cx", 0)), 1) if self.simple_mode else 1, K)
         assert _packing_const() == self.C["VM_SPECIAL_TIES_PER_BLOCK"]
         # tie-sorted gamma pass (vm_ctx.gamma_ts): few reporters, counts small enough for its 2^-30 fixed point
-        self.gamma_ts = bool(P.r_mode == 1 and M <= 256 and P.I1 > 0 and os.environ.get("VM_NO_GAMMA_TS") != "1"
+        self.gamma_ts = bool(P.r_mode == 1 and K <= 8 and M <= 256 and P.I1 > 0 and os.environ.get("VM_NO_GAMMA_TS") != "1"
                              and float(P.t["f_x"].max()) < 2.0 ** 19)
         n_blk = max(P.n_gchunk, L * P.n_phichunk * K, (L * P.n_phichunk * M) if self.gamma_ts else 0,
                     L * P.n_ublk * 8 * (3 + 2 * K) + P.nct * L * P.nrt + 128 + 2 * 64 + L * 64 * (3 + K)) + 64
