@@ -29,13 +29,11 @@ def get_optimal_threshold(model):
 
 
 def apply_rho_threshold(model, threshold=None):
-    """Binarise rho_f[..., 1] (reference utils.py:207-217)."""
-    if threshold is None:
-        threshold = get_optimal_threshold(model)
-    Y_rec = np.copy(model.rho_f[:, :, :, 1])
-    Y_rec[Y_rec < threshold] = 0
-    Y_rec[Y_rec >= threshold] = 1
-    return Y_rec
+    """Binarise rho_f[..., 1]: 1.0 where it reaches the threshold, else 0.0 (restated from reference utils.py:207-217;
+    host-side helper -- `VimureModel.get_inferred_model` does this on the device, `vm_infer` mode 1)."""
+    thr = get_optimal_threshold(model) if threshold is None else threshold
+    r1 = np.asarray(model.rho_f)[..., 1]
+    return (r1 >= thr).astype(r1.dtype)
 
 
 def calculate_overall_reciprocity(Y):
